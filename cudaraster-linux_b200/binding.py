@@ -1,0 +1,279 @@
+"""ctypes binding of include/crb200.h and the Python mirror of the reference host API."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+RenderModeFlag_EnableDepth = 1
+RenderModeFlag_EnableLerp = 2
+RenderModeFlag_EnableQuads = 4
+
+
+class CrbError(RuntimeError):
+    """Raised where the reference would call fail() (print + exit)."""
+
+
+class _PipeSpec(ctypes.Structure):
+    _fields_ = [("samplesLog2", ctypes.c_int32), ("vertexStructSize", ctypes.c_int32), ("renderModeFlags", ctypes.c_uint32),
+                ("profilingMode", ctypes.c_int32), ("blendShaderName", ctypes.c_char * 128)]
+
+
+class Atomics(ctypes.Structure):
+    _fields_ = [("numSubtris", ctypes.c_int32), ("numBinEntries", ctypes.c_int32), ("numCoarseItems", ctypes.c_int32),
+                ("numTileEntries", ctypes.c_int32), ("numActiveTiles", ctypes.c_int32), ("overflow", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 2)]
+
+
+class WorkBuffers(ctypes.Structure):
+    _fields_ = [("triSubtris", ctypes.c_void_p), ("triHeader", ctypes.c_void_p), ("triData", ctypes.c_void_p), ("maxSubtris", ctypes.c_int32),
+                ("binQueue", ctypes.c_void_p), ("binStart", ctypes.c_void_p), ("binTotal", ctypes.c_void_p), ("numBins", ctypes.c_int32),
+                ("tileQueue", ctypes.c_void_p), ("tileStart", ctypes.c_void_p), ("tileCount", ctypes.c_void_p), ("numTiles", ctypes.c_int32),
+                ("activeTiles", ctypes.c_void_p)]
+
+
+def library_path():
+    return os.path.join(_HERE, "libcrb200.so")
+
+
+def build_library(verbose=False):
+    """Compiles every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", _HERE, "-j8", "libcrb200.so"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise CrbError("building libcrb200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return library_path()
+
+
+def load_library():
+    """Loads libcrb200.so.  Fails loudly when it is missing: there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise CrbError("libcrb200.so is not built (%s); run __graft_entry__.build() or make -C cudaraster-linux_b200" % path)
+    lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    vp, i32, u32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_float
+    sigs = {
+        "crb_abi_version": (i32, []),
+        "crb_create": (i32, [i32, ctypes.POINTER(vp)]),
+        "crb_destroy": (i32, [vp]),
+        "crb_last_error": (ctypes.c_char_p, [vp]),
+        "crb_set_surfaces": (i32, [vp, vp, vp, i32, i32, i32]),
+        "crb_deferred_clear": (i32, [vp, u32, u32]),
+        "crb_pack_abgr": (u32, [f32, f32, f32, f32]),
+        "crb_encode_clear_depth": (u32, [f32]),
+        "crb_set_pixel_pipe": (i32, [vp, vp]),
+        "crb_set_pixel_pipe_by_name": (i32, [vp, vp, ctypes.c_char_p]),
+        "crb_set_vertex_buffer": (i32, [vp, vp, ctypes.c_size_t]),
+        "crb_set_index_buffer": (i32, [vp, vp, i32]),
+        "crb_set_subviewport": (i32, [vp, i32, i32, i32, i32]),
+        "crb_draw_triangles": (i32, [vp, vp]),
+        "crb_draw_triangles_host": (i32, [vp, vp, ctypes.c_size_t, vp, i32, vp, vp, vp]),
+        "crb_get_stats": (i32, [vp, ctypes.POINTER(f32 * 4)]),
+        "crb_get_counters": (i32, [vp, ctypes.POINTER(Atomics)]),
+        "crb_get_profiling_info": (i32, [vp, ctypes.c_char_p, ctypes.c_size_t]),
+        "crb_get_launch_count": (i32, [vp]),
+        "crb_get_work_buffers": (i32, [vp, ctypes.POINTER(WorkBuffers)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
+                    "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
+                    "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_host", "crb_get_stats", "crb_get_counters",
+                    "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers"]
+
+
+def pipe_name(base, samples_log2, flags, blend="BlendReplace"):
+    """Name of a precompiled pipe variant (csrc/BuiltinPipes.cu)."""
+    return "PixelPipe_%s_s%d_f%d_%s" % (base, samples_log2, flags, blend)
+
+
+class CudaSurface:
+    """Render target (reference: CudaSurface.hpp:36-78): LINEAR device memory, U32 texels,
+    rows = rounded height, row pitch = rounded width * numSamples, MSAA samples of an 8x8 tile
+    stored as numSamples horizontally adjacent 8x8 blocks."""
+    FORMAT_RGBA8 = 0
+    FORMAT_DEPTH32 = 1
+
+    def __init__(self, size, fmt, num_samples=1, device="cuda:0"):
+        import torch
+        w, h = int(size[0]), int(size[1])
+        if min(w, h) <= 0:
+            raise CrbError("CudaSurface: Size must be positive!")
+        if max(w, h) > 2048:
+            raise CrbError("CudaSurface: CR_MAXVIEWPORT_SIZE exceeded!")
+        if fmt not in (0, 1):
+            raise CrbError("CudaSurface: Invalid format!")
+        if num_samples > 8:
+            raise CrbError("CudaSurface: numSamples cannot exceed 8!")
+        if num_samples < 1 or (num_samples & (num_samples - 1)):
+            raise CrbError("CudaSurface: numSamples must be a power of two!")
+        self.size = (w, h)
+        self.rounded_size = ((w + 7) & ~7, (h + 7) & ~7)
+        self.texture_size = (self.rounded_size[0] * num_samples, self.rounded_size[1])
+        self.format = fmt
+        self.num_samples = num_samples
+        self.tensor = torch.zeros((self.texture_size[1], self.texture_size[0]), dtype=torch.int32, device=device)
+
+    def getSize(self):
+        return self.size
+
+    def getRoundedSize(self):
+        return self.rounded_size
+
+    def getTextureSize(self):
+        return self.texture_size
+
+    def getFormat(self):
+        return self.format
+
+    def getNumSamples(self):
+        return self.num_samples
+
+    def getSamplesLog2(self):
+        return self.num_samples.bit_length() - 1
+
+    def numpy(self):
+        return self.tensor.cpu().numpy().view(np.uint32)
+
+
+class CudaRaster:
+    """Python mirror of FW::CudaRaster (reference: CudaRaster.hpp:42-190) over the C ABI."""
+
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise CrbError("CudaRaster: No CUDA-capable devices found!")
+        self.lib = load_library()
+        self.device = device
+        self.torch = torch
+        ctx = ctypes.c_void_p()
+        rc = self.lib.crb_create(device, ctypes.byref(ctx))
+        if rc != 0:
+            raise CrbError("CudaRaster: crb_create failed with status %d (no CPU fallback exists)" % rc)
+        self.ctx = ctx
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.crb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CrbError(self.lib.crb_last_error(self.ctx).decode() or ("status %d" % rc))
+
+    # -- reference API -----------------------------------------------------------------------
+    def setSurfaces(self, color, depth):
+        if color is None and depth is None:
+            self._check(self.lib.crb_set_surfaces(self.ctx, None, None, 0, 0, 1))
+            return
+        if color is None:
+            raise CrbError("CudaRaster: No color buffer specified!")
+        if depth is None:
+            raise CrbError("CudaRaster: No depth buffer specified!")
+        if color.getFormat() != CudaSurface.FORMAT_RGBA8:
+            raise CrbError("CudaRaster: Unsupported color buffer format!")
+        if depth.getFormat() != CudaSurface.FORMAT_DEPTH32:
+            raise CrbError("CudaRaster: Unsupported depth buffer format!")
+        if color.getSize() != depth.getSize():
+            raise CrbError("CudaRaster: Mismatch in size between surfaces!")
+        if color.getNumSamples() != depth.getNumSamples():
+            raise CrbError("CudaRaster: Mismatch in multisampling between surfaces!")
+        self._keep["color"], self._keep["depth"] = color, depth
+        self._check(self.lib.crb_set_surfaces(self.ctx, color.tensor.data_ptr(), depth.tensor.data_ptr(), color.size[0], color.size[1], color.num_samples))
+
+    def deferredClear(self, color=(0.0, 0.0, 0.0, 0.0), depth=1.0):
+        abgr = self.lib.crb_pack_abgr(*[float(c) for c in color])
+        self._check(self.lib.crb_deferred_clear(self.ctx, abgr, self.lib.crb_encode_clear_depth(float(depth))))
+
+    def setPixelPipe(self, module, name):
+        """module: a ctypes.CDLL of a pixel-pipe shared object, or None for the built-in pipes."""
+        handle = None if module is None else ctypes.c_void_p(module._handle)
+        self._check(self.lib.crb_set_pixel_pipe_by_name(self.ctx, handle, name.encode()))
+
+    def setVertexBuffer(self, buf, ofs=0):
+        self._keep["vb"] = buf
+        self._check(self.lib.crb_set_vertex_buffer(self.ctx, buf.data_ptr() + ofs, buf.numel() * buf.element_size() - ofs))
+
+    def setIndexBuffer(self, buf, ofs, num_tris):
+        self._keep["ib"] = buf
+        self._check(self.lib.crb_set_index_buffer(self.ctx, buf.data_ptr() + ofs, int(num_tris)))
+
+    def setSubViewport(self, full_w, full_h, x0, y0):
+        self._check(self.lib.crb_set_subviewport(self.ctx, full_w, full_h, x0, y0))
+
+    def drawTriangles(self, stream=None):
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(self.lib.crb_draw_triangles(self.ctx, ctypes.c_void_p(s)))
+
+    def drawTrianglesHost(self, h_verts, h_idx, num_tris, h_color, h_depth=None, stream=None):
+        """Host-buffer entry: pinned torch CPU tensors in, surfaces out (crb_draw_triangles_host)."""
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(self.lib.crb_draw_triangles_host(
+            self.ctx, h_verts.data_ptr(), h_verts.numel() * h_verts.element_size(), h_idx.data_ptr(), int(num_tris), h_color.data_ptr(),
+            None if h_depth is None else h_depth.data_ptr(), ctypes.c_void_p(s)))
+
+    def getStats(self):
+        out = (ctypes.c_float * 4)()
+        self._check(self.lib.crb_get_stats(self.ctx, ctypes.byref(out)))
+        return {"setupTime": out[0], "binTime": out[1], "coarseTime": out[2], "fineTime": out[3]}
+
+    def getProfilingInfo(self):
+        buf = ctypes.create_string_buffer(2048)
+        self._check(self.lib.crb_get_profiling_info(self.ctx, buf, 2048))
+        return buf.value.decode()
+
+    # -- extras ------------------------------------------------------------------------------
+    def getCounters(self):
+        a = Atomics()
+        self._check(self.lib.crb_get_counters(self.ctx, ctypes.byref(a)))
+        return {k: getattr(a, k) for k, _ in Atomics._fields_ if k != "reserved"}
+
+    def getLaunchCount(self):
+        return self.lib.crb_get_launch_count(self.ctx)
+
+    def _dev_to_numpy(self, ptr, nbytes, dtype):
+        out = self.torch.empty(nbytes, dtype=self.torch.uint8, device="cuda:%d" % self.device)
+        cudart = self.torch.cuda.cudart()
+        rc = cudart.cudaMemcpy(out.data_ptr(), ptr, nbytes, 3)  # device to device
+        if int(rc) != 0:
+            raise CrbError("cudaMemcpy failed: %s" % rc)
+        return out.cpu().numpy().view(dtype)
+
+    def getWorkBuffers(self, num_tris):
+        """Downloads setup output and the bin/tile queues (parity tests)."""
+        wb = WorkBuffers()
+        self._check(self.lib.crb_get_work_buffers(self.ctx, ctypes.byref(wb)))
+        c = self.getCounters()
+        n_sub = min(c["numSubtris"], wb.maxSubtris)
+        res = {"counters": c}
+        res["triSubtris"] = self._dev_to_numpy(wb.triSubtris, max(num_tris, 1), np.uint8)[:num_tris]
+        res["triHeader"] = self._dev_to_numpy(wb.triHeader, max(n_sub, 1) * 16, np.uint32).reshape(-1, 4)[:n_sub]
+        res["triData"] = self._dev_to_numpy(wb.triData, max(n_sub, 1) * 64, np.uint32).reshape(-1, 16)[:n_sub]
+        res["binStart"] = self._dev_to_numpy(wb.binStart, 256 * 4, np.int32)[:wb.numBins]
+        res["binTotal"] = self._dev_to_numpy(wb.binTotal, 256 * 4, np.int32)[:wb.numBins]
+        res["binQueue"] = self._dev_to_numpy(wb.binQueue, max(c["numBinEntries"], 1) * 4, np.int32)[:c["numBinEntries"]]
+        res["tileStart"] = self._dev_to_numpy(wb.tileStart, wb.numTiles * 4, np.int32)
+        res["tileCount"] = self._dev_to_numpy(wb.tileCount, wb.numTiles * 4, np.int32)
+        res["tileQueue"] = self._dev_to_numpy(wb.tileQueue, max(c["numTileEntries"], 1) * 4, np.int32)[:c["numTileEntries"]]
+        res["activeTiles"] = self._dev_to_numpy(wb.activeTiles, max(c["numActiveTiles"], 1) * 4, np.int32)[:c["numActiveTiles"]]
+        return res

@@ -1,0 +1,520 @@
+// Host driver behind the C ABI (include/crb200.h).  B200-native replacement for the reference's
+// CudaRaster host class (src/cudaraster/CudaRaster.cpp:53-363, :508-665): state setters, work-buffer
+// sizing with the same slack / overflow-retry policy, the stage launches bracketed by five CUDA
+// events, counter read-back.  Differences: runtime API on an explicit stream, frame parameters as
+// kernel arguments, linear-memory surfaces, CSR queues instead of segment pools, optional
+// asynchronous operation (the reference blocks on the atomics read-back every frame).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cudaraster/cuda/PrivateDefs.hpp"
+#include "../../include/cudaraster/cuda/Util.cuh"
+
+extern "C" int crb_bin_launches(const crb_frame* f);
+extern "C" int crb_coarse_launches(const crb_frame* f);
+
+namespace {
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    // Grow-only "resizeDiscard" (reference: gpu/Buffer.cpp resizeDiscard): contents are not kept.
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct crb_ctx {
+    int device = 0;
+    int numSMs = 1;
+    std::string err;
+
+    // state (CudaRaster.hpp:69-108)
+    uint32_t* color = nullptr;
+    uint32_t* depth = nullptr;
+    int width = 0, height = 0, numSamples = 1, samplesLog2 = 0;
+    int fullWidth = 0, fullHeight = 0, subX0 = 0, subY0 = 0;
+    bool deferredClear = false;
+    uint32_t clearColor = 0, clearDepth = 0;
+    const void* vertices = nullptr;
+    size_t vertexBytes = 0;
+    const int32_t* indices = nullptr;
+    int numTris = 0;
+    bool hasPipe = false;
+    crb_pipe_desc pipe{};
+    crb_pipe_spec spec{};
+    std::string pipeName;
+
+    // work buffers
+    int maxSubtris = 1, maxBinEntries = 1, maxTileEntries = 1, maxItems = 1;
+    DevBuf triSubtris, triHeader, triData;
+    DevBuf binCountMat, binStart, binTotal, binQueue;
+    DevBuf items, binItemBase, binItemCount, tileCountMat;
+    DevBuf tileQueue, tileStart, tileCount, activeTiles;
+    DevBuf atomics;
+    crb_atomics* hostAtomics = nullptr;  // pinned
+    DevBuf hostVerts, hostIdx;           // device staging for crb_draw_triangles_host
+
+    cudaEvent_t ev[5] = {};
+    crb_frame frame{};
+    crb_atomics lastAtomics{};
+    int launchCount = 0;
+    bool drawn = false;
+};
+
+namespace {
+
+int setError(crb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+int cudaFail(crb_ctx* c, const char* what, cudaError_t e) { return setError(c, CRB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
+
+#define CRB_CUDA(ctx, call)                                        \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cudaFail((ctx), #call, e_);  \
+    } while (0)
+
+int popc8(int v) { return __builtin_popcount((unsigned)v & 0xFF); }
+
+// Fills the frame block and (re)allocates the work buffers for the current capacities.
+int prepareFrame(crb_ctx* c) {
+    crb_frame& f = c->frame;
+    std::memset(&f, 0, sizeof(f));
+    f.numTris = c->numTris;
+    f.vertexStride = c->spec.vertexStructSize;
+    f.vertexBuffer = c->vertices;
+    f.indexBuffer = c->indices;
+
+    f.viewportWidth = c->width;
+    f.viewportHeight = c->height;
+    f.widthPixels = (c->width + CR_TILE_SIZE - 1) & -CR_TILE_SIZE;
+    f.heightPixels = (c->height + CR_TILE_SIZE - 1) & -CR_TILE_SIZE;
+    f.widthTiles = f.widthPixels >> CR_TILE_LOG2;
+    f.heightTiles = f.heightPixels >> CR_TILE_LOG2;
+    f.numTiles = f.widthTiles * f.heightTiles;
+    f.widthBins = (f.widthTiles + CR_BIN_SIZE - 1) >> CR_BIN_LOG2;
+    f.heightBins = (f.heightTiles + CR_BIN_SIZE - 1) >> CR_BIN_LOG2;
+    f.numBins = f.widthBins * f.heightBins;
+    f.samplesLog2 = c->samplesLog2;
+
+    if (c->fullWidth > 0) {
+        // sort-first window: snap in the full-frame grid, shift to this viewport's centre
+        f.fullWidth = c->fullWidth;
+        f.fullHeight = c->fullHeight;
+        f.centerOfsX = c->subX0 * CR_SUBPIXEL_SIZE + c->width * (CR_SUBPIXEL_SIZE / 2) - c->fullWidth * (CR_SUBPIXEL_SIZE / 2);
+        f.centerOfsY = c->subY0 * CR_SUBPIXEL_SIZE + c->height * (CR_SUBPIXEL_SIZE / 2) - c->fullHeight * (CR_SUBPIXEL_SIZE / 2);
+        f.subX0 = c->subX0;
+        f.subY0 = c->subY0;
+        f.clipLoX = (float)(2.0 * c->subX0 / c->fullWidth - 1.0);
+        f.clipHiX = (float)(2.0 * (c->subX0 + c->width) / c->fullWidth - 1.0);
+        f.clipLoY = (float)(2.0 * c->subY0 / c->fullHeight - 1.0);
+        f.clipHiY = (float)(2.0 * (c->subY0 + c->height) / c->fullHeight - 1.0);
+    } else {
+        f.fullWidth = c->width;
+        f.fullHeight = c->height;
+        f.centerOfsX = f.centerOfsY = 0;
+        f.clipLoX = f.clipLoY = -1.0f;
+        f.clipHiX = f.clipHiY = 1.0f;
+    }
+
+    f.deferredClear = c->deferredClear ? 1 : 0;
+    f.clearColor = c->clearColor;
+    f.clearDepth = c->clearDepth;
+    f.colorBuffer = c->color;
+    f.depthBuffer = c->depth;
+    f.surfacePitch = f.widthPixels << c->samplesLog2;
+
+    f.numChunks = (c->numTris + CRB_CHUNK_TRIS - 1) / CRB_CHUNK_TRIS;
+    f.maxSubtris = c->maxSubtris;
+    f.maxBinEntries = c->maxBinEntries;
+    f.maxTileEntries = c->maxTileEntries;
+    f.maxItems = c->maxItems;
+    f.numSMs = c->numSMs;
+
+    CRB_CUDA(c, c->triSubtris.reserve((size_t)c->maxSubtris));
+    CRB_CUDA(c, c->triHeader.reserve((size_t)c->maxSubtris * 16));
+    CRB_CUDA(c, c->triData.reserve((size_t)c->maxSubtris * 64));
+    CRB_CUDA(c, c->binCountMat.reserve((size_t)std::max(1, f.numBins * f.numChunks) * 4));
+    CRB_CUDA(c, c->binStart.reserve(CR_MAXBINS_SQR * 4));
+    CRB_CUDA(c, c->binTotal.reserve(CR_MAXBINS_SQR * 4));
+    CRB_CUDA(c, c->binItemBase.reserve(CR_MAXBINS_SQR * 4));
+    CRB_CUDA(c, c->binItemCount.reserve(CR_MAXBINS_SQR * 4));
+    CRB_CUDA(c, c->binQueue.reserve((size_t)c->maxBinEntries * 4));
+    CRB_CUDA(c, c->items.reserve((size_t)c->maxItems * sizeof(crb_item)));
+    CRB_CUDA(c, c->tileCountMat.reserve((size_t)c->maxItems * CR_BIN_SQR * 4));
+    CRB_CUDA(c, c->tileQueue.reserve((size_t)c->maxTileEntries * 4));
+    CRB_CUDA(c, c->tileStart.reserve(CR_MAXTILES_SQR * 4));
+    CRB_CUDA(c, c->tileCount.reserve(CR_MAXTILES_SQR * 4));
+    CRB_CUDA(c, c->activeTiles.reserve(CR_MAXTILES_SQR * 4));
+
+    f.triSubtris = (uint8_t*)c->triSubtris.ptr;
+    f.triHeader = (uint4*)c->triHeader.ptr;
+    f.triData = (uint4*)c->triData.ptr;
+    f.binCountMat = (int32_t*)c->binCountMat.ptr;
+    f.binStart = (int32_t*)c->binStart.ptr;
+    f.binTotal = (int32_t*)c->binTotal.ptr;
+    f.binQueue = (int32_t*)c->binQueue.ptr;
+    f.items = (crb_item*)c->items.ptr;
+    f.binItemBase = (int32_t*)c->binItemBase.ptr;
+    f.binItemCount = (int32_t*)c->binItemCount.ptr;
+    f.tileCountMat = (int32_t*)c->tileCountMat.ptr;
+    f.tileQueue = (int32_t*)c->tileQueue.ptr;
+    f.tileStart = (int32_t*)c->tileStart.ptr;
+    f.tileCount = (int32_t*)c->tileCount.ptr;
+    f.activeTiles = (int32_t*)c->activeTiles.ptr;
+    f.atomics = (crb_atomics*)c->atomics.ptr;
+    return CRB_OK;
+}
+
+// Enqueues one frame (reference: CudaRaster::launchStages, CudaRaster.cpp:508-665).
+int launchStages(crb_ctx* c, cudaStream_t s) {
+    const crb_frame* f = &c->frame;
+    CRB_CUDA(c, cudaMemsetAsync(c->atomics.ptr, 0, sizeof(crb_atomics), s));
+    CRB_CUDA(c, cudaEventRecord(c->ev[0], s));
+    int rc = c->pipe.triangleSetup(f, s);
+    if (rc != CRB_OK) return setError(c, rc, "CudaRaster: triangleSetup launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    CRB_CUDA(c, cudaEventRecord(c->ev[1], s));
+    rc = c->pipe.binRaster(f, s);
+    if (rc != CRB_OK) return setError(c, rc, "CudaRaster: binRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    CRB_CUDA(c, cudaEventRecord(c->ev[2], s));
+    rc = c->pipe.coarseRaster(f, s);
+    if (rc != CRB_OK) return setError(c, rc, "CudaRaster: coarseRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    CRB_CUDA(c, cudaEventRecord(c->ev[3], s));
+    rc = c->pipe.fineRaster(f, s);
+    if (rc != CRB_OK) return setError(c, rc, "CudaRaster: fineRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    CRB_CUDA(c, cudaEventRecord(c->ev[4], s));
+    c->launchCount += (f->numTris > 0 ? 1 : 0) + crb_bin_launches(f) + crb_coarse_launches(f) + 1;
+    return CRB_OK;
+}
+
+int validateDraw(crb_ctx* c) {
+    // same checks, same order, same messages as CudaRaster::drawTriangles (CudaRaster.cpp:243-260)
+    if (!c->color) return setError(c, CRB_ERR_INVALID, "CudaRaster: Surfaces not set!");
+    if (!c->hasPipe) return setError(c, CRB_ERR_INVALID, "CudaRaster: Pixel pipe not set!");
+    if (!c->vertices) return setError(c, CRB_ERR_INVALID, "CudaRaster: Vertex buffer not set!");
+    if (!c->indices) return setError(c, CRB_ERR_INVALID, "CudaRaster: Index buffer not set!");
+    if (c->spec.samplesLog2 != c->samplesLog2) return setError(c, CRB_ERR_INVALID, "CudaRaster: Mismatch in multisampling between pixel pipe and surface!");
+    if ((c->spec.renderModeFlags & CRB_FLAG_QUADS) != 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: RenderModeFlag_EnableQuads is not supported by the B200 pipeline yet!");
+    return CRB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crb_abi_version(void) { return CRB_ABI_VERSION; }
+
+int crb_create(int device, crb_ctx** out) {
+    if (!out) return CRB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return CRB_ERR_NO_DEVICE;  // "CudaRaster: No CUDA-capable devices found!" -- there is no CPU path
+    }
+    if (device < 0 || device >= count) return CRB_ERR_INVALID;
+    crb_ctx* c = new crb_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    if (prop.major < 10) {  // sm_100a code only
+        delete c;
+        return CRB_ERR_NO_DEVICE;
+    }
+    c->numSMs = prop.multiProcessorCount;
+    for (int i = 0; i < 5; i++)
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    if (c->atomics.reserve(sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    if (cudaMallocHost((void**)&c->hostAtomics, sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    std::memset(c->hostAtomics, 0, sizeof(crb_atomics));
+    *out = c;
+    return CRB_OK;
+}
+
+int crb_destroy(crb_ctx* c) {
+    if (!c) return CRB_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
+                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->atomics, &c->hostVerts, &c->hostIdx};
+    for (DevBuf* b : bufs) b->release();
+    if (c->hostAtomics) cudaFreeHost(c->hostAtomics);
+    for (int i = 0; i < 5; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+    return CRB_OK;
+}
+
+const char* crb_last_error(const crb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int crb_set_surfaces(crb_ctx* c, void* d_color, void* d_depth, int width, int height, int numSamples) {
+    if (!c) return CRB_ERR_INVALID;
+    c->color = (uint32_t*)d_color;
+    c->depth = (uint32_t*)d_depth;
+    if (!d_color && !d_depth) return CRB_OK;
+    // CudaRaster::setSurfaces / CudaSurface::CudaSurface checks and messages
+    if (!d_color) return setError(c, CRB_ERR_INVALID, "CudaRaster: No color buffer specified!");
+    if (!d_depth) return setError(c, CRB_ERR_INVALID, "CudaRaster: No depth buffer specified!");
+    if (std::min(width, height) <= 0) return setError(c, CRB_ERR_INVALID, "CudaSurface: Size must be positive!");
+    if (std::max(width, height) > CR_MAXVIEWPORT_SIZE) return setError(c, CRB_ERR_LIMIT, "CudaSurface: CR_MAXVIEWPORT_SIZE exceeded!");
+    if (numSamples > 8) return setError(c, CRB_ERR_LIMIT, "CudaSurface: numSamples cannot exceed 8!");
+    if (numSamples < 1 || popc8(numSamples) != 1) return setError(c, CRB_ERR_INVALID, "CudaSurface: numSamples must be a power of two!");
+    c->width = width;
+    c->height = height;
+    c->numSamples = numSamples;
+    c->samplesLog2 = popc8(numSamples - 1);
+    return CRB_OK;
+}
+
+int crb_deferred_clear(crb_ctx* c, uint32_t abgr, uint32_t encodedDepth) {
+    if (!c) return CRB_ERR_INVALID;
+    c->deferredClear = true;
+    c->clearColor = abgr;
+    c->clearDepth = encodedDepth;
+    return CRB_OK;
+}
+
+uint32_t crb_pack_abgr(float r, float g, float b, float a) { return FW::Vec4f(r, g, b, a).toABGR(); }
+
+uint32_t crb_encode_clear_depth(float depth) {
+    double d = (double)depth * 4294967296.0;
+    unsigned long long q = d <= 0.0 ? 0ull : (d >= 18446744073709551615.0 ? ~0ull : (unsigned long long)d);
+    return FW::encodeDepth((uint32_t)std::min<unsigned long long>(q, 0xFFFFFFFFull));
+}
+
+int crb_set_pixel_pipe(crb_ctx* c, const crb_pipe_desc* pipe) {
+    if (!c) return CRB_ERR_INVALID;
+    c->hasPipe = false;
+    if (!pipe) return CRB_OK;
+    if (!pipe->spec || !pipe->triangleSetup || !pipe->binRaster || !pipe->coarseRaster || !pipe->fineRaster)
+        return setError(c, CRB_ERR_INVALID, "CudaRaster: Invalid pixel pipe!");
+    c->pipe = *pipe;
+    c->spec = *pipe->spec;
+    c->pipe.spec = &c->spec;
+    c->pipeName = pipe->name ? pipe->name : "";
+    c->pipe.name = c->pipeName.c_str();
+    c->hasPipe = true;
+    return CRB_OK;
+}
+
+int crb_set_pixel_pipe_by_name(crb_ctx* c, void* module, const char* name) {
+    if (!c || !name) return CRB_ERR_INVALID;
+    void* handle = module;
+    if (!handle) {
+        // the pipes compiled into this library
+        Dl_info info;
+        if (dladdr((const void*)&crb_abi_version, &info) && info.dli_fname) handle = dlopen(info.dli_fname, RTLD_NOW | RTLD_NOLOAD);
+        if (!handle) handle = dlopen(nullptr, RTLD_NOW);
+    }
+    const std::string n(name);
+    crb_pipe_desc d{};
+    d.name = name;
+    d.spec = (const crb_pipe_spec*)dlsym(handle, (n + "_spec").c_str());
+    d.triangleSetup = (crb_stage_fn)dlsym(handle, (n + "_triangleSetup").c_str());
+    d.binRaster = (crb_stage_fn)dlsym(handle, (n + "_binRaster").c_str());
+    d.coarseRaster = (crb_stage_fn)dlsym(handle, (n + "_coarseRaster").c_str());
+    d.fineRaster = (crb_stage_fn)dlsym(handle, (n + "_fineRaster").c_str());
+    if (!d.spec || !d.triangleSetup || !d.binRaster || !d.coarseRaster || !d.fineRaster) {
+        c->hasPipe = false;
+        return setError(c, CRB_ERR_INVALID, "CudaRaster: Invalid pixel pipe!");
+    }
+    return crb_set_pixel_pipe(c, &d);
+}
+
+int crb_set_vertex_buffer(crb_ctx* c, const void* d_vertices, size_t bytes) {
+    if (!c) return CRB_ERR_INVALID;
+    c->vertices = d_vertices;
+    c->vertexBytes = bytes;
+    return CRB_OK;
+}
+
+int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
+    if (!c) return CRB_ERR_INVALID;
+    if (numTris < 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: negative triangle count!");
+    c->indices = (const int32_t*)d_indices;
+    c->numTris = numTris;
+    return CRB_OK;
+}
+
+int crb_set_subviewport(crb_ctx* c, int fullWidth, int fullHeight, int x0, int y0) {
+    if (!c) return CRB_ERR_INVALID;
+    if (fullWidth <= 0) {
+        c->fullWidth = c->fullHeight = c->subX0 = c->subY0 = 0;
+        return CRB_OK;
+    }
+    if (fullHeight <= 0 || x0 < 0 || y0 < 0 || (x0 & 7) || (y0 & 7)) return setError(c, CRB_ERR_INVALID, "CudaRaster: sub-viewport origin must be a non-negative multiple of 8!");
+    c->fullWidth = fullWidth;
+    c->fullHeight = fullHeight;
+    c->subX0 = x0;
+    c->subY0 = y0;
+    return CRB_OK;
+}
+
+int crb_draw_triangles(crb_ctx* c, void* stream) {
+    if (!c) return CRB_ERR_INVALID;
+    int rc = validateDraw(c);
+    if (rc != CRB_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CUDA(c, cudaSetDevice(c->device));
+    if (c->fullWidth > 0 && (c->subX0 + c->width > c->fullWidth || c->subY0 + c->height > c->fullHeight))
+        return setError(c, CRB_ERR_INVALID, "CudaRaster: sub-viewport exceeds the full frame!");
+
+    // Initial capacities: the reference's slack for sub-triangles (CudaRaster.cpp:239-241, :264-275);
+    // queue capacities are estimates that the retry loop corrects once per scene.
+    const int numTris = c->numTris;
+    const int numTilesEst = (((c->width + 7) >> 3) * ((c->height + 7) >> 3));
+    c->maxSubtris = std::max(c->maxSubtris, numTris + 4096);
+    c->maxBinEntries = std::max(c->maxBinEntries, numTris + numTris / 4 + 16384);
+    c->maxTileEntries = std::max(c->maxTileEntries, std::max(numTilesEst, numTris * 2) + 65536);
+    c->launchCount = 0;
+
+    for (int attempt = 0;; attempt++) {
+        if (c->maxSubtris > CR_MAXSUBTRIS_SIZE) return setError(c, CRB_ERR_LIMIT, "CudaRaster: CR_MAXSUBTRIS_SIZE exceeded!");
+        c->maxItems = c->maxBinEntries / CRB_ITEM_ENTRIES + CR_MAXBINS_SQR + 1;
+        rc = prepareFrame(c);
+        if (rc != CRB_OK) return rc;
+        rc = launchStages(c, s);
+        if (rc != CRB_OK) return rc;
+        // counters back to the host (reference: CudaRaster.cpp:326 -- one blocking round trip per frame)
+        CRB_CUDA(c, cudaMemcpyAsync(c->hostAtomics, c->atomics.ptr, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(c, cudaStreamSynchronize(s));
+        crb_atomics a = *c->hostAtomics;
+        a.numSubtris += numTris;
+        c->lastAtomics = a;
+        if (a.overflow == 0) break;
+        if (attempt > 8) return setError(c, CRB_ERR_LIMIT, "CudaRaster: work buffers keep overflowing (flags %d)", a.overflow);
+        // grow and rerun ALL stages (CudaRaster.cpp:328-338)
+        if (a.overflow & 1) c->maxSubtris = std::max(c->maxSubtris, a.numSubtris + 4096);
+        if (a.overflow & (2 | 8)) c->maxBinEntries = std::max(c->maxBinEntries, a.numBinEntries + a.numBinEntries / 16 + 16384);
+        if (a.overflow & 4) c->maxTileEntries = std::max(c->maxTileEntries, a.numTileEntries + a.numTileEntries / 16 + 65536);
+    }
+    c->deferredClear = false;
+    c->drawn = true;
+    return CRB_OK;
+}
+
+int crb_draw_triangles_host(crb_ctx* c, const void* h_vertices, size_t vertexBytes, const int32_t* h_indices, int numTris, uint32_t* h_color, uint32_t* h_depth,
+                            void* stream) {
+    if (!c) return CRB_ERR_INVALID;
+    if (!c->color) return setError(c, CRB_ERR_INVALID, "CudaRaster: Surfaces not set!");
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CUDA(c, cudaSetDevice(c->device));
+    CRB_CUDA(c, c->hostVerts.reserve(std::max<size_t>(vertexBytes, 16)));
+    CRB_CUDA(c, c->hostIdx.reserve(std::max<size_t>((size_t)numTris * 12, 16)));
+    CRB_CUDA(c, cudaMemcpyAsync(c->hostVerts.ptr, h_vertices, vertexBytes, cudaMemcpyHostToDevice, s));
+    CRB_CUDA(c, cudaMemcpyAsync(c->hostIdx.ptr, h_indices, (size_t)numTris * 12, cudaMemcpyHostToDevice, s));
+    c->vertices = c->hostVerts.ptr;
+    c->vertexBytes = vertexBytes;
+    c->indices = (const int32_t*)c->hostIdx.ptr;
+    c->numTris = numTris;
+    int rc = crb_draw_triangles(c, stream);
+    if (rc != CRB_OK) return rc;
+    const size_t surfBytes = (size_t)c->frame.surfacePitch * c->frame.heightPixels * 4;
+    if (h_color) CRB_CUDA(c, cudaMemcpyAsync(h_color, c->color, surfBytes, cudaMemcpyDeviceToHost, s));
+    if (h_depth) CRB_CUDA(c, cudaMemcpyAsync(h_depth, c->depth, surfBytes, cudaMemcpyDeviceToHost, s));
+    CRB_CUDA(c, cudaStreamSynchronize(s));
+    return CRB_OK;
+}
+
+int crb_get_stats(crb_ctx* c, float out[4]) {
+    if (!c || !out) return CRB_ERR_INVALID;
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    if (!c->drawn) return CRB_OK;
+    CRB_CUDA(c, cudaEventSynchronize(c->ev[4]));
+    for (int i = 0; i < 4; i++) {
+        float ms = 0.0f;
+        CRB_CUDA(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+        out[i] = ms * 1.0e-3f;  // seconds, like CudaRaster::Stats
+    }
+    return CRB_OK;
+}
+
+int crb_get_counters(crb_ctx* c, crb_atomics* out) {
+    if (!c || !out) return CRB_ERR_INVALID;
+    *out = c->lastAtomics;
+    return CRB_OK;
+}
+
+int crb_get_launch_count(crb_ctx* c) { return c ? c->launchCount : 0; }
+
+int crb_get_profiling_info(crb_ctx* c, char* buf, size_t bufSize) {
+    if (!c || !buf || bufSize == 0) return CRB_ERR_INVALID;
+    std::string s("\n");
+    if (!c->hasPipe) s += "Pixel pipe not set!\n";
+    float st[4];
+    int rc = crb_get_stats(c, st);
+    if (rc != CRB_OK) return rc;
+    const crb_atomics& a = c->lastAtomics;
+    const float total = st[0] + st[1] + st[2] + st[3];
+    const float pct = total > 0.0f ? 100.0f / total : 0.0f;
+    char line[256];
+    s += "ProfilingMode_Default\n---------------------\n\n";
+    const char* names[4] = {"triangleSetup", "binRaster", "coarseRaster", "fineRaster"};
+    for (int i = 0; i < 4; i++) {
+        snprintf(line, sizeof(line), "%-16s%.3f ms (%.0f%%)\n", names[i], st[i] * 1.0e3f, st[i] * pct);
+        s += line;
+    }
+    s += "\n";
+    snprintf(line, sizeof(line), "%-16s%-10d(%.1f MB)\n", "numSubtris", a.numSubtris, (float)a.numSubtris * 81.0f / 1048576.0f);
+    s += line;
+    snprintf(line, sizeof(line), "%-16s%-10d(%.1f MB)\n", "numBinEntries", a.numBinEntries, (float)a.numBinEntries * 4.0f / 1048576.0f);
+    s += line;
+    snprintf(line, sizeof(line), "%-16s%-10d(%.1f MB)\n", "numTileEntries", a.numTileEntries, (float)a.numTileEntries * 4.0f / 1048576.0f);
+    s += line;
+    snprintf(line, sizeof(line), "%-16s%-10d\n", "numActiveTiles", a.numActiveTiles);
+    s += line;
+    s += "\n";
+    snprintf(buf, bufSize, "%s", s.c_str());
+    return CRB_OK;
+}
+
+int crb_get_work_buffers(crb_ctx* c, crb_work_buffers* out) {
+    if (!c || !out) return CRB_ERR_INVALID;
+    const crb_frame& f = c->frame;
+    out->triSubtris = f.triSubtris;
+    out->triHeader = f.triHeader;
+    out->triData = f.triData;
+    out->maxSubtris = f.maxSubtris;
+    out->binQueue = f.binQueue;
+    out->binStart = f.binStart;
+    out->binTotal = f.binTotal;
+    out->numBins = f.numBins;
+    out->tileQueue = f.tileQueue;
+    out->tileStart = f.tileStart;
+    out->tileCount = f.tileCount;
+    out->numTiles = f.numTiles;
+    out->activeTiles = f.activeTiles;
+    return CRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+/* crb200.h -- C ABI of the B200-native CudaRaster pipeline (libcrb200.so).
+ *
+ * Drop-in boundary for the hot path of tcoppex/cudaraster-linux:
+ *   FW::CudaRaster::drawTriangles() -> triangleSetup -> binRaster -> coarseRaster -> fineRaster
+ *   (reference: src/cudaraster/CudaRaster.cpp:237-342, :508-665).
+ * Every entry point cites the reference interface it replaces.  Plain pointers and sizes only;
+ * all functions return 0 on success or a non-zero crb_status (the C++ shim in
+ * include/cudaraster/CudaRaster.hpp turns non-zero into the reference's fail() convention,
+ * src/framework/base/Defs.hpp:107-117).  There is no CPU fallback: without a CUDA device
+ * crb_create() fails.
+ */
+#ifndef CRB200_H_
+#define CRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRB_ABI_VERSION 1
+
+typedef enum crb_status {
+    CRB_OK = 0,
+    CRB_ERR_INVALID = 1,      /* bad argument / state (message in crb_last_error) */
+    CRB_ERR_CUDA = 2,         /* a CUDA runtime call failed                         */
+    CRB_ERR_NO_DEVICE = 3,    /* no CUDA device: the product has no CPU path        */
+    CRB_ERR_LIMIT = 4         /* a format limit was exceeded (CR_MAXSUBTRIS_SIZE...) */
+} crb_status;
+
+/* Render-mode flags: cuda/PixelPipe.hpp:30-35. */
+enum { CRB_FLAG_DEPTH = 1, CRB_FLAG_LERP = 2, CRB_FLAG_QUADS = 4 };
+
+/* Format limits: cuda/Constants.hpp:21-39. */
+enum {
+    CRB_MAX_VIEWPORT = 2048,
+    CRB_MAX_SAMPLES = 8,
+    CRB_MAX_SUBTRIS = 1 << 24,
+    CRB_TILE_SIZE = 8,
+    CRB_BIN_TILES = 16
+};
+
+typedef struct crb_ctx crb_ctx;
+
+/* == PixelPipeSpec, cuda/PrivateDefs.hpp:147-154 (same field order and sizes). */
+typedef struct crb_pipe_spec {
+    int32_t samplesLog2;
+    int32_t vertexStructSize;
+    uint32_t renderModeFlags;
+    int32_t profilingMode;
+    char blendShaderName[128];
+} crb_pipe_spec;
+
+/* == CRAtomics, cuda/PrivateDefs.hpp:123-143, extended with the counters of the new
+ * count/scan/scatter binning (the segment counters of the reference do not exist here). */
+typedef struct crb_atomics {
+    int32_t numSubtris;        /* starts at numTris; += n for every triangle clipped into n>=2  */
+    int32_t numBinEntries;     /* triangle-bin pairs written to the bin queue                  */
+    int32_t numCoarseItems;    /* work items the coarse stage processed                        */
+    int32_t numTileEntries;    /* triangle-tile pairs written to the tile queue                */
+    int32_t numActiveTiles;    /* tiles the fine stage touches                                 */
+    int32_t overflow;          /* bit0 subtris, bit1 bin queue, bit2 tile queue, bit3 items    */
+    int32_t reserved[2];
+} crb_atomics;
+
+/* Everything a stage launcher needs; filled by crb_draw_triangles().  Opaque to C callers,
+ * defined in include/cudaraster/cuda/PrivateDefs.hpp for pixel-pipe translation units. */
+typedef struct crb_frame crb_frame;
+
+/* A stage launcher enqueues one stage on `stream` (a cudaStream_t) and returns a crb_status.
+ * The four launchers of a pipe replace the four kernels CR_DEFINE_PIXEL_PIPE emits
+ * (cuda/PixelPipe.inl:241-275) and are found by the same string names
+ * (<pipe>_triangleSetup ... <pipe>_fineRaster, <pipe>_spec; CudaRaster.cpp:190-201). */
+typedef int (*crb_stage_fn)(const crb_frame* frame, void* stream);
+
+typedef struct crb_pipe_desc {
+    const char* name;
+    const crb_pipe_spec* spec;
+    crb_stage_fn triangleSetup;
+    crb_stage_fn binRaster;
+    crb_stage_fn coarseRaster;
+    crb_stage_fn fineRaster;
+} crb_pipe_desc;
+
+/* ---- lifetime: CudaRaster::CudaRaster/init/~CudaRaster, CudaRaster.cpp:53-128 ---------------- */
+int crb_abi_version(void);
+int crb_create(int device, crb_ctx** out);
+int crb_destroy(crb_ctx* ctx);
+const char* crb_last_error(const crb_ctx* ctx);
+
+/* ---- state setters ---------------------------------------------------------------------------
+ * crb_set_surfaces: CudaRaster::setSurfaces (CudaRaster.cpp:132-170) + CudaSurface
+ * (CudaSurface.cpp:39-91).  Surfaces are LINEAR device memory, U32 texels,
+ * row pitch = roundedWidth * numSamples texels, rows = roundedHeight (rounded = up to a
+ * multiple of 8).  Sample i of pixel (x,y) lives at texel ((x>>3)*8*N + i*8 + (x&7), y), the
+ * reference's horizontally tile-replicated MSAA layout (FineRaster.inl:909, :1088-1100).
+ * Colour texel = 0xAABBGGRR, depth texel = raw encoded U32.  Row 0 is the bottom scanline. */
+int crb_set_surfaces(crb_ctx* ctx, void* d_color, void* d_depth, int width, int height, int numSamples);
+
+/* CudaRaster::deferredClear (CudaRaster.cpp:174-179): clear on the next draw. */
+int crb_deferred_clear(crb_ctx* ctx, uint32_t abgr, uint32_t encodedDepth);
+/* Vec4f::toABGR (base/Math.cpp:41-48) and the depth encoding of CudaRaster.cpp:178. */
+uint32_t crb_pack_abgr(float r, float g, float b, float a);
+uint32_t crb_encode_clear_depth(float depth);
+
+/* CudaRaster::setPixelPipe (CudaRaster.cpp:183-216).  The _by_name form resolves
+ * "<name>_triangleSetup" ... "<name>_spec" with dlsym in `module` (a dlopen handle of a pixel-pipe
+ * shared object; NULL = the pipes built into libcrb200.so), exactly like
+ * CudaModule::getKernel(name + "_triangleSetup"). */
+int crb_set_pixel_pipe(crb_ctx* ctx, const crb_pipe_desc* pipe);
+int crb_set_pixel_pipe_by_name(crb_ctx* ctx, void* module, const char* name);
+
+/* CudaRaster::setVertexBuffer / setIndexBuffer (CudaRaster.cpp:220-233); device pointers.
+ * Vertices: vertexStructSize bytes each, clipPos (4 x F32) first, then 4 x F32 varyings.
+ * Indices: numTris x int32[3]. */
+int crb_set_vertex_buffer(crb_ctx* ctx, const void* d_vertices, size_t bytes);
+int crb_set_index_buffer(crb_ctx* ctx, const void* d_indices, int numTris);
+
+/* Sort-first sub-viewport (new): this context renders the rectangle
+ * [x0,x0+width) x [y0,y0+height) (multiples of 8) of a fullWidth x fullHeight frame whose
+ * clip space the vertices are expressed in.  width/height must match crb_set_surfaces.
+ * Vertices are snapped once in full-frame subpixels so seams are watertight for any split.
+ * Passing fullWidth = 0 restores the plain single viewport. */
+int crb_set_subviewport(crb_ctx* ctx, int fullWidth, int fullHeight, int x0, int y0);
+
+/* ---- the hot path ----------------------------------------------------------------------------
+ * CudaRaster::drawTriangles (CudaRaster.cpp:237-342): sizes the work buffers, launches the four
+ * stages on `stream` (NULL = default stream), reads the counters back and, if a queue
+ * overflowed, grows the buffers and re-runs the frame, like the reference's retry loop. */
+int crb_draw_triangles(crb_ctx* ctx, void* stream);
+
+/* The same call for HOST buffers (the reference's Buffer class mirrors host memory to the device
+ * on demand, gpu/Buffer.cpp:235-346): uploads vertices + indices, draws with a deferred clear if
+ * one is pending, downloads colour (and depth when h_depth != NULL).  Host pointers should be
+ * pinned for full PCIe rate.  This is the end-to-end entry the benchmark times. */
+int crb_draw_triangles_host(crb_ctx* ctx, const void* h_vertices, size_t vertexBytes, const int32_t* h_indices, int numTris,
+                            uint32_t* h_color, uint32_t* h_depth, void* stream);
+
+/* CudaRaster::getStats (CudaRaster.cpp:346-363): seconds per stage of the last draw
+ * {setup, bin, coarse, fine}.  Synchronizes. */
+int crb_get_stats(crb_ctx* ctx, float outSeconds[4]);
+/* g_crAtomics read-back (CudaRaster.cpp:326). */
+int crb_get_counters(crb_ctx* ctx, crb_atomics* out);
+/* CudaRaster::getProfilingInfo, ProfilingMode_Default report (CudaRaster.cpp:367-422). */
+int crb_get_profiling_info(crb_ctx* ctx, char* buf, size_t bufSize);
+/* Number of kernels the last crb_draw_triangles enqueued (all retries included). */
+int crb_get_launch_count(crb_ctx* ctx);
+
+/* ---- inspection of the work buffers (parity tests; the reference exposes the same data through
+ * its Buffer members and DebugParams, CudaRaster.hpp:53-67, :109-138) ------------------------- */
+typedef struct crb_work_buffers {
+    const uint8_t* triSubtris;   /* [maxSubtris] U8                                    */
+    const void* triHeader;       /* [maxSubtris] 16 B  (cuda/PrivateDefs.hpp:26-36)   */
+    const void* triData;         /* [maxSubtris] 64 B  (cuda/PrivateDefs.hpp:40-62)   */
+    int32_t maxSubtris;
+    const int32_t* binQueue;     /* triIdx*8+sub, grouped by bin, submission order     */
+    const int32_t* binStart;     /* [numBins] first entry of each bin                  */
+    const int32_t* binTotal;     /* [numBins] entries per bin                          */
+    int32_t numBins;
+    const int32_t* tileQueue;    /* triIdx*8+sub, grouped by tile, submission order    */
+    const int32_t* tileStart;    /* [numTiles]                                         */
+    const int32_t* tileCount;    /* [numTiles]                                         */
+    int32_t numTiles;
+    const int32_t* activeTiles;  /* [numActiveTiles]                                   */
+} crb_work_buffers;
+int crb_get_work_buffers(crb_ctx* ctx, crb_work_buffers* out); /* device pointers, valid until the next draw */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRB200_H_ */

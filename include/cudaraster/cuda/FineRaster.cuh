@@ -1,0 +1,282 @@
+// Stage 4 -- fine raster for sm_100a: one warp per 8x8 px tile, every lane OWNS two pixels.
+//
+// Computes what the reference's fineRasterImpl_SingleSample / _MultiSample compute
+// (src/cudaraster/cuda/FineRaster.inl:499-752, :855-1126): exact top-left coverage at the
+// sample positions, U32 plane-equation depth with a strict LESS test, one fragment-shader run per
+// (triangle, pixel) at the pixel centre / MSAA centroid, blend, all in submission order.
+//
+// What is different (DESIGN.md "fine raster"):
+//  * Pixel ownership.  The reference maps 32 *fragments* to lanes and resolves same-pixel
+//    conflicts with racing shared-memory stores whose arbitration was deterministic on Fermi
+//    only.  Here lane l owns pixels l and l+32 of the tile for the whole tile:
+//    fragments of one pixel are applied by one thread in queue order, so the serial rule holds
+//    by construction and the tile colour/depth live in registers, not shared memory.
+//  * Refill: 32 queue entries at a time, one lane per triangle, computes the three edge
+//    equations relative to the tile (exact integer arithmetic, no FP32 LUT) and the tile-relative
+//    depth plane into a 64 B shared-memory record; __ballot_sync picks the live ones.
+//  * Visibility-first shading: when the blend does not read dst and the shader cannot discard,
+//    the loop only tracks (depth, queue position) of the winning fragment per sample and the
+//    shader runs once per covered pixel at the end -- overdraw costs no shading.
+//  * Explicit __syncwarp / __ballot_sync / __shfl_sync everywhere; no volatile-shared tricks.
+#pragma once
+#include "Overlap.cuh"
+#include "PixelPipe.hpp"
+
+namespace FW {
+
+struct FineTriRec {  // 64 B, one per queued triangle of the current batch
+    S32 a0, b0, c0, a1;   // edge i: E(sx, sy) = c_i + a_i*sx + b_i*sy >= 0, (sx, sy) = subpixel
+    S32 b1, c1, a2, b2;   //         offset of the sample from the centre of the tile's pixel (0,0)
+    S32 c2;
+    U32 zx, zy, zb;       // depth = zb + zx*dsx + zy*dsy, (dsx, dsy) = sample offset in sample units
+    S32 dataIdx, triIdx, seq, pad;
+};
+
+// Edge equations of a sub-triangle relative to the sample-space origin (bx, by) given in
+// viewport-centred subpixels.  Exact: the constant is formed in S64 and clamped to +-2^30, which
+// cannot change the sign of E anywhere inside a tile (|a*sx + b*sy| < 2^24 there).
+__device__ __forceinline__ void setupTileEdges(const uint4& h, S32 bx, S32 by, S32 (&a)[3], S32 (&b)[3], S32 (&c)[3]) {
+    const S32 x0 = (S32)(S16)(h.x & 0xFFFF), y0 = (S32)h.x >> 16;
+    const S32 x1 = (S32)(S16)(h.y & 0xFFFF), y1 = (S32)h.y >> 16;
+    const S32 x2 = (S32)(S16)(h.z & 0xFFFF), y2 = (S32)h.z >> 16;
+    const S32 ox[3] = {x0, x1, x0}, oy[3] = {y0, y1, y0};
+    const S32 dx[3] = {x1 - x0, x2 - x1, x0 - x2}, dy[3] = {y1 - y0, y2 - y1, y0 - y2};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        // E(s) = (o.x - s.x)*d.y - (o.y - s.y)*d.x - tie,  s = (bx + sx, by + sy)
+        const S64 tie = (dy[i] > 0 || (dy[i] == 0 && dx[i] <= 0)) ? 1 : 0;
+        S64 e = (S64)(ox[i] - bx) * dy[i] - (S64)(oy[i] - by) * dx[i] - tie;
+        e = max(min(e, (S64)(1 << 30)), -(S64)(1 << 30));
+        c[i] = (S32)e;
+        a[i] = -dy[i];
+        b[i] = dx[i];
+    }
+}
+
+// Perspective-correct barycentrics from the integer w/u/v planes (reference: FineRaster.inl:21-48).
+template <int SamplesLog2>
+__device__ __forceinline__ void computeBarys(Vec3f& bary, Vec3f& baryDX, Vec3f& baryDY, const int3& wp, const int3& up, const int3& vp, int sampleX, int sampleY) {
+    const F32 w = __frcp_rn((F32)(wp.x * sampleX + wp.y * sampleY + wp.z));
+    const F32 u = __fmul_rn(w, (F32)(up.x * sampleX + up.y * sampleY + up.z));
+    const F32 v = __fmul_rn(w, (F32)(vp.x * sampleX + vp.y * sampleY + vp.z));
+    bary = Vec3f(__fsub_rn(__fsub_rn(1.0f, u), v), u, v);
+    const F32 wd = w * (F32)(1 << (SamplesLog2 + 1));
+    const F32 udx = wd * ((F32)up.x - u * (F32)wp.x), udy = wd * ((F32)up.y - u * (F32)wp.y);
+    const F32 vdx = wd * ((F32)vp.x - v * (F32)wp.x), vdy = wd * ((F32)vp.y - v * (F32)wp.y);
+    baryDX = Vec3f(-udx - vdx, udx, vdx);
+    baryDY = Vec3f(-udy - vdy, udy, vdy);
+}
+
+// Fills the shader inputs and runs it (reference: FineRaster.inl:52-119).  centroid = packed
+// half-sample position of the shading point inside the pixel (low nibble x, high nibble y).
+template <class VertexClass, class FragmentShaderClass, int SamplesLog2, U32 RenderModeFlags>
+__device__ __forceinline__ void runFragmentShader(FragmentShaderClass& fs, const crb_frame& f, int triIdx, int dataIdx, int pixelX, int pixelY, U32 centroid) {
+    const uint4 t3 = __ldg(&f.triData[(size_t)dataIdx * 4 + 3]);  // vb, vi0, vi1, vi2
+    fs.m_triIdx = triIdx;
+    fs.m_vertIdx = Vec3i((S32)t3.y, (S32)t3.z, (S32)t3.w);
+    fs.m_pixelPos = Vec2i(pixelX, pixelY);
+    fs.m_vertexBytes = (S32)sizeof(VertexClass);
+    fs.m_vertexBuffer = f.vertexBuffer;
+    fs.m_color = 0xFF0000FFu;
+    fs.m_discard = false;
+    if ((RenderModeFlags & RenderModeFlag_EnableLerp) == 0) {
+        // interpolation off: varyings come from the last vertex
+        fs.m_center = Vec3f(0.0f, 0.0f, 1.0f);
+        fs.m_centerDX = Vec3f(0.0f); fs.m_centerDY = Vec3f(0.0f);
+        fs.m_centroid = Vec3f(0.0f, 0.0f, 1.0f);
+        fs.m_centroidDX = Vec3f(0.0f); fs.m_centroidDY = Vec3f(0.0f);
+    } else {
+        const uint4 t1 = __ldg(&f.triData[(size_t)dataIdx * 4 + 1]);  // wx, wy, wb, ux
+        const uint4 t2 = __ldg(&f.triData[(size_t)dataIdx * 4 + 2]);  // uy, ub, vx, vy
+        const int3 wp = make_int3((S32)t1.x, (S32)t1.y, (S32)t1.z);
+        const int3 up = make_int3((S32)t1.w, (S32)t2.x, (S32)t2.y);
+        const int3 vp = make_int3((S32)t2.z, (S32)t2.w, (S32)t3.x);
+        computeBarys<SamplesLog2>(fs.m_center, fs.m_centerDX, fs.m_centerDY, wp, up, vp, (pixelX * 2 + 1) << SamplesLog2, (pixelY * 2 + 1) << SamplesLog2);
+        if (SamplesLog2 == 0) {
+            fs.m_centroid = fs.m_center; fs.m_centroidDX = fs.m_centerDX; fs.m_centroidDY = fs.m_centerDY;
+        } else {
+            computeBarys<SamplesLog2>(fs.m_centroid, fs.m_centroidDX, fs.m_centroidDY, wp, up, vp, (pixelX << (SamplesLog2 + 1)) + (S32)(centroid & 0xF),
+                                      (pixelY << (SamplesLog2 + 1)) + (S32)(centroid >> 4));
+        }
+    }
+    fs.run();
+}
+
+template <class BlendShaderClass>
+__device__ __forceinline__ void runBlendShader(BlendShaderClass& bs, int triIdx, int pixelX, int pixelY, int sampleIdx, U32 src, U32 dst) {
+    bs.m_triIdx = triIdx;
+    bs.m_pixelPos = Vec2i(pixelX, pixelY);
+    bs.m_sampleIdx = sampleIdx;
+    bs.m_src = src;
+    bs.m_dst = dst;
+    bs.m_color = 0xFF0000FFu;
+    bs.m_writeColor = true;
+    bs.run();
+}
+
+// Packed half-sample position of the shading point for a sample coverage mask
+// (reference: FineRaster.inl:151-164): pixel centre when all or none are covered.
+template <int SamplesLog2>
+__device__ __forceinline__ U32 centroidCode(U32 sampleMask) {
+    const int y = selectMSAACentroid(SamplesLog2, sampleMask);
+    if (y < 0) return 0x11u << SamplesLog2;
+    return (U32)(msaaSampleX(SamplesLog2, y) * 0x02 + y * 0x20 + 0x11);
+}
+
+// Lane-per-triangle refill of one batch of <= 32 queue entries.  Returns the ballot of triangles
+// that can touch the tile.
+template <int SamplesLog2, U32 RenderModeFlags>
+__device__ __forceinline__ U32 fineRefill(const crb_frame& f, FineTriRec* recs, int queuePos, int remaining, int tileX, int tileY) {
+    const int lane = laneId();
+    bool live = false;
+    if (lane < remaining) {
+        const S32 entry = __ldg(&f.tileQueue[queuePos + lane]);
+        const S32 dataIdx = resolveDataIdx(entry, f.triHeader);
+        const uint4 h = __ldg(&f.triHeader[dataIdx]);
+        // sample-space origin: centre of pixel (0,0) of the tile, viewport-centred subpixels
+        const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1));
+        const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1));
+        S32 a[3], b[3], c[3];
+        setupTileEdges(h, bx, by, a, b, c);
+        // sample offsets inside the tile span [-8, 120] subpixels on both axes
+        const S32 lo = SamplesLog2 == 0 ? 0 : -8, hi = SamplesLog2 == 0 ? 112 : 120;
+        live = true;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const S32 emax = c[i] + max(a[i] * lo, a[i] * hi) + max(b[i] * lo, b[i] * hi);
+            live &= emax >= 0;
+        }
+        if (live) {
+            FineTriRec r;
+            r.a0 = a[0]; r.b0 = b[0]; r.c0 = c[0];
+            r.a1 = a[1]; r.b1 = b[1]; r.c1 = c[1];
+            r.a2 = a[2]; r.b2 = b[2]; r.c2 = c[2];
+            r.zx = r.zy = r.zb = 0;
+            if ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0) {
+                const uint4 z = __ldg(&f.triData[(size_t)dataIdx * 4]);
+                r.zx = z.x; r.zy = z.y;
+                r.zb = z.z + z.x * (U32)(tileX << (CR_TILE_LOG2 + SamplesLog2)) + z.y * (U32)(tileY << (CR_TILE_LOG2 + SamplesLog2));
+            }
+            r.dataIdx = dataIdx; r.triIdx = entry >> 3; r.seq = 0; r.pad = 0;
+            uint4* dst = reinterpret_cast<uint4*>(&recs[lane]);
+            dst[0] = make_uint4((U32)r.a0, (U32)r.b0, (U32)r.c0, (U32)r.a1);
+            dst[1] = make_uint4((U32)r.b1, (U32)r.c1, (U32)r.a2, (U32)r.b2);
+            dst[2] = make_uint4((U32)r.c2, r.zx, r.zy, r.zb);
+            dst[3] = make_uint4((U32)r.dataIdx, (U32)r.triIdx, 0u, 0u);
+        }
+    }
+    const U32 mask = __ballot_sync(0xFFFFFFFFu, live);
+    __syncwarp();
+    return mask;
+}
+
+//------------------------------------------------------------------------------------------------
+// Single-sample kernel.
+//------------------------------------------------------------------------------------------------
+
+template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
+__global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
+    __shared__ __align__(16) FineTriRec s_recs[CRB_FINE_WARPS][32];
+
+    constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int activeIdx = blockIdx.x * CRB_FINE_WARPS + warp;
+    if (f.atomics->overflow != 0) return;
+    if (activeIdx >= f.atomics->numActiveTiles) return;
+
+    BlendShaderClass blendProbe;
+    const bool deferred = !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
+
+    FineTriRec* recs = s_recs[warp];
+    const int tileIdx = __ldg(&f.activeTiles[activeIdx]);
+    const int tileY = tileIdx / f.widthTiles, tileX = tileIdx - tileY * f.widthTiles;
+    const int queueStart = __ldg(&f.tileStart[tileIdx]);
+    const int queueCount = __ldg(&f.tileCount[tileIdx]);
+
+    // this lane's two pixels: (lx, ly) and (lx, ly + 4)
+    const int lx = lane & 7, ly = lane >> 3;
+    const int pixelX = (tileX << CR_TILE_LOG2) + lx;
+    const int pixelY0 = (tileY << CR_TILE_LOG2) + ly;
+    U32* colorPtr = f.colorBuffer + (size_t)pixelY0 * f.surfacePitch + pixelX;
+    U32* depthPtr = f.depthBuffer + (size_t)pixelY0 * f.surfacePitch + pixelX;
+    const size_t rowStep = (size_t)4 * f.surfacePitch;
+
+    U32 color[2], depth[2];
+    int winner[2] = {0, 0};   // 1-based position in this tile's queue of the visible fragment (deferred mode)
+    if (f.deferredClear) {
+        color[0] = color[1] = f.clearColor;
+        depth[0] = depth[1] = f.clearDepth;
+    } else {
+        color[0] = colorPtr[0]; color[1] = colorPtr[rowStep];
+        depth[0] = kDepth ? depthPtr[0] : 0u; depth[1] = kDepth ? depthPtr[rowStep] : 0u;
+    }
+
+    const S32 sx = lx << CR_SUBPIXEL_LOG2;
+    const S32 sy[2] = {ly << CR_SUBPIXEL_LOG2, (ly + 4) << CR_SUBPIXEL_LOG2};
+
+    for (int base = 0; base < queueCount; base += 32) {
+        U32 liveMask = fineRefill<0, RenderModeFlags>(f, recs, queueStart + base, queueCount - base, tileX, tileY);
+        while (liveMask) {
+            const int j = __ffs(liveMask) - 1;
+            liveMask &= liveMask - 1;
+            const uint4 r0 = reinterpret_cast<const uint4*>(&recs[j])[0];
+            const uint4 r1 = reinterpret_cast<const uint4*>(&recs[j])[1];
+            const uint4 r2 = reinterpret_cast<const uint4*>(&recs[j])[2];
+            // edge values at pixel 0, pixel 1 is 4 rows (64 subpixels) further along y
+            const S32 e0 = (S32)r0.z + (S32)r0.x * sx + (S32)r0.y * sy[0];
+            const S32 e1 = (S32)r1.y + (S32)r0.w * sx + (S32)r1.x * sy[0];
+            const S32 e2 = (S32)r2.x + (S32)r1.z * sx + (S32)r1.w * sy[0];
+            const S32 g0 = e0 + (S32)r0.y * 64, g1 = e1 + (S32)r1.x * 64, g2 = e2 + (S32)r1.w * 64;
+            const bool in[2] = {(e0 | e1 | e2) >= 0, (g0 | g1 | g2) >= 0};
+            if (!(in[0] | in[1])) continue;
+            const U32 z0 = r2.w + r2.y * (U32)lx + r2.z * (U32)ly;
+            const U32 z[2] = {z0, z0 + (r2.z << 2)};
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                if (!in[p]) continue;
+                if (kDepth && z[p] >= depth[p]) continue;
+                if (deferred) {
+                    if (kDepth) depth[p] = z[p];
+                    winner[p] = base + j + 1;
+                } else {
+                    const uint4 r3 = reinterpret_cast<const uint4*>(&recs[j])[3];
+                    FragmentShaderClass fs;
+                    runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, (int)r3.y, (int)r3.x, pixelX, pixelY0 + 4 * p, 0x11u);
+                    if (fs.m_discard) continue;
+                    if (kDepth) depth[p] = z[p];
+                    BlendShaderClass bs;
+                    runBlendShader(bs, (int)r3.y, pixelX, pixelY0 + 4 * p, 0, fs.m_color, color[p]);
+                    if (bs.m_writeColor) color[p] = bs.m_color;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    if (deferred) {
+        // shade only the visible fragment of each pixel
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            const int win = p == 0 ? winner[0] : winner[1];
+            if (win == 0) continue;
+            const S32 entry = __ldg(&f.tileQueue[queueStart + win - 1]);
+            const S32 dataIdx = resolveDataIdx(entry, f.triHeader);
+            FragmentShaderClass fs;
+            runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, entry >> 3, dataIdx, pixelX, pixelY0 + 4 * p, 0x11u);
+            BlendShaderClass bs;
+            runBlendShader(bs, entry >> 3, pixelX, pixelY0 + 4 * p, 0, fs.m_color, 0u);
+            if (bs.m_writeColor) {
+                if (p == 0) color[0] = bs.m_color; else color[1] = bs.m_color;
+            }
+        }
+    }
+
+    colorPtr[0] = color[0];
+    colorPtr[rowStep] = color[1];
+    if (kDepth || f.deferredClear) {
+        depthPtr[0] = depth[0];
+        depthPtr[rowStep] = depth[1];
+    }
+}
+
+}  // namespace FW

@@ -1,0 +1,93 @@
+// Work-buffer formats shared by the library kernels and pixel-pipe translation units.
+// CRTriangleHeader / CRTriangleData / PixelPipeSpec keep the reference's layout bit for bit
+// (src/cudaraster/cuda/PrivateDefs.hpp:26-62, :147-154) because the parity tests compare them
+// against the golden model and the rebuilt reference kernels.  crb_frame replaces CRParams
+// (:68-120): it is passed BY VALUE as the kernel argument (no __constant__ upload per launch).
+#pragma once
+#include "../../crb200.h"
+#include "../base/Math.hpp"
+#include "Constants.hpp"
+
+namespace FW {
+
+struct CRTriangleHeader {  // 16 B
+    S16 v0x, v0y;          // subpixels relative to the viewport centre; valid if triSubtris == 1
+    S16 v1x, v1y;
+    S16 v2x, v2y;
+    U32 misc;              // triSubtris == 1: zmin:20 | f01:4 | f12:4 | f20:4;  >= 2: sub-triangle base
+};
+
+struct CRTriangleData {  // 64 B
+    U32 zx, zy, zb, zslope;  // depth = zx*sampleX + zy*sampleY + zb (U32 wrap)
+    S32 wx, wy, wb;          // evaluated at (sampleX*2+1, sampleY*2+1): minW/w * CR_BARY_MAX
+    S32 ux, uy, ub;
+    S32 vx, vy, vb;
+    U32 vi0, vi1, vi2;
+};
+
+typedef crb_pipe_spec PixelPipeSpec;
+typedef crb_atomics CRAtomics;
+
+}  // namespace FW
+
+// One coarse work item: `count` consecutive entries of one bin's queue.
+struct crb_item {
+    int32_t bin;
+    int32_t first;   // index into binQueue
+    int32_t count;
+    int32_t slot;    // k-th item of its bin (row of tileCountMat = itemBase[bin] + slot)
+};
+
+struct crb_frame {
+    // ---- input (CRParams: numTris, vertexBuffer, indexBuffer)
+    int32_t numTris;
+    int32_t vertexStride;         // bytes per vertex (multiple of 16)
+    const void* vertexBuffer;
+    const int32_t* indexBuffer;   // numTris x int3
+
+    // ---- viewport (CRParams: viewportWidth .. numTiles)
+    int32_t viewportWidth, viewportHeight;   // surface size before rounding
+    int32_t widthPixels, heightPixels;       // rounded to tiles
+    int32_t widthBins, heightBins, numBins;
+    int32_t widthTiles, heightTiles, numTiles;
+    int32_t samplesLog2;
+    // sort-first window: snap grid of the full frame, integer centre offset, clip window in NDC
+    int32_t fullWidth, fullHeight, centerOfsX, centerOfsY;
+    int32_t subX0, subY0;                    // pixel origin of this viewport in the full frame
+    float clipLoX, clipHiX, clipLoY, clipHiY;
+
+    int32_t deferredClear;
+    uint32_t clearColor, clearDepth;
+    uint32_t* colorBuffer;        // linear surfaces, pitch in texels = widthPixels << samplesLog2
+    uint32_t* depthBuffer;
+    int32_t surfacePitch;
+
+    // ---- setup output
+    int32_t maxSubtris;
+    uint8_t* triSubtris;
+    uint4* triHeader;
+    uint4* triData;               // 4 x uint4 per sub-triangle
+
+    // ---- bin stage: count matrix -> exclusive offsets, CSR queue
+    int32_t numChunks;            // ceil(numTris / CRB_CHUNK_TRIS)
+    int32_t* binCountMat;         // [numBins][numChunks]; counts, then exclusive prefix over chunks
+    int32_t* binStart;            // [CR_MAXBINS_SQR]
+    int32_t* binTotal;            // [CR_MAXBINS_SQR]
+    int32_t maxBinEntries;
+    int32_t* binQueue;            // [maxBinEntries] triIdx*8 + (single ? 7 : sub)
+
+    // ---- coarse stage: work items, per-item tile counts, CSR queue
+    int32_t maxItems;
+    crb_item* items;              // [maxItems]
+    int32_t* binItemBase;         // [CR_MAXBINS_SQR] first item row of each bin
+    int32_t* binItemCount;        // [CR_MAXBINS_SQR]
+    int32_t* tileCountMat;        // [maxItems][CR_BIN_SQR]; counts, then exclusive prefix over items
+    int32_t maxTileEntries;
+    int32_t* tileQueue;           // [maxTileEntries]
+    int32_t* tileStart;           // [CR_MAXTILES_SQR] indexed by global tile index
+    int32_t* tileCount;           // [CR_MAXTILES_SQR]
+    int32_t* activeTiles;         // [CR_MAXTILES_SQR]
+
+    crb_atomics* atomics;
+    int32_t numSMs;
+};

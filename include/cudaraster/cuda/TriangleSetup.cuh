@@ -1,0 +1,272 @@
+// Stage 1 -- triangle setup + per-chunk bin histogram, hand-written for sm_100a.
+//
+// Computes what the reference's triangleSetupImpl computes (src/cudaraster/cuda/
+// TriangleSetup.inl:19-417): frustum cull, subpixel snap (cvt.rni.sat), backface and
+// between-samples cull, guard-band test, frustum clipping into <= 7 sub-triangles, integer
+// plane equations, and the triSubtris / triHeader / triData records -- bit for bit.
+//
+// What is different (B200 design, DESIGN.md "setup"):
+//  * one CTA owns a CHUNK of CRB_CHUNK_TRIS consecutive triangles and, besides setting them
+//    up, histograms the bins their sub-triangles touch into shared memory and publishes one
+//    column of the [bin][chunk] count matrix.  That column is all the bin stage needs to place
+//    this chunk's queue entries with a plain scan -- no 16-CTA bin kernel, no segment lists;
+//  * the frame parameters travel as a __grid_constant__ kernel argument, not through
+//    __constant__ uploads; vertices are read through the read-only path with 128-bit loads;
+//  * the clipper lives in a __noinline__ cold path so the common path needs no local stack.
+#pragma once
+#include "Overlap.cuh"
+
+namespace FW {
+
+struct SnappedTri {
+    int2 p0, p1, p2, lo, hi;
+    float3 rcpW;
+};
+
+__device__ __forceinline__ void snapTriangle(const crb_frame& f, float4 v0, float4 v1, float4 v2, SnappedTri& s) {
+    const F32 sx = (F32)(f.fullWidth << (CR_SUBPIXEL_LOG2 - 1));
+    const F32 sy = (F32)(f.fullHeight << (CR_SUBPIXEL_LOG2 - 1));
+    s.rcpW = make_float3(__frcp_rn(v0.w), __frcp_rn(v1.w), __frcp_rn(v2.w));
+    s.p0 = make_int2(f32ToS32SatRni(__fmul_rn(__fmul_rn(v0.x, s.rcpW.x), sx)) - f.centerOfsX, f32ToS32SatRni(__fmul_rn(__fmul_rn(v0.y, s.rcpW.x), sy)) - f.centerOfsY);
+    s.p1 = make_int2(f32ToS32SatRni(__fmul_rn(__fmul_rn(v1.x, s.rcpW.y), sx)) - f.centerOfsX, f32ToS32SatRni(__fmul_rn(__fmul_rn(v1.y, s.rcpW.y), sy)) - f.centerOfsY);
+    s.p2 = make_int2(f32ToS32SatRni(__fmul_rn(__fmul_rn(v2.x, s.rcpW.z), sx)) - f.centerOfsX, f32ToS32SatRni(__fmul_rn(__fmul_rn(v2.y, s.rcpW.z), sy)) - f.centerOfsY);
+    s.lo = make_int2(min(min(s.p0.x, s.p1.x), s.p2.x), min(min(s.p0.y, s.p1.y), s.p2.y));
+    s.hi = make_int2(max(max(s.p0.x, s.p1.x), s.p2.x), max(max(s.p0.y, s.p1.y), s.p2.y));
+}
+
+// 0 = visible, 1 = backfacing / degenerate, 2 = no sample inside the AABB.
+template <int SamplesLog2>
+__device__ __forceinline__ int prepareTriangle(const crb_frame& f, const SnappedTri& s, int2& d1, int2& d2, S32& area) {
+    d1 = make_int2(s.p1.x - s.p0.x, s.p1.y - s.p0.y);
+    d2 = make_int2(s.p2.x - s.p0.x, s.p2.y - s.p0.y);
+    area = d1.x * d2.y - d1.y * d2.x;
+    if (area <= 0) return 1;
+
+    const int sampleSize = 1 << (CR_SUBPIXEL_LOG2 - SamplesLog2);
+    const S32 biasX = (f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1)) - (sampleSize >> 1);
+    const S32 biasY = (f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1)) - (sampleSize >> 1);
+    const S32 lox = (s.lo.x + (sampleSize - 1) + biasX) & -sampleSize;
+    const S32 loy = (s.lo.y + (sampleSize - 1) + biasY) & -sampleSize;
+    const S32 hix = (s.hi.x + biasX) & -sampleSize;
+    const S32 hiy = (s.hi.y + biasY) & -sampleSize;
+    if (lox > hix || loy > hiy) return 2;
+
+    const S32 diff = hix + hiy - lox - loy;
+    if (diff <= sampleSize) {
+        // the AABB holds one or two sample points: test them exactly (no fill-rule bias here)
+        S32 qx = lox, qy = loy;
+        for (int pass = 0;; pass++) {
+            int2 t0 = make_int2(s.p0.x + biasX - qx, s.p0.y + biasY - qy);
+            int2 t1 = make_int2(s.p1.x + biasX - qx, s.p1.y + biasY - qy);
+            int2 t2 = make_int2(s.p2.x + biasX - qx, s.p2.y + biasY - qy);
+            S32 e0 = t0.x * t1.y - t0.y * t1.x;
+            S32 e1 = t1.x * t2.y - t1.y * t2.x;
+            S32 e2 = t2.x * t0.y - t2.y * t0.x;
+            if (!(e0 < 0 || e1 < 0 || e2 < 0)) break;
+            if (pass == 1 || diff == 0) return 2;
+            qx = hix, qy = hiy;
+        }
+    }
+    return 0;
+}
+
+// Writes one sub-triangle record and returns its packed header (for the bin histogram).
+template <int SamplesLog2, U32 RenderModeFlags>
+__device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, uint4* td, int3 vidx, float4 v0, float4 v1, float4 v2,
+                                               float2 b0, float2 b1, float2 b2, const SnappedTri& s, int2 d1, int2 d2, S32 area) {
+    F32 areaRcp = 0.0f;
+    int2 wv0 = make_int2(0, 0);
+    if ((RenderModeFlags & (CRB_FLAG_DEPTH | CRB_FLAG_LERP)) != 0) {
+        areaRcp = __frcp_rn((F32)area);
+        // Plane equations are set up in FULL-FRAME viewport-corner coordinates and translated
+        // to this viewport below, so a sort-first split renders the same depth / barycentrics as
+        // the unsplit frame.  For a plain viewport this is the reference's wv0.
+        wv0.x = s.p0.x + f.centerOfsX + (f.fullWidth << (CR_SUBPIXEL_LOG2 - 1));
+        wv0.y = s.p0.y + f.centerOfsY + (f.fullHeight << (CR_SUBPIXEL_LOG2 - 1));
+    }
+
+    U32 zmin = 0;
+    if ((RenderModeFlags & CRB_FLAG_DEPTH) != 0) {
+        const F32 zcoef = (F32)(CR_DEPTH_MAX - CR_DEPTH_MIN) * 0.5f;
+        const F32 zbias = (F32)(CR_DEPTH_MAX + CR_DEPTH_MIN) * 0.5f;
+        float3 zvert;
+        zvert.x = __fmaf_rn(__fmul_rn(v0.z, zcoef), s.rcpW.x, zbias);
+        zvert.y = __fmaf_rn(__fmul_rn(v1.z, zcoef), s.rcpW.y, zbias);
+        zvert.z = __fmaf_rn(__fmul_rn(v2.z, zcoef), s.rcpW.z, zbias);
+        int2 zv0 = make_int2(wv0.x - (1 << (CR_SUBPIXEL_LOG2 - SamplesLog2 - 1)), wv0.y - (1 << (CR_SUBPIXEL_LOG2 - SamplesLog2 - 1)));
+        uint3 zp = setupPleq(zvert, zv0, d1, d2, areaRcp, SamplesLog2);
+        zmin = f32ToU32SatRni(__fsub_rn(fminf(fminf(zvert.x, zvert.y), zvert.z), (F32)CR_LERP_ERROR(SamplesLog2)));
+        U32 zslope = 0;
+        if (SamplesLog2 != 0) {
+            S32 ax = (S32)zp.x; ax = ax >= 0 ? ax : -ax;
+            S32 ay = max((S32)zp.y, -FW_S32_MAX); ay = ay >= 0 ? ay : -ay;
+            U32 tmp = (U32)ax + (U32)ay;
+            const int k = SamplesLog2 - 1 > 0 ? SamplesLog2 - 1 : 0;
+            zslope = tmp << k;
+            if ((zslope >> k) != tmp) zslope = FW_U32_MAX;
+        }
+        zp.z += zp.x * ((U32)f.subX0 << SamplesLog2) + zp.y * ((U32)f.subY0 << SamplesLog2);
+        td[0] = make_uint4(zp.x, zp.y, zp.z, zslope);
+    }
+
+    if ((RenderModeFlags & CRB_FLAG_LERP) != 0) {
+        F32 wcoef = __fmul_rn(fminf(fminf(v0.w, v1.w), v2.w), (F32)CR_BARY_MAX);
+        float3 wvert = make_float3(__fmul_rn(wcoef, s.rcpW.x), __fmul_rn(wcoef, s.rcpW.y), __fmul_rn(wcoef, s.rcpW.z));
+        float3 uvert = make_float3(__fmul_rn(b0.x, wvert.x), __fmul_rn(b1.x, wvert.y), __fmul_rn(b2.x, wvert.z));
+        float3 vvert = make_float3(__fmul_rn(b0.y, wvert.x), __fmul_rn(b1.y, wvert.y), __fmul_rn(b2.y, wvert.z));
+        uint3 wp = setupPleq(wvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+        uint3 up = setupPleq(uvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+        uint3 vp = setupPleq(vvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+        const U32 ox2 = (U32)f.subX0 << (SamplesLog2 + 1), oy2 = (U32)f.subY0 << (SamplesLog2 + 1);
+        wp.z += wp.x * ox2 + wp.y * oy2;
+        up.z += up.x * ox2 + up.y * oy2;
+        vp.z += vp.x * ox2 + vp.y * oy2;
+        td[1] = make_uint4(wp.x, wp.y, wp.z, up.x);
+        td[2] = make_uint4(up.y, up.z, vp.x, vp.y);
+        td[3] = make_uint4(vp.z, (U32)vidx.x, (U32)vidx.y, (U32)vidx.z);
+    } else {
+        td[3] = make_uint4(0u, (U32)vidx.x, (U32)vidx.y, (U32)vidx.z);
+    }
+
+    const U32 f01 = cover8x8_selectFlips(d1.x, d1.y);
+    const U32 f12 = cover8x8_selectFlips(d2.x - d1.x, d2.y - d1.y);
+    const U32 f20 = cover8x8_selectFlips(-d2.x, -d2.y);
+    uint4 h = make_uint4(((U32)s.p0.x & 0xFFFFu) | ((U32)s.p0.y << 16), ((U32)s.p1.x & 0xFFFFu) | ((U32)s.p1.y << 16),
+                         ((U32)s.p2.x & 0xFFFFu) | ((U32)s.p2.y << 16), (zmin & 0xFFFFF000u) | (f01 << 6) | (f12 << 2) | (f20 >> 2));
+    *th = h;
+    return h;
+}
+
+template <int SamplesLog2>
+__device__ __forceinline__ void histogramBins(const crb_frame& f, uint4 h, int* s_binCount) {
+    TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
+    forEachCell<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(fp, 0, 0, f.widthBins - 1, f.heightBins - 1,
+                                                          [&](S32 bx, S32 by) { atomicAdd(&s_binCount[bx + by * f.widthBins], 1); });
+}
+
+// Cold path: clip against the view window, fan the polygon, re-snap / re-cull every sub-triangle.
+template <int SamplesLog2, U32 RenderModeFlags>
+__device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, int3 vidx, float4 v0, float4 v1, float4 v2, int* s_binCount) {
+    const F32 lo[3] = {f.clipLoX, f.clipLoY, -1.0f}, hi[3] = {f.clipHiX, f.clipHiY, 1.0f};
+    const float4 d1 = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), __fsub_rn(v1.w, v0.w));
+    const float4 d2 = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), __fsub_rn(v2.w, v0.w));
+    float2 bary[9];
+    int numVerts = clipTriangleWithWindow(bary, v0, v1, v2, d1, d2, lo, hi);
+
+    auto vertexAt = [&](int i) {
+        float2 b = bary[i];
+        return make_float4(__fmaf_rn(d2.x, b.y, __fmaf_rn(d1.x, b.x, v0.x)), __fmaf_rn(d2.y, b.y, __fmaf_rn(d1.y, b.x, v0.y)),
+                           __fmaf_rn(d2.z, b.y, __fmaf_rn(d1.z, b.x, v0.z)), __fmaf_rn(d2.w, b.y, __fmaf_rn(d1.w, b.x, v0.w)));
+    };
+
+    SnappedTri s;
+    int2 e1, e2;
+    S32 area;
+    int numSub = 0;
+    if (numVerts >= 3) {
+        const float4 c0 = vertexAt(0);
+        float4 cPrev = vertexAt(1);
+        for (int i = 2; i < numVerts; i++) {
+            float4 cCur = vertexAt(i);
+            snapTriangle(f, c0, cPrev, cCur, s);
+            if (prepareTriangle<SamplesLog2>(f, s, e1, e2, area) == 0) numSub++;
+            cPrev = cCur;
+        }
+    }
+    f.triSubtris[tri] = (U8)numSub;
+    if (numSub == 0) return 0;
+
+    // 0/1 survivors live in slot `tri`; more take a contiguous run from the global cursor
+    // (allocation order is non-deterministic, consumers go through triHeader[tri].misc).
+    int slot = tri;
+    if (numSub > 1) {
+        // the device counter holds the EXTRA slots; slot numbering starts at numTris like CRAtomics.numSubtris
+        slot = f.numTris + atomicAdd(&f.atomics->numSubtris, numSub);
+        reinterpret_cast<U32*>(&f.triHeader[tri])[3] = (U32)slot;
+        if (slot + numSub > f.maxSubtris) {   // overflow: counted, not written; the host grows the buffers and reruns
+            atomicOr(&f.atomics->overflow, 1);
+            return numSub;
+        }
+    }
+    const float4 c0 = vertexAt(0);
+    float4 cPrev = vertexAt(1);
+    for (int i = 2; i < numVerts; i++) {
+        float4 cCur = vertexAt(i);
+        snapTriangle(f, c0, cPrev, cCur, s);
+        if (prepareTriangle<SamplesLog2>(f, s, e1, e2, area) == 0) {
+            uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[slot], &f.triData[(size_t)slot * 4], vidx, c0, cPrev, cCur, bary[0], bary[i - 1], bary[i], s, e1, e2, area);
+            histogramBins<SamplesLog2>(f, h, s_binCount);
+            slot++;
+        }
+        cPrev = cCur;
+    }
+    return numSub;
+}
+
+template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
+__global__ void __launch_bounds__(CRB_SETUP_THREADS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
+    __shared__ int s_binCount[CR_MAXBINS_SQR];
+    for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
+    __syncthreads();
+
+    const int chunk = blockIdx.x;
+    const int stride4 = (int)(sizeof(VertexClass) / sizeof(float4));
+    const float4* __restrict__ verts = reinterpret_cast<const float4*>(f.vertexBuffer);
+    const S32 aabbLimit = (1 << (CR_MAXVIEWPORT_LOG2 + CR_SUBPIXEL_LOG2)) - 1;
+
+#pragma unroll 1
+    for (int r = 0; r < CRB_CHUNK_TRIS / CRB_SETUP_THREADS; r++) {
+        const int tri = chunk * CRB_CHUNK_TRIS + r * CRB_SETUP_THREADS + threadIdx.x;
+        if (tri >= f.numTris) break;
+
+        const int3 vidx = make_int3(__ldg(&f.indexBuffer[tri * 3 + 0]), __ldg(&f.indexBuffer[tri * 3 + 1]), __ldg(&f.indexBuffer[tri * 3 + 2]));
+        const float4 v0 = __ldg(&verts[(size_t)vidx.x * stride4]);
+        const float4 v1 = __ldg(&verts[(size_t)vidx.y * stride4]);
+        const float4 v2 = __ldg(&verts[(size_t)vidx.z * stride4]);
+
+        // all three vertices outside one plane of the view window -> culled
+        const F32 wx0h = __fmul_rn(v0.w, f.clipHiX), wx1h = __fmul_rn(v1.w, f.clipHiX), wx2h = __fmul_rn(v2.w, f.clipHiX);
+        const F32 wx0l = __fmul_rn(v0.w, f.clipLoX), wx1l = __fmul_rn(v1.w, f.clipLoX), wx2l = __fmul_rn(v2.w, f.clipLoX);
+        const F32 wy0h = __fmul_rn(v0.w, f.clipHiY), wy1h = __fmul_rn(v1.w, f.clipHiY), wy2h = __fmul_rn(v2.w, f.clipHiY);
+        const F32 wy0l = __fmul_rn(v0.w, f.clipLoY), wy1l = __fmul_rn(v1.w, f.clipLoY), wy2l = __fmul_rn(v2.w, f.clipLoY);
+        const bool outside = ((wx0h < v0.x) & (wx1h < v1.x) & (wx2h < v2.x)) | ((wx0l > v0.x) & (wx1l > v1.x) & (wx2l > v2.x)) |
+                             ((wy0h < v0.y) & (wy1h < v1.y) & (wy2h < v2.y)) | ((wy0l > v0.y) & (wy1l > v1.y) & (wy2l > v2.y)) |
+                             ((v0.w < v0.z) & (v1.w < v1.z) & (v2.w < v2.z)) | ((v0.w < -v0.z) & (v1.w < -v1.z) & (v2.w < -v2.z));
+        if (outside) {
+            f.triSubtris[tri] = 0;
+            continue;
+        }
+
+        // inside the depth range: snap; inside the S16 guard band and small enough -> fast path
+        if ((v0.w >= fabsf(v0.z)) & (v1.w >= fabsf(v1.z)) & (v2.w >= fabsf(v2.z))) {
+            SnappedTri s;
+            snapTriangle(f, v0, v1, v2, s);
+            const S32 loxy = min(s.lo.x, s.lo.y), hixy = max(s.hi.x, s.hi.y);
+            if (loxy >= -32768 && hixy <= 32767 && hixy - loxy <= aabbLimit) {
+                int2 d1, d2;
+                S32 area;
+                const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
+                f.triSubtris[tri] = (res == 0) ? 1 : 0;
+                if (res == 0) {
+                    uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
+                                                                          make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area);
+                    histogramBins<SamplesLog2>(f, h, s_binCount);
+                }
+                continue;
+            }
+        }
+        setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, s_binCount);
+    }
+
+    __syncthreads();
+    for (int b = threadIdx.x; b < f.numBins; b += CRB_SETUP_THREADS) f.binCountMat[(size_t)b * f.numChunks + chunk] = s_binCount[b];
+}
+
+template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
+inline int launchTriangleSetup(const crb_frame* f, void* stream) {
+    if (f->numTris <= 0) return CRB_OK;
+    triangleSetupKernel<VertexClass, SamplesLog2, RenderModeFlags><<<f->numChunks, CRB_SETUP_THREADS, 0, (cudaStream_t)stream>>>(*f);
+    return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}
+
+}  // namespace FW

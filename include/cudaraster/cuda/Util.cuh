@@ -1,0 +1,184 @@
+// Device helpers of the B200 pipeline: saturating conversions, colour pack / blend, flip-bit
+// selection, the barycentric clipper and the fixed-point plane-equation setup.
+//
+// These follow the reference's NUMERICAL contract (reference files
+// src/cudaraster/cuda/Util.hpp:182-298 and Util.inl:30-91) so that triHeader / triData are
+// bit-identical, but are written against today's intrinsics: no Fermi video-SIMD PTX, no
+// texture references, no implicit warp-synchronous code.  Every float expression spells out its
+// roundings (__fmul_rn / __fmaf_rn ...) at exactly the places where nvcc contracts the
+// reference's source, so results do not depend on -fmad.
+#pragma once
+#include <cuda_runtime.h>
+#include "PrivateDefs.hpp"
+
+namespace FW {
+
+// c_msaaPatterns[log2 N][sampleY] = sampleX  (reference: cuda/Util.hpp:27-35)
+#define CRB_MSAA_X_TABLE {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0, 0, 0}, {1, 3, 0, 2, 0, 0, 0, 0}, {7, 2, 4, 0, 6, 3, 1, 5}}
+
+__host__ __device__ __forceinline__ int msaaSampleX(int samplesLog2, int i) {
+    // packed 3-bit nibbles, sample i in bits [4i, 4i+3]
+    const unsigned pat[4] = {0x0u, 0x10u, 0x2031u, 0x51360427u};
+    return (int)((pat[samplesLog2] >> (4 * i)) & 0xFu);
+}
+
+#ifdef __CUDACC__
+
+// ---- conversions with PTX semantics -----------------------------------------------------------
+__device__ __forceinline__ S32 f32ToS32SatRni(F32 a) { return __float2int_rn(a); }     // cvt.rni.sat.s32 (CUDA's float->int intrinsics saturate, NaN -> 0)
+__device__ __forceinline__ U32 f32ToU32SatRni(F32 a) { return __float2uint_rn(a); }    // cvt.rni.sat.u32
+__device__ __forceinline__ U32 f32ToU32SatRmi(F32 a) { return __float2uint_rd(a); }    // cvt.rmi.sat.u32
+__device__ __forceinline__ U32 f32ToU32Rzi(F32 a) { return __float2uint_rz(a); }       // (U32)float
+
+// ---- colour -------------------------------------------------------------------------------------
+// Round-half-up of c*255 with clamping, evaluated as floor(c*255*2^24 + 2^23) >> 24 with the
+// multiply-add and the conversion both rounding down (reference: cuda/Util.inl:30-38).
+__device__ __forceinline__ U32 packUnorm8x4(F32 r, F32 g, F32 b, F32 a) {
+    const F32 scale = 16777216.0f * 255.0f, half = 8388608.0f;
+    U32 x = f32ToU32SatRmi(__fmaf_rd(r, scale, half));
+    U32 y = f32ToU32SatRmi(__fmaf_rd(g, scale, half));
+    U32 z = f32ToU32SatRmi(__fmaf_rd(b, scale, half));
+    U32 w = f32ToU32SatRmi(__fmaf_rd(a, scale, half));
+    return (x >> 24) | ((y >> 24) << 8) | ((z >> 24) << 16) | (w & 0xFF000000u);
+}
+__device__ __forceinline__ U32 toABGR(const Vec4f& c) { return packUnorm8x4(c.x, c.y, c.z, c.w); }
+__device__ __forceinline__ U32 toABGR(float4 c) { return packUnorm8x4(c.x, c.y, c.z, c.w); }
+
+// 8-bit fixed point blend: ((s*fs + d*fd) * 0x010101 + 0x800000) >> 24 per channel; the factors
+// are taken from the top byte of the factor words (reference: cuda/Util.inl:42-60).
+template <bool Clamp>
+__device__ __forceinline__ U32 blendChannels(U32 src, U32 dst, U32 fsC, U32 fdC, U32 fsA, U32 fdA) {
+    U32 out = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        U32 fs = (c == 3 ? fsA : fsC) >> 24, fd = (c == 3 ? fdA : fdC) >> 24;
+        U32 t = ((src >> (8 * c)) & 0xFF) * fs + ((dst >> (8 * c)) & 0xFF) * fd;
+        if (Clamp) t = min(t, 255u * 255u);
+        out |= (((t * 0x010101u + 0x800000u) >> 24) & 0xFF) << (8 * c);
+    }
+    return out;
+}
+__device__ __forceinline__ U32 blendABGR(U32 src, U32 dst, U32 fsC, U32 fdC, U32 fsA, U32 fdA) { return blendChannels<false>(src, dst, fsC, fdC, fsA, fdA); }
+__device__ __forceinline__ U32 blendABGRClamp(U32 src, U32 dst, U32 fsC, U32 fdC, U32 fsA, U32 fdA) { return blendChannels<true>(src, dst, fsC, fdC, fsA, fdA); }
+
+#endif  // __CUDACC__
+
+// ---- edge orientation code stored in triHeader.misc (reference: cuda/Util.hpp:207-217) ---------
+__host__ __device__ __forceinline__ U32 cover8x8_selectFlips(S32 dx, S32 dy) {
+    const U32 FY = 1u << CR_FLIPBIT_FLIP_Y, FX = 1u << CR_FLIPBIT_FLIP_X, SW = 1u << CR_FLIPBIT_SWAP_XY, CO = 1u << CR_FLIPBIT_COMPL;
+    U32 f = 0;
+    if (dy > 0 || (dy == 0 && dx <= 0)) f ^= FX ^ FY ^ CO;
+    if (dx > 0) f ^= FX ^ FY;
+    if (abs(dx) < abs(dy)) f ^= SW ^ FY;
+    return f;
+}
+
+// Sample nearest to the pixel centre among the covered ones; -1 when all or none are covered
+// (reference: cuda/Util.hpp:182-203).
+__host__ __device__ __forceinline__ int selectMSAACentroid(int samplesLog2, U32 sampleMask) {
+    int n = 1 << samplesLog2;
+    if (sampleMask == 0 || sampleMask == (1u << n) - 1) return -1;
+    int best = -1, bestDist = 0x7FFFFFFF;
+    for (int i = 0; i < n; i++) {
+        if (!((sampleMask >> i) & 1)) continue;
+        int ax = msaaSampleX(samplesLog2, i) * 2 + 1 - n, ay = i * 2 + 1 - n;
+        int d = ax * ax + ay * ay;
+        if (d < bestDist) best = i, bestDist = d;
+    }
+    return best;
+}
+
+__host__ __device__ inline U32 encodeDepth(U32 depth) {  // reference: cuda/Util.hpp:290-298
+    double v = (double)depth / (65536.0 * 65536.0 - 1.0);
+    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    v = v * (double)(CR_DEPTH_MAX - CR_DEPTH_MIN) + (double)CR_DEPTH_MIN;
+    return (U32)v;
+}
+
+#ifdef __CUDACC__
+
+// ---- clipper: Sutherland-Hodgman in barycentric space (reference: cuda/Util.hpp:221-286) -------
+// dist(b) = p0 + p1*b.x + p2*b.y evaluated as fma(p2, b.y, fma(p1, b.x, p0)).
+__device__ __forceinline__ F32 clipPlaneDist(F32 p0, F32 p1, F32 p2, float2 b) { return __fmaf_rn(p2, b.y, __fmaf_rn(p1, b.x, p0)); }
+
+static __device__ __noinline__ int clipPolygonWithPlane(float2* out, const float2* in, int n, F32 p0, F32 p1, F32 p2) {
+    if (n < 3) return 0;
+    int m = 0;
+    float2 a = in[n - 1];
+    F32 da = clipPlaneDist(p0, p1, p2, a);
+    for (int i = 0; i < n; i++) {
+        float2 b = in[i];
+        F32 db = clipPlaneDist(p0, p1, p2, b);
+        if (__fmul_rn(da, db) < 0.0f) {
+            F32 tb = __fdiv_rn(da, __fsub_rn(da, db));
+            F32 ta = __fsub_rn(1.0f, tb);
+            out[m].x = __fmaf_rn(a.x, ta, __fmul_rn(b.x, tb));
+            out[m].y = __fmaf_rn(a.y, ta, __fmul_rn(b.y, tb));
+            m++;
+        }
+        if (db >= 0.0f) out[m++] = b;
+        a = b;
+        da = db;
+    }
+    return m;
+}
+
+// Clips against lo[a]*w <= v[a] <= hi[a]*w for a = x,y,z.  With lo = -1, hi = +1 every expression
+// reduces exactly to the reference's  w < |x|,  w + x,  w - x.
+static __device__ __noinline__ int clipTriangleWithWindow(float2* bary, float4 v0, float4 v1, float4 v2, float4 d1, float4 d2, const F32* lo, const F32* hi) {
+    int n = 3;
+    bary[0] = make_float2(0.0f, 0.0f);
+    bary[1] = make_float2(1.0f, 0.0f);
+    bary[2] = make_float2(0.0f, 1.0f);
+    const F32 c0[3] = {v0.x, v0.y, v0.z}, c1[3] = {v1.x, v1.y, v1.z}, c2[3] = {v2.x, v2.y, v2.z};
+    const F32 e1[3] = {d1.x, d1.y, d1.z}, e2[3] = {d2.x, d2.y, d2.z};
+    float2 tmp[9];
+    for (int a = 0; a < 3; a++) {
+        bool any = (__fmul_rn(v0.w, hi[a]) < c0[a]) | (__fmul_rn(v0.w, lo[a]) > c0[a]) | (__fmul_rn(v1.w, hi[a]) < c1[a]) | (__fmul_rn(v1.w, lo[a]) > c1[a]) |
+                   (__fmul_rn(v2.w, hi[a]) < c2[a]) | (__fmul_rn(v2.w, lo[a]) > c2[a]);
+        if (!any) continue;
+        n = clipPolygonWithPlane(tmp, bary, n, __fmaf_rn(-lo[a], v0.w, c0[a]), __fmaf_rn(-lo[a], d1.w, e1[a]), __fmaf_rn(-lo[a], d2.w, e2[a]));
+        n = clipPolygonWithPlane(bary, tmp, n, __fmaf_rn(hi[a], v0.w, -c0[a]), __fmaf_rn(hi[a], d1.w, -e1[a]), __fmaf_rn(hi[a], d2.w, -e2[a]));
+    }
+    return n;
+}
+
+// ---- plane equation in fixed point (reference: cuda/Util.inl:65-91) ----------------------------
+// values at the three vertices -> (x slope, y slope, constant) such that
+// plane(sx, sy) = x*sx + y*sy + z in sample units (samplesLog2 selects the unit).  All integer
+// after the initial float -> U32 truncation; S64 intermediates; shifts are arithmetic.
+__device__ __forceinline__ uint3 setupPleq(float3 values, int2 v0, int2 d1, int2 d2, F32 areaRcp, int samplesLog2) {
+    F32 mx = fmaxf(fmaxf(values.x, values.y), values.z);
+    int sh = min(max((__float_as_int(mx) >> 23) - (127 + 22), 0), 8);
+    S32 t0 = (S32)(f32ToU32Rzi(values.x) >> sh);
+    S32 t1 = (S32)((f32ToU32Rzi(values.y) >> sh) - (U32)t0);
+    S32 t2 = (S32)((f32ToU32Rzi(values.z) >> sh) - (U32)t0);
+
+    U32 rcpMant = ((U32)__float_as_int(areaRcp) & 0x007FFFFFu) | 0x00800000u;
+    int rcpShift = (23 + 127) - (__float_as_int(areaRcp) >> 23);
+
+    S64 xc = ((S64)t1 * d2.y - (S64)t2 * d1.y) * (S64)rcpMant;
+    S64 yc = ((S64)t2 * d1.x - (S64)t1 * d2.x) * (S64)rcpMant;
+    const int sub = CR_SUBPIXEL_LOG2 - samplesLog2;
+    uint3 p;
+    p.x = (U32)(xc >> (rcpShift - (sh + sub)));
+    p.y = (U32)(yc >> (rcpShift - (sh + sub)));
+
+    S32 cx = (v0.x * 2 + min(min(d1.x, d2.x), 0) + max(max(d1.x, d2.x), 0)) >> (sub + 1);
+    S32 cy = (v0.y * 2 + min(min(d1.y, d2.y), 0) + max(max(d1.y, d2.y), 0)) >> (sub + 1);
+    S32 vcx = v0.x - (cx << sub);
+    S32 vcy = v0.y - (cy << sub);
+
+    p.z = (U32)t0 << sh;
+    p.z -= (U32)(((xc >> 13) * vcx + (yc >> 13) * vcy) >> (rcpShift - (sh + 13)));
+    p.z -= p.x * (U32)cx + p.y * (U32)cy;
+    return p;
+}
+
+// ---- warp helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ U32 laneId() { return threadIdx.x & 31; }
+__device__ __forceinline__ U32 laneMaskLt() { U32 r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
+
+#endif  // __CUDACC__
+
+}  // namespace FW

@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library loads and exports every entry point include/crb200.h declares; without
+a GPU it refuses to create a context (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "crb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(crb_[a-z_0-9]+)\s*\(", src)) - {"crb_stage_fn"})
+
+
+def test_header_functions_are_exported(crb):
+    lib = crb.load_library()
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "libcrb200.so does not export %s" % n
+    assert lib.crb_abi_version() == 1
+
+
+def test_builtin_pipes_resolve_by_name(crb):
+    lib = crb.load_library()
+    for base, s, f, blend in [("passthrough", 0, 1, "BlendReplace"), ("gouraud", 0, 3, "BlendReplace"), ("gouraud", 2, 3, "BlendSrcOver"),
+                              ("texPhong", 2, 3, "BlendReplace"), ("gouraud", 3, 3, "BlendReplace")]:
+        name = crb.pipe_name(base, s, f, blend)
+        for suffix in ("_triangleSetup", "_binRaster", "_coarseRaster", "_fineRaster", "_spec"):
+            assert hasattr(lib, name + suffix), name + suffix
+    for suffix in ("_triangleSetup", "_binRaster", "_coarseRaster", "_fineRaster", "_spec"):
+        assert hasattr(lib, "PixelPipe_passthrough" + suffix)
+
+
+def test_pipe_spec_layout(crb):
+    from cudaraster_linux_b200.binding import _PipeSpec
+    lib = crb.load_library()
+    spec = _PipeSpec.in_dll(lib, crb.pipe_name("gouraud", 2, 3, "BlendSrcOver") + "_spec")
+    assert (spec.samplesLog2, spec.vertexStructSize, spec.renderModeFlags, spec.profilingMode) == (2, 32, 3, 0)
+    assert spec.blendShaderName == b"BlendSrcOver"
+    assert ctypes.sizeof(_PipeSpec) == 144  # == sizeof(PixelPipeSpec), cuda/PrivateDefs.hpp:147-154
+
+
+def test_no_cpu_fallback(crb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = crb.load_library()
+    ctx = ctypes.c_void_p()
+    rc = lib.crb_create(0, ctypes.byref(ctx))
+    assert rc == 3 and not ctx.value  # CRB_ERR_NO_DEVICE
+    with pytest.raises(crb.CrbError):
+        crb.CudaRaster(0)
+
+
+def test_pack_helpers_match_reference_known_answers(crb):
+    lib = crb.load_library()
+    # known answers computed with the reference's own host code
+    assert lib.crb_pack_abgr(0.2, 0.4, 0.8, 1.0) == 0xFFCC6633
+    assert lib.crb_encode_clear_depth(1.0) == 0xFFFFBB3F
+    assert lib.crb_encode_clear_depth(0.5) == 0x7FFFFFFF
+    assert lib.crb_encode_clear_depth(0.0) == 0x000044C0

@@ -1,0 +1,178 @@
+"""GPU: the CUDA pipeline (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for triSubtris / triHeader / triData, depth and colour; queues must be ordered supersets."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_surfaces(cc, cd, g, lsb=0):
+    assert np.array_equal(cd, g["depth"]), "depth differs at %d texels" % int((cd != g["depth"]).sum())
+    if lsb == 0:
+        assert np.array_equal(cc, g["color"]), "colour differs at %d texels" % int((cc != g["color"]).sum())
+    else:
+        assert util.color_max_diff(cc, g["color"]) <= lsb
+
+
+def test_c1_cube_known_answers(raster, crb):
+    """BASELINE config 1 at both resolutions: every texel is background or cube."""
+    for w, h in ((1024, 768), (720, 480)):
+        v, i = crb.scenes.cube(w, h)
+        cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "passthrough", 1, pipe="PixelPipe_passthrough")
+        g = util.draw_gold(v, i, w, h, "passthrough", 1)
+        _check_surfaces(cc, cd, g)
+        assert set(np.unique(cc).tolist()) == {0xFF0000FF, 0xFFCC6633}
+        assert cd.max() == 0xFFFFBB3F and (cd[cc == 0xFF0000FF] < 0xFFFFBB3F).all() and (cd[cc == 0xFFCC6633] == 0xFFFFBB3F).all()
+        st = raster.getStats()
+        assert all(st[k] >= 0 for k in st) and "triangleSetup" in raster.getProfilingInfo()
+
+
+@pytest.mark.parametrize("shader,flags", [("passthrough", 1), ("passthrough", 0), ("gouraud", 3), ("gouraud", 2), ("gouraud", 1), ("gouraud", 0)])
+def test_setup_and_surfaces_random_soup(raster, crb, shader, flags):
+    """Mixed triangle soup with frustum-crossing and w<=0 triangles: setup records bit-exact
+    (clipped ones through the misc indirection), then surfaces bit-exact."""
+    w, h = 640, 360
+    v, i = crb.scenes.random_soup(20000, seed=1234 + flags, stride_floats=util.STRIDE[shader] // 4)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, shader, flags)
+    wb = raster.getWorkBuffers(i.shape[0])
+    gs = util.gold_setup(v, i, w, h, shader, flags)
+    n_single, n_multi = util.compare_setup(wb, gs, i.shape[0], flags)
+    assert n_single > 1000 and n_multi > 100
+    _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, shader, flags))
+
+
+def test_queues_are_ordered_supersets(raster, crb, gold):
+    """Bin and tile queues: per-bin / per-tile entries strictly increasing in triIdx*8+sub, and every
+    (triangle, tile) pair with coverage is present."""
+    import ctypes
+    w, h = 640, 360
+    v, i = crb.scenes.random_soup(6000, seed=77, stride_floats=4, size=0.6)
+    util.draw_cuda(raster, crb, v, i, w, h, "passthrough", 1)
+    wb = raster.getWorkBuffers(i.shape[0])
+    tq, ts, tc = wb["tileQueue"], wb["tileStart"], wb["tileCount"]
+    bq, bs, bt = wb["binQueue"], wb["binStart"], wb["binTotal"]
+    for b in range(len(bs)):
+        e = bq[bs[b]:bs[b] + bt[b]]
+        assert (np.diff(e) > 0).all(), "bin %d not strictly increasing" % b
+    tiles_x = (w + 7) // 8
+    present = {}
+    for t in range(len(ts)):
+        e = tq[ts[t]:ts[t] + tc[t]]
+        assert (np.diff(e) > 0).all(), "tile %d not strictly increasing" % t
+        present[t] = set(e.tolist())
+    # exact coverage from the oracle for a sample of sub-triangles
+    L = gold.lib()
+    hdr, sub = wb["triHeader"], wb["triSubtris"]
+    rng = np.random.default_rng(5)
+    checked = 0
+    for tri in rng.permutation(i.shape[0])[:1500]:
+        n = int(sub[tri])
+        for s in range(n):
+            di = tri if n == 1 else int(hdr[tri, 3]) + s
+            entry = tri * 8 + (7 if n == 1 else s)
+            hraw = np.ascontiguousarray(hdr[di])
+            xs = hraw[:3].view(np.int16)[0::2].astype(np.int64) + w * 8
+            ys = hraw[:3].view(np.int16)[1::2].astype(np.int64) + h * 8
+            for ty in range(max(int(ys.min()) >> 7, 0), min(int(ys.max()) >> 7, (h + 7) // 8 - 1) + 1):
+                for tx in range(max(int(xs.min()) >> 7, 0), min(int(xs.max()) >> 7, tiles_x - 1) + 1):
+                    if L.gold_cover_tile(hraw.ctypes.data, w, h, tx, ty):
+                        assert entry in present[tx + ty * tiles_x], "covered pair missing from tile queue"
+                        checked += 1
+    assert checked > 1000
+
+
+@pytest.mark.parametrize("samples_log2", [1, 2, 3])
+def test_msaa_gouraud(raster, crb, samples_log2):
+    w, h = 320, 200
+    v, i = crb.scenes.random_soup(8000, seed=99 + samples_log2, stride_floats=8)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, samples_log2)
+    wb = raster.getWorkBuffers(i.shape[0])
+    util.compare_setup(wb, util.gold_setup(v, i, w, h, "gouraud", 3, samples_log2), i.shape[0], 3)
+    _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, samples_log2), lsb=1)
+
+
+@pytest.mark.parametrize("shader,flags,samples_log2,blend", [
+    ("gouraud", 3, 0, "BlendSrcOver"), ("gouraud", 2, 0, "BlendSrcOver"), ("gouraud", 3, 0, "BlendAdditive"), ("gouraud", 3, 2, "BlendSrcOver"),
+    ("gouraud", 2, 2, "BlendSrcOver"), ("passthrough", 1, 0, "BlendDepthOnly"), ("gouraudDiscard", 3, 0, "BlendReplace"),
+    ("gouraudDiscard", 3, 2, "BlendReplace"), ("texPhong", 3, 0, "BlendReplace"), ("texPhong", 3, 2, "BlendReplace"), ("passthrough", 1, 2, "BlendReplace")])
+def test_blend_and_shader_variants(raster, crb, shader, flags, samples_log2, blend):
+    """Ordered blending, discard and the Phong pipe: submission order must be honoured exactly."""
+    w, h = 256, 192
+    v, i = crb.scenes.random_soup(5000, seed=4242, stride_floats=util.STRIDE[shader] // 4, size=0.5)
+    if shader.startswith("gouraud"):
+        v[:, 7] = np.random.default_rng(3).uniform(0.2, 1.0, v.shape[0]).astype(np.float32)  # alpha
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, shader, flags, samples_log2, blend)
+    g = util.draw_gold(v, i, w, h, shader, flags, samples_log2, blend)
+    _check_surfaces(cc, cd, g, lsb=0 if shader == "passthrough" else 1)
+
+
+def test_no_deferred_clear_accumulates(raster, crb):
+    """Without a deferred clear the previous surface contents persist and untouched tiles stay untouched."""
+    w, h = 320, 200
+    rng = np.random.default_rng(11)
+    rw, rh = (w + 7) & ~7, (h + 7) & ~7
+    init = (rng.integers(0, 2**32, (rh, rw), dtype=np.uint32), rng.integers(2**31, 2**32, (rh, rw), dtype=np.uint32))
+    v, i = crb.scenes.random_soup(3000, seed=8, stride_floats=8, size=0.3)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, clear=None, init=init)
+    g = util.draw_gold(v, i, w, h, "gouraud", 3, clear=None, init=init)
+    _check_surfaces(cc, cd, g, lsb=1)
+    assert (cc == init[0]).any() and (cc != init[0]).any()
+
+
+def test_odd_viewport_and_empty_draw(raster, crb):
+    """Viewport not a multiple of 8 (rounded surface), and a draw with zero triangles that only clears."""
+    w, h = 333, 257
+    v, i = crb.scenes.random_soup(4000, seed=21, stride_floats=8, size=0.4)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+    _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3), lsb=1)
+    cc, cd = util.draw_cuda(raster, crb, v, i[:0], w, h, "gouraud", 3)
+    assert (cc == 0xFFCC6633).all() and (cd == 0xFFFFBB3F).all()
+
+
+def test_sort_first_window_matches_full_frame(raster, crb):
+    """A frame rendered as four sub-viewports equals the same frame rendered whole (CUDA and oracle)."""
+    fw, fh = 512, 384
+    v, i = crb.scenes.random_soup(6000, seed=31, stride_floats=8, size=0.5)
+    full_c, full_d = util.draw_cuda(raster, crb, v, i, fw, fh, "gouraud", 3)
+    _check_surfaces(full_c, full_d, util.draw_gold(v, i, fw, fh, "gouraud", 3), lsb=1)
+    for (x0, y0, w, h) in [(0, 0, 256, 192), (256, 0, 256, 192), (0, 192, 256, 192), (256, 192, 256, 192)]:
+        cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0))
+        g = util.draw_gold(v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0))
+        _check_surfaces(cc, cd, g, lsb=1)
+        assert np.array_equal(cd, full_d[y0:y0 + h, x0:x0 + w])
+        assert np.array_equal(cc, full_c[y0:y0 + h, x0:x0 + w])
+    raster.setSubViewport(0, 0, 0, 0)
+
+
+def test_c2_reduced_and_host_entry(raster, crb):
+    """C2-style grid (reduced to 100k triangles) bit-exact, and the host-buffer entry returns the same frame."""
+    import torch
+    w, h = 1920, 1080
+    v, i = crb.scenes.grid_gouraud(250, 200)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+    g = util.draw_gold(v, i, w, h, "gouraud", 3)
+    _check_surfaces(cc, cd, g, lsb=1)
+    hv = torch.from_numpy(v).pin_memory()
+    hi = torch.from_numpy(i).pin_memory()
+    hc = torch.zeros((1080, 1920), dtype=torch.int32).pin_memory()
+    hd = torch.zeros((1080, 1920), dtype=torch.int32).pin_memory()
+    raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+    raster.drawTrianglesHost(hv, hi, i.shape[0], hc, hd)
+    assert np.array_equal(hc.numpy().view(np.uint32), cc) and np.array_equal(hd.numpy().view(np.uint32), cd)
+
+
+def test_c2_full_size_properties(raster, crb):
+    """BASELINE config 2 at full size (1M triangles, 1080p): depth bit-exact against the oracle
+    (8 host threads) and size-independent properties: idempotence, full coverage, counters."""
+    w, h = 1920, 1080
+    v, i = crb.scenes.grid_gouraud(1000, 500)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+    cc2, cd2 = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+    assert np.array_equal(cc, cc2) and np.array_equal(cd, cd2)           # deterministic / idempotent
+    assert (cd < 0xFFFFBB3F).all()                                        # the mesh covers the whole frame
+    c = raster.getCounters()
+    assert c["overflow"] == 0 and c["numActiveTiles"] == 240 * 135 and c["numTileEntries"] >= c["numBinEntries"] > 900000
+    g = util.draw_gold(v, i, w, h, "gouraud", 3)
+    _check_surfaces(cc, cd, g, lsb=1)
