@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native CudaRaster hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
+
+A "step" is one pass of the hot path (CudaRaster::drawTriangles: setup -> bin -> coarse -> fine,
+reference src/cudaraster/CudaRaster.cpp:237-342) over one synthetic frame.  Default workload is
+BASELINE.json configs[1] ("c2"): 1 M-triangle tessellated grid, Gouraud, depth test, 1920x1080.
+
+N = 1   the frame is rendered K times on cuda:0.
+N > 1   one process per GPU (torchrun); view-parallel sharding: every step each rank
+        renders ITS OWN view of the mesh and the colour frames are gathered to rank 0 with NCCL
+        (the composite is inside the timed region).  Weak scaling: per-GPU work is fixed.
+
+Prints ONE JSON line (rank 0).  Keys: see the task contract; additionally
+  stage_ms     median per-stage device time (the reference's five event positions)
+  roofline     dominant kernel: algorithmic bytes per launch / mean launch duration vs measured HBM peak
+  cpu_baseline the CPU oracle (oracle/golden.hpp) timed on this box's host cores on a bounded sample
+  ref_kernels  the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref), if they run here
+  e2e          the same metric through crb_draw_triangles_host (pinned HOST buffers, H2D + D2H inside)
+
+--impl reference times the CPU restatement of the path (the reference has no runnable CPU path of
+its own: its host emulators are broken in this port) with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, scene fn name, kwargs, width, height, shader, samplesLog2, flags, varyings)
+    "c2": ("C2: 1M-triangle tessellated grid, Gouraud, depth test, 1920x1080", "grid_gouraud", {"nx": 1000, "ny": 500}, 1920, 1080, "gouraud", 0, 3, 1),
+    "c3": ("C3: 5M-triangle 5-layer scene, Phong + procedural texture, 4x MSAA, 2048x2048", "layered_phong", {"nx": 1000, "ny": 500, "layers": 5}, 2048, 2048, "texPhong", 2, 3, 3),
+    "c4": ("C4: 10M sub-pixel triangles, PassThrough, depth test, 1920x1080", "subpixel_soup", {"num_tris": 10_000_000}, 1920, 1080, "passthrough", 0, 1, 0),
+}
+STAGES = ("triangleSetup", "binRaster", "coarseRaster", "fineRaster")
+NUM_INPUT_COPIES = 4  # inputs rotate over this many copies so that no step finds its inputs in L2
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_scene(workload):
+    import cudaraster_linux_b200 as crb
+    desc, fn, kw, w, h, shader, s_log2, flags, k_var = WORKLOADS[workload]
+    verts, idx = getattr(crb.scenes, fn)(**kw)
+    return desc, verts, idx, w, h, shader, s_log2, flags, k_var
+
+
+def stage_bytes(counts, num_tris, k_var, pixels, samples, lerp):
+    """Per-stage split of B_alg (DESIGN.md 'algorithmic bytes'); the four add up to B_alg."""
+    c = counts
+    t, tsub, v = num_tris, c["numSubtris"], c["vertsReferenced"]
+    return {
+        "triangleSetup": 12 * t + 16 * v + 1 * t + 80 * tsub,
+        "binRaster": 1 * t + 16 * tsub + 4 * c["eBin"],
+        "coarseRaster": (4 + 16) * c["eBin"] + 4 * c["eTile"],
+        "fineRaster": (4 + 16) * c["eTile"] + 16 * c["eCov"] + (48 * c["eShade"] if lerp else 0) + 16 * k_var * v + 8 * pixels * samples,
+    }
+
+
+def cpu_oracle_frame(verts, idx, w, h, shader, s_log2, flags, threads, want_counts):
+    from oracle import binding as G
+    from tests.util import STRIDE
+    cfg = G.make_config(w, h, s_log2, flags, STRIDE[shader], shader, "BlendReplace", clear=G.clear_values(), threads=threads)
+    t0 = time.perf_counter()
+    r = G.render(cfg, verts, idx, want_counts=want_counts)
+    return time.perf_counter() - t0, r
+
+
+def run_reference_arm(args):
+    """The CPU restatement of the path on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import binding as G
+    desc, verts, idx, w, h, shader, s_log2, flags, k_var = make_scene(args.workload)
+    threads = G.hardware_threads()
+    n = idx.shape[0]
+    # bounded sample: the first `sample_tris` triangles of the frame (whole frame when it is cheap)
+    sample = n if args.workload == "c2" else min(n, 1_000_000)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_frame(verts, idx[:sample], w, h, shader, s_log2, flags, threads, False)
+    times = [cpu_oracle_frame(verts, idx[:sample], w, h, shader, s_log2, flags, threads, False)[0] for _ in range(args.steps)]
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "frames_per_s": 1e3 / ms * (sample / n), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32",
+        "data": "synthetic", "config": {"workload": desc, "triangles": int(n), "resolution": [w, h]},
+        "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d triangles of the frame per step, all %d host threads (oracle/golden.hpp; the reference has no runnable CPU path)" % (sample, n, threads)},
+        "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def time_ref_kernels(workload, timeout=240):
+    """Times the reference's own CUDA kernels rebuilt for sm_100a in a SUBPROCESS (they are
+    implicitly warp-synchronous Fermi code and may hang or fault on Blackwell)."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so")
+    if not os.path.exists(lib):
+        return {"status": "not built"}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "7"],
+                           capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"status": "hang (killed after %d s)" % timeout}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {"status": "failed rc=%d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:].replace("\n", " | "))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-kernels", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import cudaraster_linux_b200 as crb
+    from cudaraster_linux_b200 import multigpu
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    desc, verts, idx, w, h, shader, s_log2, flags, k_var = make_scene(args.workload)
+    n_tris, n_samples = idx.shape[0], 1 << s_log2
+    raster = crb.CudaRaster(local)
+    color = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, n_samples, device=dev)
+    depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32, n_samples, device=dev)
+    raster.setSurfaces(color, depth)
+    raster.setPixelPipe(None, crb.pipe_name(shader, s_log2, flags, "BlendReplace"))
+
+    # view-parallel sharding: rank r renders view (step * world + r); N = 1 renders the identity view
+    views = crb.scenes.view_matrix_variants(48)
+    h_verts = torch.from_numpy(verts).pin_memory()
+    h_idx = torch.from_numpy(idx).pin_memory()
+    copies = []
+    for k in range(NUM_INPUT_COPIES):
+        vv = verts if world == 1 else crb.scenes.apply_view(verts, views[(k * world + rank) % len(views)])
+        copies.append((torch.from_numpy(vv).to(dev), torch.from_numpy(idx).to(dev)))
+    gather_list = [torch.empty_like(color.tensor) for _ in range(world)] if (world > 1 and rank == 0) else None
+    stream = torch.cuda.current_stream(dev)
+
+    def step(k):
+        vb, ib = copies[k % NUM_INPUT_COPIES]
+        raster.setVertexBuffer(vb, 0)
+        raster.setIndexBuffer(ib, 0, n_tris)
+        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+        raster.drawTriangles()
+        if world > 1:
+            multigpu.gather_frames(color.tensor, gather_list, dst=0)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(args.warmup):
+        step(k)
+    sync_all()
+    launches_per_frame = raster.getLaunchCount()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_times = {s: [] for s in STAGES}
+    sync_all()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(k)
+        st = raster.getStats()  # the draw has already synchronised (counter read-back), this costs nothing
+        for s, key in zip(STAGES, ("setupTime", "binTime", "coarseTime", "fineTime")):
+            stage_times[s].append(st[key] * 1e3)
+    e1.record(stream)
+    sync_all()
+    clocks = sampler.result()
+    total_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n_tris / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer entry (pinned host memory in, colour frame out) ----------------
+    h_color = torch.zeros_like(color.tensor, device="cpu").pin_memory()
+    for _ in range(2):
+        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+        raster.drawTrianglesHost(h_verts, h_idx, n_tris, h_color)
+    sync_all()
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+        raster.drawTrianglesHost(h_verts, h_idx, n_tris, h_color)
+    e1.record(stream)
+    sync_all()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    h2d = h_verts.numel() * 4 + h_idx.numel() * 4
+    d2h = h_color.numel() * 4
+
+    if rank == 0:
+        med = {s: statistics.median(v) for s, v in stage_times.items()}
+        mean = {s: sum(v) / len(v) for s, v in stage_times.items()}
+        line = {
+            "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "frames_per_s": world * 1e3 / ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
+            "config": {"workload": desc, "triangles": int(n_tris), "resolution": [w, h], "samples": n_samples, "pipe": crb.pipe_name(shader, s_log2, flags, "BlendReplace"),
+                       "sharding": "1 GPU" if world == 1 else "view-parallel: 1 view per rank per step, colour frames gathered to rank 0 over NCCL inside the timed region",
+                       "l2": "inputs rotate over %d device copies (%.0f MB) and each frame rewrites ~100 MB of intermediates, > 126 MB L2" %
+                             (NUM_INPUT_COPIES, NUM_INPUT_COPIES * (verts.nbytes + idx.nbytes) / 1e6)},
+            "stage_ms": med, "device_frame_ms": sum(med.values()), "gpu_launches": launches_per_frame * args.steps, "clocks": clocks,
+            "e2e": {"value": world * n_tris / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "crb_draw_triangles_host (pinned host vertices+indices in, colour surface out)"},
+        }
+        # ---- CPU oracle: baseline + algorithmic byte counts (bounded: one frame on all host threads) -------
+        counts = None
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import binding as G
+            threads = G.hardware_threads()
+            sample = n_tris if args.workload == "c2" else min(n_tris, 1_000_000)
+            t, r = cpu_oracle_frame(verts, idx[:sample], w, h, shader, s_log2, flags, threads, True)
+            line["cpu_baseline"] = {"value": sample / t / 1e6, "unit": "Mtris/s", "cores": threads, "kind": "port",
+                                    "sample": "%d of %d triangles, one frame, oracle/golden.hpp on %d host threads (%.2f s)" % (sample, n_tris, threads, t)}
+            if sample == n_tris:
+                counts = r["counts"]
+        peak, peak_src = measured_peak()
+        if counts is not None:
+            sb = stage_bytes(counts, n_tris, k_var, ((w + 7) & ~7) * ((h + 7) & ~7), n_samples, bool(flags & 2))
+            dom = max(STAGES, key=lambda s: mean[s])
+            ach = sb[dom] / (mean[dom] * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                "peak_source": peak_src, "algorithmic_bytes_per_launch": sb[dom], "launch_ms": mean[dom]}
+            b_alg = sum(sb.values())
+            line["frame_roofline"] = {"algorithmic_bytes": b_alg, "achieved": b_alg / (sum(mean.values()) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": b_alg / (sum(mean.values()) * 1e-3) / 1e9 / peak,
+                                      "stages": {s: {"bytes": sb[s], "ms": mean[s], "GB/s": sb[s] / (mean[s] * 1e-3) / 1e9} for s in STAGES}}
+            prof = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(prof):
+                try:
+                    line["roofline"]["traffic"] = json.load(open(prof)).get(args.workload, {}).get(dom)
+                except Exception:
+                    pass
+        if not args.no_ref_kernels and world == 1:
+            line["ref_kernels"] = time_ref_kernels(args.workload)
+        print(json.dumps(line))
+    raster.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -80,6 +80,7 @@ def load_library():
         "crb_get_profiling_info": (i32, [vp, ctypes.c_char_p, ctypes.c_size_t]),
         "crb_get_launch_count": (i32, [vp]),
         "crb_get_work_buffers": (i32, [vp, ctypes.POINTER(WorkBuffers)]),
+        "crb_download": (i32, [vp, vp, vp, ctypes.c_size_t]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -92,7 +93,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_host", "crb_get_stats", "crb_get_counters",
-                    "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers"]
+                    "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download"]
 
 
 def pipe_name(base, samples_log2, flags, blend="BlendReplace"):
@@ -252,12 +253,9 @@ class CudaRaster:
         return self.lib.crb_get_launch_count(self.ctx)
 
     def _dev_to_numpy(self, ptr, nbytes, dtype):
-        out = self.torch.empty(nbytes, dtype=self.torch.uint8, device="cuda:%d" % self.device)
-        cudart = self.torch.cuda.cudart()
-        rc = cudart.cudaMemcpy(out.data_ptr(), ptr, nbytes, 3)  # device to device
-        if int(rc) != 0:
-            raise CrbError("cudaMemcpy failed: %s" % rc)
-        return out.cpu().numpy().view(dtype)
+        out = np.empty(nbytes, np.uint8)
+        self._check(self.lib.crb_download(self.ctx, ptr, out.ctypes.data, nbytes))
+        return out.view(dtype)
 
     def getWorkBuffers(self, num_tris):
         """Downloads setup output and the bin/tile queues (parity tests)."""

@@ -61,6 +61,7 @@ struct crb_ctx {
     size_t vertexBytes = 0;
     const int32_t* indices = nullptr;
     int numTris = 0;
+    bool verticesSet = false, indicesSet = false;  // an EMPTY buffer is still a buffer (CudaRaster.cpp:220-233)
     bool hasPipe = false;
     crb_pipe_desc pipe{};
     crb_pipe_spec spec{};
@@ -220,8 +221,8 @@ int validateDraw(crb_ctx* c) {
     // same checks, same order, same messages as CudaRaster::drawTriangles (CudaRaster.cpp:243-260)
     if (!c->color) return setError(c, CRB_ERR_INVALID, "CudaRaster: Surfaces not set!");
     if (!c->hasPipe) return setError(c, CRB_ERR_INVALID, "CudaRaster: Pixel pipe not set!");
-    if (!c->vertices) return setError(c, CRB_ERR_INVALID, "CudaRaster: Vertex buffer not set!");
-    if (!c->indices) return setError(c, CRB_ERR_INVALID, "CudaRaster: Index buffer not set!");
+    if (!c->verticesSet || (!c->vertices && c->numTris > 0)) return setError(c, CRB_ERR_INVALID, "CudaRaster: Vertex buffer not set!");
+    if (!c->indicesSet || (!c->indices && c->numTris > 0)) return setError(c, CRB_ERR_INVALID, "CudaRaster: Index buffer not set!");
     if (c->spec.samplesLog2 != c->samplesLog2) return setError(c, CRB_ERR_INVALID, "CudaRaster: Mismatch in multisampling between pixel pipe and surface!");
     if ((c->spec.renderModeFlags & CRB_FLAG_QUADS) != 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: RenderModeFlag_EnableQuads is not supported by the B200 pipeline yet!");
     return CRB_OK;
@@ -355,6 +356,7 @@ int crb_set_vertex_buffer(crb_ctx* c, const void* d_vertices, size_t bytes) {
     if (!c) return CRB_ERR_INVALID;
     c->vertices = d_vertices;
     c->vertexBytes = bytes;
+    c->verticesSet = d_vertices != nullptr || bytes == 0;
     return CRB_OK;
 }
 
@@ -363,6 +365,7 @@ int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
     if (numTris < 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: negative triangle count!");
     c->indices = (const int32_t*)d_indices;
     c->numTris = numTris;
+    c->indicesSet = d_indices != nullptr || numTris == 0;
     return CRB_OK;
 }
 
@@ -437,6 +440,7 @@ int crb_draw_triangles_host(crb_ctx* c, const void* h_vertices, size_t vertexByt
     c->vertexBytes = vertexBytes;
     c->indices = (const int32_t*)c->hostIdx.ptr;
     c->numTris = numTris;
+    c->verticesSet = c->indicesSet = true;
     int rc = crb_draw_triangles(c, stream);
     if (rc != CRB_OK) return rc;
     const size_t surfBytes = (size_t)c->frame.surfacePitch * c->frame.heightPixels * 4;
@@ -514,6 +518,14 @@ int crb_get_work_buffers(crb_ctx* c, crb_work_buffers* out) {
     out->tileCount = f.tileCount;
     out->numTiles = f.numTiles;
     out->activeTiles = f.activeTiles;
+    return CRB_OK;
+}
+
+int crb_download(crb_ctx* c, const void* d_src, void* h_dst, size_t bytes) {
+    if (!c || (bytes && (!d_src || !h_dst))) return CRB_ERR_INVALID;
+    CRB_CUDA(c, cudaSetDevice(c->device));
+    CRB_CUDA(c, cudaDeviceSynchronize());
+    CRB_CUDA(c, cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
     return CRB_OK;
 }
 

@@ -1,0 +1,123 @@
+"""Multi-GPU sharding of the hot path (new design; the reference is single-GPU).
+
+One process per GPU, `torch.distributed` for the plumbing (NCCL over NVLink on the GPU box, gloo in
+the CPU tests).  Work is partitioned only where it shards naturally:
+
+* sort-first   a large frame is cut into a grid of rectangles (multiples of 8 px, each <= 2048 px --
+               the reference's viewport limit, cuda/Constants.hpp:21); rank r renders the rectangles
+               ``rects[r::world]`` through ``CudaRaster.setSubViewport`` with the geometry replicated.
+* view-parallel independent views (cube-map faces, shadow cascades) go round-robin over the ranks.
+
+The only exchange step is the composite: disjoint framebuffer rectangles (or whole frames) are
+gathered to the display rank.  No reduction operator is needed because regions are disjoint.
+"""
+import math
+
+MAX_VIEWPORT = 2048
+
+
+def grid_for(parts):
+    """(columns, rows) of the sort-first grid for `parts` rectangles: 1x1, 2x1, 2x2, 4x2, 4x4, ..."""
+    if parts < 1 or parts & (parts - 1):
+        raise ValueError("the number of sort-first parts must be a power of two")
+    lg = parts.bit_length() - 1
+    return 1 << ((lg + 1) // 2), 1 << (lg // 2)
+
+
+def min_parts(full_w, full_h):
+    """Fewest power-of-two parts whose rectangles respect the 2048 px viewport limit."""
+    parts = 1
+    while True:
+        cols, rows = grid_for(parts)
+        if _cell(full_w, cols) <= MAX_VIEWPORT and _cell(full_h, rows) <= MAX_VIEWPORT:
+            return parts
+        parts *= 2
+
+
+def _cell(full, n):
+    return (-(-full // n) + 7) & ~7
+
+
+def split_frame(full_w, full_h, parts):
+    """Cuts the frame into `parts` rectangles (x0, y0, w, h); origins are multiples of 8, rectangles
+    tile the frame exactly, row-major order."""
+    parts = max(parts, min_parts(full_w, full_h))
+    cols, rows = grid_for(parts)
+    cw, ch = _cell(full_w, cols), _cell(full_h, rows)
+    rects = []
+    for r in range(rows):
+        for c in range(cols):
+            x0, y0 = c * cw, r * ch
+            w, h = min(cw, full_w - x0), min(ch, full_h - y0)
+            if w > 0 and h > 0:
+                rects.append((x0, y0, w, h))
+    return rects
+
+
+def rects_of_rank(rects, rank, world):
+    """Rectangles rank `rank` renders (round robin keeps neighbours on different GPUs)."""
+    return [(i, r) for i, r in enumerate(rects) if i % world == rank]
+
+
+def views_of_rank(num_views, rank, world):
+    """View indices rank `rank` renders."""
+    return list(range(rank, num_views, world))
+
+
+def gather_frames(frame, gather_list, dst=0):
+    """Gathers one equally sized frame per rank to `dst` (NCCL gather over NVLink / gloo)."""
+    import torch.distributed as dist
+    dist.gather(frame, gather_list if dist.get_rank() == dst else None, dst=dst)
+
+
+def composite_sort_first(local_rects, local_tiles, full_w, full_h, num_rects, dst=0, out=None):
+    """Composites sort-first rectangles on rank `dst`.
+
+    local_rects  [(index, (x0, y0, w, h))] this rank rendered, local_tiles the matching 2-D U32/int32
+    tensors (rows >= h, cols >= w: rounded surfaces are accepted).  Every rank must own the same
+    number of rectangles (pad with empty work otherwise).  Returns the [full_h, full_w] frame on
+    `dst`, None elsewhere.  Rectangles are disjoint, so the composite is a pure gather + paste.
+    """
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per_rank = math.ceil(num_rects / world)
+    assert len(local_rects) <= per_rank
+    rects_all = [None] * world
+    dist.all_gather_object(rects_all, [(i, tuple(r)) for i, r in local_rects])
+    cw = max(r[2] for rr in rects_all for _, r in rr)
+    ch = max(r[3] for rr in rects_all for _, r in rr)
+    dev, dt = local_tiles[0].device, local_tiles[0].dtype
+    send = torch.zeros((per_rank, ch, cw), dtype=dt, device=dev)
+    for k, ((_, (x0, y0, w, h)), t) in enumerate(zip(local_rects, local_tiles)):
+        send[k, :h, :w] = t[:h, :w]
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst)
+    if rank != dst:
+        return None
+    if out is None:
+        out = torch.zeros((full_h, full_w), dtype=dt, device=dev)
+    for r in range(world):
+        for k, (_, (x0, y0, w, h)) in enumerate(rects_all[r]):
+            out[y0:y0 + h, x0:x0 + w] = recv[r][k, :h, :w]
+    return out
+
+
+def render_sort_first(raster, crb, vb, ib, num_tris, full_w, full_h, pipe, rects, clear=((0.2, 0.4, 0.8, 1.0), 1.0), samples=1, device=None):
+    """Renders this rank's rectangles of a full_w x full_h frame; returns [(index, rect)], [colour tensors], [depth tensors]."""
+    out_c, out_d = [], []
+    for _, (x0, y0, w, h) in rects:
+        color = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, samples, device=device or "cuda:%d" % raster.device)
+        depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32, samples, device=device or "cuda:%d" % raster.device)
+        raster.setSurfaces(color, depth)
+        raster.setPixelPipe(None, pipe)
+        raster.setVertexBuffer(vb, 0)
+        raster.setIndexBuffer(ib, 0, num_tris)
+        raster.setSubViewport(full_w, full_h, x0, y0)
+        if clear is not None:
+            raster.deferredClear(*clear)
+        raster.drawTriangles()
+        out_c.append(color.tensor)
+        out_d.append(depth.tensor)
+    raster.setSubViewport(0, 0, 0, 0)
+    return rects, out_c, out_d

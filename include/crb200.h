@@ -165,6 +165,9 @@ typedef struct crb_work_buffers {
     const int32_t* activeTiles;  /* [numActiveTiles]                                   */
 } crb_work_buffers;
 int crb_get_work_buffers(crb_ctx* ctx, crb_work_buffers* out); /* device pointers, valid until the next draw */
+/* Buffer::getPtr() of the reference (gpu/Buffer.cpp:235-346: device -> host mirror): blocking copy of
+ * `bytes` bytes of device memory (a work buffer or a surface) into host memory. */
+int crb_download(crb_ctx* ctx, const void* d_src, void* h_dst, size_t bytes);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,90 @@
+"""Runs the REFERENCE's own CUDA kernels, rebuilt for sm_100a (oracle/_ref/libcrref_cuda.so, built by
+oracle/Makefile from the sources under /root/reference), on one of the benchmark workloads.
+TEST / BASELINE INFRASTRUCTURE -- never imported by the product.
+
+Meant to be run as a subprocess with a timeout: the Fermi code is implicitly warp-synchronous
+ and can hang or fault on Blackwell.  Prints one JSON line:
+  {"status": "ok"|"mismatch"|..., "stage_ms": {...}, "frame_ms": ..., "Mtris/s": ..., "depth_mismatch_texels": n, ...}
+
+    python oracle/run_ref_kernels.py --workload c2 [--frames 7] [--check]
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def load():
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so"))
+    vp = ctypes.c_void_p
+    lib.crref_last_error.restype = ctypes.c_char_p
+    lib.crref_pipe_name.restype = ctypes.c_char_p
+    lib.crref_draw.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                               ctypes.c_uint32, ctypes.c_uint32, vp, vp]
+    lib.crref_get_setup_output.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    return lib
+
+
+def draw(lib, pipe, verts, idx, w, h, samples_log2, clear=(0xFFCC6633, 0xFFFFBB3F), frames=1):
+    """Renders `frames` times; returns (color, depth, [stage seconds per frame], atomics)."""
+    import torch
+    n = 1 << samples_log2
+    rw, rh = (w + 7) & ~7, (h + 7) & ~7
+    vb = torch.from_numpy(np.ascontiguousarray(verts, np.float32)).cuda()
+    ib = torch.from_numpy(np.ascontiguousarray(idx, np.int32)).cuda()
+    color = torch.zeros((rh, rw * n), dtype=torch.int32, device="cuda")
+    depth = torch.zeros((rh, rw * n), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    times, atomics = [], (ctypes.c_int * 7)()
+    for _ in range(frames):
+        st = (ctypes.c_float * 4)()
+        rc = lib.crref_draw(pipe.encode(), vb.data_ptr(), vb.numel() * 4, ib.data_ptr(), idx.shape[0], color.data_ptr(), depth.data_ptr(), w, h, n,
+                            1, clear[0], clear[1], st, atomics)
+        if rc != 0:
+            raise RuntimeError("crref_draw: " + lib.crref_last_error().decode())
+        times.append(list(st))
+    torch.cuda.synchronize()
+    return color.cpu().numpy().view(np.uint32), depth.cpu().numpy().view(np.uint32), times, list(atomics)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--frames", type=int, default=7)
+    ap.add_argument("--check", action="store_true", help="compare depth/colour with the CPU oracle")
+    args = ap.parse_args()
+    import bench
+    desc, verts, idx, w, h, shader, s_log2, flags, _ = bench.make_scene(args.workload)
+    pipe = "ref_%s_s%d_f%d_BlendReplace" % (shader, s_log2, flags)
+    lib = load()
+    names = [lib.crref_pipe_name(i).decode() for i in range(lib.crref_num_pipes())]
+    if pipe not in names:
+        print(json.dumps({"status": "no reference pipe %s (the reference ships no such shader)" % pipe}))
+        return 0
+    color, depth, times, atomics = draw(lib, pipe, verts, idx, w, h, s_log2, frames=args.frames)
+    steady = times[2:] if len(times) > 3 else times
+    med = [statistics.median(t[i] for t in steady) * 1e3 for i in range(4)]
+    out = {"status": "ok", "what": "reference kernels rebuilt for sm_100a behind oracle/ref_kernels/shim.h, launch shapes of CudaRaster.cpp:593-655",
+           "stage_ms": dict(zip(("triangleSetup", "binRaster", "coarseRaster", "fineRaster"), med)), "frame_ms": sum(med),
+           "Mtris/s": idx.shape[0] / (sum(med) * 1e-3) / 1e6, "atomics": atomics}
+    if args.check:
+        from tests import util
+        g = util.draw_gold(verts, idx, w, h, shader, flags, s_log2)
+        out["depth_mismatch_texels"] = int((depth != g["depth"]).sum())
+        out["color_max_lsb"] = util.color_max_diff(color, g["color"])
+        out["color_mismatch_texels"] = int((color != g["color"]).sum())
+        if out["depth_mismatch_texels"]:
+            out["status"] = "mismatch"
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -114,7 +114,7 @@ def test_no_deferred_clear_accumulates(raster, crb):
     rng = np.random.default_rng(11)
     rw, rh = (w + 7) & ~7, (h + 7) & ~7
     init = (rng.integers(0, 2**32, (rh, rw), dtype=np.uint32), rng.integers(2**31, 2**32, (rh, rw), dtype=np.uint32))
-    v, i = crb.scenes.random_soup(3000, seed=8, stride_floats=8, size=0.3)
+    v, i = crb.scenes.random_soup(300, seed=8, stride_floats=8, size=0.15)
     cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, clear=None, init=init)
     g = util.draw_gold(v, i, w, h, "gouraud", 3, clear=None, init=init)
     _check_surfaces(cc, cd, g, lsb=1)
