@@ -171,12 +171,85 @@ __device__ __forceinline__ U32 fineRefill(const crb_frame& f, FineTriRec* recs, 
 }
 
 //------------------------------------------------------------------------------------------------
+// Coverage helpers shared by the single- and multi-sample kernels.
+//------------------------------------------------------------------------------------------------
+
+// 32x32 bit-matrix transpose across the warp: lane j passes row j (bit i = element (j, i)),
+// lane i receives column i (bit j = element (j, i)).  Five butterfly stages of one shuffle each.
+__device__ __forceinline__ U32 warpTranspose32(U32 x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const U32 lo = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const U32 o = __shfl_xor_sync(0xFFFFFFFFu, x, s);
+        x = (lane & s) ? ((x & ~lo) | ((o >> s) & lo)) : ((x & lo) | ((o << s) & ~lo));
+    }
+    return x;
+}
+
+// 64-bit coverage of one 8x8 tile for edge equations given relative to the centre of pixel
+// (0,0) of the tile, E_i(sx, sy) = c_i + a_i*sx + b_i*sy with (sx, sy) = 16 * (x, y).  Bit x + 8y.
+// Exact (integer arithmetic, the tie rule is folded into c_i).  Only rows [rowLo, rowHi] are
+// visited, so the cost follows the triangle's height inside the tile; SampleOfs shifts the
+// sample point (used by the MSAA kernel to build its conservative pixel mask).
+__device__ __forceinline__ void coverTileRows(const S32 (&a)[3], const S32 (&b)[3], const S32 (&c)[3], int rowLo, int rowHi, U32& maskLo, U32& maskHi) {
+    maskLo = 0; maskHi = 0;
+    const S32 a0 = a[0] << CR_SUBPIXEL_LOG2, a1 = a[1] << CR_SUBPIXEL_LOG2, a2 = a[2] << CR_SUBPIXEL_LOG2;
+#pragma unroll 1
+    for (int r = rowLo; r <= rowHi; r++) {
+        // start at column 7 and walk left so that the funnel shift leaves column 0 in bit 0
+        S32 e0 = c[0] + b[0] * (r << CR_SUBPIXEL_LOG2) + a0 * 7;
+        S32 e1 = c[1] + b[1] * (r << CR_SUBPIXEL_LOG2) + a1 * 7;
+        S32 e2 = c[2] + b[2] * (r << CR_SUBPIXEL_LOG2) + a2 * 7;
+        U32 row = 0;
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            row = __funnelshift_l(~(U32)(e0 | e1 | e2), row, 1);   // row = row << 1 | inside
+            e0 -= a0; e1 -= a1; e2 -= a2;
+        }
+        if (r < 4) maskLo |= row << (8 * r);
+        else maskHi |= row << (8 * (r - 4));
+    }
+}
+
+// One queued sub-triangle as the refill stage fetched it.
+struct FineFetch {
+    S32 entry;     // triIdx*8 + sub, < 0 = none
+    S32 dataIdx;
+    uint4 h;       // CRTriangleHeader
+    uint4 z;       // first row of CRTriangleData (zx, zy, zb, zslope)
+};
+
+template <U32 RenderModeFlags>
+__device__ __forceinline__ void fineFetch(FineFetch& t, const crb_frame& f, S32 entry) {
+    t.entry = entry;
+    if (entry < 0) return;
+    t.dataIdx = resolveDataIdx(entry, f.triHeader);
+    t.h = __ldg(&f.triHeader[t.dataIdx]);
+    if ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0) t.z = __ldg(&f.triData[(size_t)t.dataIdx * 4]);
+}
+
+// Per-warp staging of the current batch, lane-indexed SoA: the per-fragment gathers of the
+// ownership loop hit distinct banks for distinct triangles and broadcast for equal ones.
+struct FineBatch {
+    U32 zx[32], zy[32], zb[32];
+    S32 entry[32];
+    S32 dataIdx[32];
+};
+
+//------------------------------------------------------------------------------------------------
 // Single-sample kernel.
+//
+// Per batch of <= 32 queue entries:  (1) lane j builds the exact 64-bit coverage mask of triangle j
+// (early-Z against the tile's max depth first);  (2) two warp transposes turn the 32 masks into,
+// for every lane, the set of triangles covering each of its two pixels;  (3) every lane walks its
+// own pixels' sets in queue order: depth test, winner update (or shade + blend in place).
+// Work is proportional to fragments, not to triangles x 64 pixels, and fragments of one pixel
+// are still applied by one thread in submission order.
 //------------------------------------------------------------------------------------------------
 
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
 __global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
-    __shared__ __align__(16) FineTriRec s_recs[CRB_FINE_WARPS][32];
+    __shared__ FineBatch s_batch[CRB_FINE_WARPS];
 
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,11 +260,17 @@ __global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(co
     BlendShaderClass blendProbe;
     const bool deferred = !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
 
-    FineTriRec* recs = s_recs[warp];
+    FineBatch& sb = s_batch[warp];
     const int tileIdx = __ldg(&f.activeTiles[activeIdx]);
     const int tileY = tileIdx / f.widthTiles, tileX = tileIdx - tileY * f.widthTiles;
     const int queueStart = __ldg(&f.tileStart[tileIdx]);
     const int queueCount = __ldg(&f.tileCount[tileIdx]);
+    const S32* __restrict__ queue = f.tileQueue + queueStart;
+
+    // software pipeline: entries two batches ahead, header + depth plane one batch ahead
+    S32 entryB = (32 + lane < queueCount) ? __ldg(&queue[32 + lane]) : -1;
+    FineFetch cur;
+    fineFetch<RenderModeFlags>(cur, f, lane < queueCount ? __ldg(&queue[lane]) : -1);
 
     // this lane's two pixels: (lx, ly) and (lx, ly + 4)
     const int lx = lane & 7, ly = lane >> 3;
@@ -202,7 +281,7 @@ __global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(co
     const size_t rowStep = (size_t)4 * f.surfacePitch;
 
     U32 color[2], depth[2];
-    int winner[2] = {0, 0};   // 1-based position in this tile's queue of the visible fragment (deferred mode)
+    S32 winner[2] = {-1, -1};   // queue entry of the visible fragment (deferred mode)
     if (f.deferredClear) {
         color[0] = color[1] = f.clearColor;
         depth[0] = depth[1] = f.clearDepth;
@@ -211,63 +290,82 @@ __global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(co
         depth[0] = kDepth ? depthPtr[0] : 0u; depth[1] = kDepth ? depthPtr[rowStep] : 0u;
     }
 
-    const S32 sx = lx << CR_SUBPIXEL_LOG2;
-    const S32 sy[2] = {ly << CR_SUBPIXEL_LOG2, (ly + 4) << CR_SUBPIXEL_LOG2};
+    // sample-space origin: centre of pixel (0,0) of the tile, viewport-centred subpixels
+    const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1));
+    const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1));
 
     for (int base = 0; base < queueCount; base += 32) {
-        U32 liveMask = fineRefill<0, RenderModeFlags>(f, recs, queueStart + base, queueCount - base, tileX, tileY);
-        while (liveMask) {
-            const int j = __ffs(liveMask) - 1;
-            liveMask &= liveMask - 1;
-            const uint4 r0 = reinterpret_cast<const uint4*>(&recs[j])[0];
-            const uint4 r1 = reinterpret_cast<const uint4*>(&recs[j])[1];
-            const uint4 r2 = reinterpret_cast<const uint4*>(&recs[j])[2];
-            // edge values at pixel 0, pixel 1 is 4 rows (64 subpixels) further along y
-            const S32 e0 = (S32)r0.z + (S32)r0.x * sx + (S32)r0.y * sy[0];
-            const S32 e1 = (S32)r1.y + (S32)r0.w * sx + (S32)r1.x * sy[0];
-            const S32 e2 = (S32)r2.x + (S32)r1.z * sx + (S32)r1.w * sy[0];
-            const S32 g0 = e0 + (S32)r0.y * 64, g1 = e1 + (S32)r1.x * 64, g2 = e2 + (S32)r1.w * 64;
-            const bool in[2] = {(e0 | e1 | e2) >= 0, (g0 | g1 | g2) >= 0};
-            if (!(in[0] | in[1])) continue;
-            const U32 z0 = r2.w + r2.y * (U32)lx + r2.z * (U32)ly;
-            const U32 z[2] = {z0, z0 + (r2.z << 2)};
+        // ---- issue the loads of the batches ahead
+        FineFetch nxt;
+        fineFetch<RenderModeFlags>(nxt, f, entryB);
+        entryB = (base + 64 + lane < queueCount) ? __ldg(&queue[base + 64 + lane]) : -1;
+
+        // ---- (1) lane j: coverage mask of triangle j
+        U32 tileZMax = 0xFFFFFFFFu;
+        if (kDepth) tileZMax = __reduce_max_sync(0xFFFFFFFFu, max(depth[0], depth[1]));
+        U32 maskLo = 0, maskHi = 0;
+        if (cur.entry >= 0 && (!kDepth || (cur.h.w & 0xFFFFF000u) < tileZMax)) {
+            const S32 y0 = (S32)cur.h.x >> 16, y1 = (S32)cur.h.y >> 16, y2 = (S32)cur.h.z >> 16;
+            const int rowLo = max((min(min(y0, y1), y2) - by + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0);
+            const int rowHi = min((max(max(y0, y1), y2) - by) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
+            S32 a[3], b[3], c[3];
+            setupTileEdges(cur.h, bx, by, a, b, c);
+            coverTileRows(a, b, c, rowLo, rowHi, maskLo, maskHi);
+        }
+        if (kDepth) {
+            sb.zx[lane] = cur.z.x; sb.zy[lane] = cur.z.y;
+            sb.zb[lane] = cur.z.z + cur.z.x * (U32)(tileX << CR_TILE_LOG2) + cur.z.y * (U32)(tileY << CR_TILE_LOG2);
+        }
+        sb.entry[lane] = cur.entry;
+        sb.dataIdx[lane] = cur.dataIdx;
+        __syncwarp();
+
+        // ---- (2) transpose: triangles covering this lane's two pixels
+        const U32 cover[2] = {warpTranspose32(maskLo, lane), warpTranspose32(maskHi, lane)};
+
+        // ---- (3) ownership loop, queue order
 #pragma unroll
-            for (int p = 0; p < 2; p++) {
-                if (!in[p]) continue;
-                if (kDepth && z[p] >= depth[p]) continue;
+        for (int p = 0; p < 2; p++) {
+            U32 w = cover[p];
+            while (w) {
+                const int j = __ffs(w) - 1;
+                w &= w - 1;
+                U32 z = 0;
+                if (kDepth) {
+                    z = sb.zb[j] + sb.zx[j] * (U32)lx + sb.zy[j] * (U32)(ly + 4 * p);
+                    if (z >= depth[p]) continue;
+                }
                 if (deferred) {
-                    if (kDepth) depth[p] = z[p];
-                    winner[p] = base + j + 1;
+                    if (kDepth) depth[p] = z;
+                    winner[p] = sb.entry[j];
                 } else {
-                    const uint4 r3 = reinterpret_cast<const uint4*>(&recs[j])[3];
+                    const S32 entry = sb.entry[j];
                     FragmentShaderClass fs;
-                    runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, (int)r3.y, (int)r3.x, pixelX, pixelY0 + 4 * p, 0x11u);
+                    runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, entry >> 3, sb.dataIdx[j], pixelX, pixelY0 + 4 * p, 0x11u);
                     if (fs.m_discard) continue;
-                    if (kDepth) depth[p] = z[p];
+                    if (kDepth) depth[p] = z;
                     BlendShaderClass bs;
-                    runBlendShader(bs, (int)r3.y, pixelX, pixelY0 + 4 * p, 0, fs.m_color, color[p]);
+                    runBlendShader(bs, entry >> 3, pixelX, pixelY0 + 4 * p, 0, fs.m_color, color[p]);
                     if (bs.m_writeColor) color[p] = bs.m_color;
                 }
             }
         }
         __syncwarp();
+        cur = nxt;
     }
 
     if (deferred) {
         // shade only the visible fragment of each pixel
-#pragma unroll 1
+#pragma unroll
         for (int p = 0; p < 2; p++) {
-            const int win = p == 0 ? winner[0] : winner[1];
-            if (win == 0) continue;
-            const S32 entry = __ldg(&f.tileQueue[queueStart + win - 1]);
+            const S32 entry = winner[p];
+            if (entry < 0) continue;
             const S32 dataIdx = resolveDataIdx(entry, f.triHeader);
             FragmentShaderClass fs;
             runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, entry >> 3, dataIdx, pixelX, pixelY0 + 4 * p, 0x11u);
             BlendShaderClass bs;
             runBlendShader(bs, entry >> 3, pixelX, pixelY0 + 4 * p, 0, fs.m_color, 0u);
-            if (bs.m_writeColor) {
-                if (p == 0) color[0] = bs.m_color; else color[1] = bs.m_color;
-            }
+            if (bs.m_writeColor) color[p] = bs.m_color;
         }
     }
 
