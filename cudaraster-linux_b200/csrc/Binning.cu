@@ -10,21 +10,28 @@
 // B200 design: sort-middle is a stable two-digit MSD radix sort with key expansion
 // (triangle -> bins, bin entry -> tiles).  Each digit is a count / scan / scatter:
 //
-//   bin stage     count   : fused into triangle setup (one column of binCountMat per chunk)
-//                 scan    : binScanKernel      one CTA per bin, exclusive scan over chunks,
-//                                              bin base from one atomicAdd, emits coarse work items
-//                 scatter : binScatterKernel   one CTA per chunk; warp-ballot masks give every
-//                                              (triangle, bin) pair its stable rank
-//   coarse stage  count   : coarseCountKernel  one CTA per work item (<= CRB_ITEM_ENTRIES entries
-//                                              of one bin), shared-memory tile histogram
+//   bin stage     count   : fused into triangle setup (one row of binCountMat per chunk of
+//                                              f.chunkTris consecutive triangles)
+//                 scan    : binScanKernel      one CTA per bin: block scan over the chunks, bin base
+//                                              from one atomicAdd, emits the coarse work items
+//                 scatter : binScatterKernel   ONE WARP per chunk, no block barriers
+//   coarse stage  count   : fused into binScatterKernel: when an entry receives its slot in the
+//                                              bin queue, its coarse work item (CRB_ITEM_ENTRIES
+//                                              consecutive entries of one bin) is known, and the
+//                                              tiles it touches are counted with global reductions
 //                 scan    : coarseScanKernel   one CTA per bin, scan over the bin's items and its
 //                                              256 tiles, tile-queue base from one atomicAdd,
-//                                              active-tile list
-//                 scatter : coarseScatterKernel same ballot-rank scheme at tile granularity
+//                                              active-tile records for the fine stage
+//                 scatter : coarseScatterKernel one warp per work item
+//
+// The scatter passes are warp-synchronous: a batch is 32 consecutive entries, one per lane; every
+// lane ORs its lane bit into a warp-private shared-memory word per cell it touches, and the rank
+// of an entry inside a cell is the popcount of the lower lanes in that word -- stable by
+// construction, any number of cells per entry, three __syncwarp per batch and no __syncthreads.
 //
 // Queues are dense CSR arrays (binQueue/binStart/binTotal, tileQueue/tileStart/tileCount): order
 // inside a bin/tile is submission order BY CONSTRUCTION (chunks and items are concatenated in
-// order, ranks inside a CTA come from ordered ballots), every SM participates, and the fine
+// order, batches and lanes inside a warp are in order), every SM participates, and the fine
 // stage reads contiguous runs instead of chasing segment pointers.
 #include <cuda_runtime.h>
 
@@ -34,58 +41,148 @@ using namespace FW;
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kWarps = 8;              // warps per CTA of the warp-centric kernels
+constexpr int kThreads = kWarps * 32;
+constexpr int kScanThreads = 256;      // binScanKernel
+constexpr int kCells = 256;            // CR_MAXBINS_SQR == CR_BIN_SQR
+constexpr int kMaxListEntries = 32 * 7;
 
-// Block-wide exclusive scan of one int per thread (kThreads threads).  Returns the exclusive
-// prefix; *total receives the block sum.  s_warp must hold kWarps + 1 ints.
-__device__ __forceinline__ int blockExclusiveScan(int v, int* s_warp, int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Warp-private staging of the scatter / count passes.
+struct WarpCells {
+    unsigned mask[kCells];   // lanes of the current batch that touch the cell
+    int cursor[kCells];      // next free queue slot of the cell
+};
+
+__device__ __forceinline__ int warpExclusiveScan(int v, int lane, int* total) {
     int incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        int n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if (lane >= d) incl += n;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int w = lane < kWarps ? s_warp[lane] : 0;
-        int wi = w;
-#pragma unroll
-        for (int d = 1; d < kWarps; d <<= 1) {
-            int n = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-            if (lane >= d) wi += n;
-        }
-        if (lane < kWarps) s_warp[lane] = wi - w;
-        if (lane == kWarps - 1) s_warp[kWarps] = wi;
+    *total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    return incl - v;
+}
+
+// Maps a cell (cx, cy) to its index in WarpCells: row-major over the whole bin grid (bin stage)
+// or relative to the bin's 16x16 tile window (coarse stage).
+struct CellIndexer {
+    S32 loX, loY, rowShift, rowPitch;
+    __device__ __forceinline__ int operator()(S32 cx, S32 cy) const { return rowShift >= 0 ? (cx - loX) + ((cy - loY) << rowShift) : cx + cy * rowPitch; }
+};
+
+// One batch of <= 32 entries (lane = entry, entry < 0 = none, fp = its footprint) scattered into
+// the cells it touches.  All 32 lanes must call.  [winLo, winHi] = inclusive cell window;
+// onPlaced(cx, cy, pos) is called for every (entry, cell) pair with the queue slot it received.
+//
+// Fast path (whole warp): every footprint is at most 2x2 cells -- four predicated slots, straight
+// line code.  Otherwise the generic three-pass enumeration with edge-refined cells.
+template <int SamplesLog2, int CellLog2, class OnPlaced>
+__device__ __forceinline__ void scatterBatch(WarpCells& wc, int32_t* __restrict__ queue, S32 entry, const TriFootprint& fp, int lane, unsigned ltMask, S32 winLoX, S32 winLoY,
+                                             S32 winHiX, S32 winHiY, const CellIndexer cellOf, OnPlaced onPlaced) {
+    const CellRange r = cellRange<CellLog2>(fp, winLoX, winLoY, winHiX, winHiY);
+    if (!__any_sync(0xFFFFFFFFu, r.refine | (r.nx > 2) | (r.ny > 2))) {
+        const unsigned bit = 1u << lane;
+        const bool v0 = r.nx > 0, v1 = r.nx > 1, v2 = r.ny > 1, v3 = v1 & v2;
+        const int c0 = cellOf(r.x0, r.y0), c1 = cellOf(r.x0 + 1, r.y0), c2 = cellOf(r.x0, r.y0 + 1), c3 = cellOf(r.x0 + 1, r.y0 + 1);
+        if (v0) atomicOr(&wc.mask[c0], bit);
+        if (v1) atomicOr(&wc.mask[c1], bit);
+        if (v2) atomicOr(&wc.mask[c2], bit);
+        if (v3) atomicOr(&wc.mask[c3], bit);
+        __syncwarp();
+        unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (v0) { m0 = wc.mask[c0]; const int pos = wc.cursor[c0] + __popc(m0 & ltMask); queue[pos] = entry; onPlaced(r.x0, r.y0, pos); }
+        if (v1) { m1 = wc.mask[c1]; const int pos = wc.cursor[c1] + __popc(m1 & ltMask); queue[pos] = entry; onPlaced(r.x0 + 1, r.y0, pos); }
+        if (v2) { m2 = wc.mask[c2]; const int pos = wc.cursor[c2] + __popc(m2 & ltMask); queue[pos] = entry; onPlaced(r.x0, r.y0 + 1, pos); }
+        if (v3) { m3 = wc.mask[c3]; const int pos = wc.cursor[c3] + __popc(m3 & ltMask); queue[pos] = entry; onPlaced(r.x0 + 1, r.y0 + 1, pos); }
+        __syncwarp();
+        // the lowest lane of every touched cell advances the cursor and clears the word
+        if (v0 && (m0 & ltMask) == 0) { wc.cursor[c0] += __popc(m0); wc.mask[c0] = 0; }
+        if (v1 && (m1 & ltMask) == 0) { wc.cursor[c1] += __popc(m1); wc.mask[c1] = 0; }
+        if (v2 && (m2 & ltMask) == 0) { wc.cursor[c2] += __popc(m2); wc.mask[c2] = 0; }
+        if (v3 && (m3 & ltMask) == 0) { wc.cursor[c3] += __popc(m3); wc.mask[c3] = 0; }
+        __syncwarp();
+        return;
     }
-    __syncthreads();
-    const int res = s_warp[warp] + incl - v;
-    *total = s_warp[kWarps];
-    __syncthreads();
-    return res;
+    forEachCell<SamplesLog2, CellLog2>(fp, winLoX, winLoY, winHiX, winHiY, [&](S32 cx, S32 cy) { atomicOr(&wc.mask[cellOf(cx, cy)], 1u << lane); });
+    __syncwarp();
+    forEachCell<SamplesLog2, CellLog2>(fp, winLoX, winLoY, winHiX, winHiY, [&](S32 cx, S32 cy) {
+        const int cell = cellOf(cx, cy);
+        const int pos = wc.cursor[cell] + __popc(wc.mask[cell] & ltMask);
+        queue[pos] = entry;
+        onPlaced(cx, cy, pos);
+    });
+    __syncwarp();
+    // the lowest lane of every touched cell advances its cursor and clears the word (a lane that
+    // reads the word after the clear sees 0 and does nothing)
+    forEachCell<SamplesLog2, CellLog2>(fp, winLoX, winLoY, winHiX, winHiY, [&](S32 cx, S32 cy) {
+        const int cell = cellOf(cx, cy);
+        const unsigned m = wc.mask[cell];
+        if (m != 0 && (m & ltMask) == 0) {
+            wc.cursor[cell] += __popc(m);
+            wc.mask[cell] = 0;
+        }
+    });
+    __syncwarp();
+}
+
+template <int SamplesLog2>
+__device__ __forceinline__ TriFootprint footprintOf(const crb_frame& f, S32 entry, const uint4& h) {
+    TriFootprint fp;
+    fp.empty = true;
+    if (entry >= 0) fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
+    return fp;
 }
 
 //------------------------------------------------------------------------------------------------
 // Bin stage.
 //------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kThreads) binScanKernel(const __grid_constant__ crb_frame f) {
-    __shared__ int s_warp[kWarps + 1];
+// One CTA per bin: exclusive scan of row `bin` of binCountMat[bin][chunk] over the chunks.
+__global__ void __launch_bounds__(kScanThreads) binScanKernel(const __grid_constant__ crb_frame f) {
+    __shared__ int s_warp[33];
     __shared__ int s_base[2];
-    const int bin = blockIdx.x;
-    int* row = f.binCountMat + (size_t)bin * f.numChunks;
-    int running = 0;
-    for (int base = 0; base < f.numChunks; base += kThreads) {
-        const int i = base + threadIdx.x;
-        const int v = i < f.numChunks ? row[i] : 0;
-        int total;
-        const int ex = blockExclusiveScan(v, s_warp, &total);
-        if (i < f.numChunks) row[i] = running + ex;
-        running += total;
+    if (threadIdx.x < 33) s_warp[threadIdx.x] = 0;
+    __syncthreads();
+    const int bin = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // thread t owns the 4-aligned run of chunks [first, first + perThread): 128-bit loads, coalesced
+    const int perThread = (((f.numChunks + kScanThreads - 1) / kScanThreads) + 3) & ~3;
+    const int first = threadIdx.x * perThread;
+    int* __restrict__ row = f.binCountMat + (size_t)bin * f.matPitch;
+    int sum = 0;
+    for (int k = 0; k < perThread; k += 4) {
+        const int c = first + k;
+        if (c < f.numChunks) {   // matPitch is padded to a multiple of 4 and the padding is zero
+            const int4 v = *reinterpret_cast<const int4*>(row + c);
+            sum += v.x + v.y + v.z + v.w;
+        }
     }
-    const int total = running;
+    int warpTotal;
+    const int ex = warpExclusiveScan(sum, lane, &warpTotal);
+    if (lane == 0) s_warp[warp] = warpTotal;
+    __syncthreads();
+    if (warp == 0) {
+        int t;
+        const int w = s_warp[lane];
+        const int e = warpExclusiveScan(w, lane, &t);
+        s_warp[lane] = e;
+        if (lane == 0) s_warp[32] = t;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + ex;
+    const int total = s_warp[32];
+    for (int k = 0; k < perThread; k += 4) {
+        const int c = first + k;
+        if (c < f.numChunks) {
+            const int4 v = *reinterpret_cast<const int4*>(row + c);
+            int4 o;
+            o.x = run; run += v.x;
+            o.y = run; run += v.y;
+            o.z = run; run += v.z;
+            o.w = run; run += v.w;
+            *reinterpret_cast<int4*>(row + c) = o;
+        }
+    }
     const int numItems = (total + CRB_ITEM_ENTRIES - 1) / CRB_ITEM_ENTRIES;
     if (threadIdx.x == 0) {
         const int start = atomicAdd(&f.atomics->numBinEntries, total);
@@ -102,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) binScanKernel(const __grid_constant_
     __syncthreads();
     const int start = s_base[0], itemBase = s_base[1];
     if (itemBase + numItems <= f.maxItems)
-        for (int k = threadIdx.x; k < numItems; k += kThreads) {
+        for (int k = threadIdx.x; k < numItems; k += kScanThreads) {
             crb_item it;
             it.bin = bin;
             it.first = start + k * CRB_ITEM_ENTRIES;
@@ -112,76 +209,76 @@ __global__ void __launch_bounds__(kThreads) binScanKernel(const __grid_constant_
         }
 }
 
-// Shared scatter machinery: a batch of <= kThreads queue entries, one per thread, each touching
-// any number of the 256 cells (bins or tiles of one bin).  Warp w records its lanes per cell in
-// s_mask[w][cell]; cell-owner threads turn the masks into per-warp offsets from the running
-// cursor; every thread then ranks itself with a popc of the lanes below it.  Stable because
-// threads are entries in queue order and cursors advance batch by batch.
-struct ScatterSmem {
-    unsigned mask[kWarps][256];
-    int warpOfs[kWarps][256];
-    int cursor[256];
-};
-
+// Tile-level count of one placed bin-queue entry: the entry sits at slot `pos` of bin (bx, by), i.e.
+// in coarse work item binItemBase + (pos - binStart) / CRB_ITEM_ENTRIES; every tile of that bin the
+// triangle touches gets +1 in the item's row of tileCountMat (fire-and-forget global reductions).
+// This is the COUNT pass of the coarse stage, fused here because the footprint is already at hand.
 template <int SamplesLog2>
-__global__ void __launch_bounds__(kThreads) binScatterKernel(const __grid_constant__ crb_frame f) {
-    __shared__ ScatterSmem sm;
-    __shared__ int s_list[kThreads * 7];
-    __shared__ int s_warp[kWarps + 1];
-    if (f.atomics->overflow != 0) return;
+__device__ __forceinline__ void countTilesOfPlacedEntry(const crb_frame& f, const TriFootprint& fp, S32 bx, S32 by, int pos) {
+    const int bin = bx + by * f.widthBins;
+    const int item = __ldg(&f.binItemBase[bin]) + ((pos - __ldg(&f.binStart[bin])) / CRB_ITEM_ENTRIES);
+    if (item >= f.maxItems) return;   // overflow: flagged by the scan, the frame is redone
+    int* row = f.tileCountMat + (size_t)item * CR_BIN_SQR;
+    const S32 tx0 = bx << CR_BIN_LOG2, ty0 = by << CR_BIN_LOG2;
+    const S32 tx1 = min(tx0 + CR_BIN_SIZE - 1, f.widthTiles - 1), ty1 = min(ty0 + CR_BIN_SIZE - 1, f.heightTiles - 1);
+    forEachCell<SamplesLog2, CR_TILE_LOG2>(fp, tx0, ty0, tx1, ty1, [&](S32 tx, S32 ty) { atomicAdd(&row[(tx - tx0) + ((ty - ty0) << CR_BIN_LOG2)], 1); });
+}
 
-    const int chunk = blockIdx.x;
+// One warp per chunk: expands the chunk's triangles into (triangle, sub-triangle) entries in
+// submission order and scatters them into the bin queue.  Loads run one batch ahead.
+template <int SamplesLog2>
+__global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_constant__ crb_frame f) {
+    __shared__ WarpCells s_cells[kWarps];
+    __shared__ int s_list[kWarps][kMaxListEntries];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x * kWarps + warp;
+    if (chunk >= f.numChunks) return;
+    const int triBegin = chunk * f.chunkTris, triEnd = min(triBegin + f.chunkTris, f.numTris);
+    // first batch in flight while the cursors are set up (a header slot of a culled triangle holds
+    // stale data, which is never interpreted: n == 0 makes the lane idle)
+    int nNext = triBegin + lane < triEnd ? (int)f.triSubtris[triBegin + lane] : 0;
+    uint4 hNext = triBegin + lane < triEnd ? __ldg(&f.triHeader[triBegin + lane]) : make_uint4(0, 0, 0, 0);
+    if (f.atomics->overflow != 0) return;
+    WarpCells& wc = s_cells[warp];
     const unsigned ltMask = laneMaskLt();
-    // one thread per bin: where this chunk's entries of that bin start
-    if (threadIdx.x < f.numBins) sm.cursor[threadIdx.x] = f.binStart[threadIdx.x] + f.binCountMat[(size_t)threadIdx.x * f.numChunks + chunk];
-    __syncthreads();
+    for (int b = lane; b < f.numBins; b += 32) {
+        wc.cursor[b] = __ldg(&f.binStart[b]) + f.binCountMat[(size_t)b * f.matPitch + chunk];
+        wc.mask[b] = 0;
+    }
+    __syncwarp();
+    const CellIndexer cellOf = {0, 0, -1, f.widthBins};
 
 #pragma unroll 1
-    for (int r = 0; r < CRB_CHUNK_TRIS / kThreads; r++) {
-        const int triBase = chunk * CRB_CHUNK_TRIS + r * kThreads;
-        if (triBase >= f.numTris) break;
-        // expand triangles into (triangle, sub-triangle) entries, submission order
-        const int tri = triBase + threadIdx.x;
-        const int n = tri < f.numTris ? (int)f.triSubtris[tri] : 0;
-        int numEntries;
-        const int pos = blockExclusiveScan(n, s_warp, &numEntries);
-        if (n == 1) s_list[pos] = tri * 8 + 7;
-        else
-            for (int k = 0; k < n; k++) s_list[pos + k] = tri * 8 + k;
-        __syncthreads();
-
-        for (int b = 0; b < numEntries; b += kThreads) {
-            for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&sm.mask[0][0])[i] = 0;
-            __syncthreads();
-            const int e = b + threadIdx.x;
-            int entry = -1;
-            TriFootprint fp;
-            fp.empty = true;
-            if (e < numEntries) {
-                entry = s_list[e];
-                const uint4 h = __ldg(&f.triHeader[resolveDataIdx(entry, f.triHeader)]);
-                fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
-                forEachCell<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(fp, 0, 0, f.widthBins - 1, f.heightBins - 1,
-                                                                      [&](S32 bx, S32 by) { atomicOr(&sm.mask[warp][bx + by * f.widthBins], 1u << lane); });
+    for (int t0 = triBegin; t0 < triEnd; t0 += 32) {
+        const int tri = t0 + lane;
+        const int n = nNext;
+        const uint4 h = hNext;
+        if (t0 + 32 + lane < triEnd) {
+            nNext = (int)f.triSubtris[t0 + 32 + lane];
+            hNext = __ldg(&f.triHeader[t0 + 32 + lane]);
+        } else nNext = 0;
+        if (__all_sync(0xFFFFFFFFu, n <= 1)) {
+            const S32 entry = n == 1 ? tri * 8 + 7 : -1;
+            const TriFootprint fp = footprintOf<SamplesLog2>(f, entry, h);
+            scatterBatch<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(wc, f.binQueue, entry, fp, lane, ltMask, 0, 0, f.widthBins - 1, f.heightBins - 1, cellOf,
+                                                                  [&](S32 bx, S32 by, int pos) { countTilesOfPlacedEntry<SamplesLog2>(f, fp, bx, by, pos); });
+        } else {
+            // clipped triangles in the batch: lay the entries out in order first
+            int numEntries;
+            const int pos = warpExclusiveScan(n, lane, &numEntries);
+            if (n == 1) s_list[warp][pos] = tri * 8 + 7;
+            else
+                for (int k = 0; k < n; k++) s_list[warp][pos + k] = tri * 8 + k;
+            __syncwarp();
+            for (int b = 0; b < numEntries; b += 32) {
+                const S32 entry = b + lane < numEntries ? s_list[warp][b + lane] : -1;
+                uint4 he = make_uint4(0, 0, 0, 0);
+                if (entry >= 0) he = __ldg(&f.triHeader[resolveDataIdx(entry, f.triHeader)]);
+                const TriFootprint fp = footprintOf<SamplesLog2>(f, entry, he);
+                scatterBatch<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(wc, f.binQueue, entry, fp, lane, ltMask, 0, 0, f.widthBins - 1, f.heightBins - 1, cellOf,
+                                                                      [&](S32 bx, S32 by, int pos) { countTilesOfPlacedEntry<SamplesLog2>(f, fp, bx, by, pos); });
             }
-            __syncthreads();
-            if (threadIdx.x < f.numBins) {
-                int run = sm.cursor[threadIdx.x];
-#pragma unroll
-                for (int w = 0; w < kWarps; w++) {
-                    sm.warpOfs[w][threadIdx.x] = run;
-                    run += __popc(sm.mask[w][threadIdx.x]);
-                }
-                sm.cursor[threadIdx.x] = run;
-            }
-            __syncthreads();
-            if (entry >= 0)
-                forEachCell<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(fp, 0, 0, f.widthBins - 1, f.heightBins - 1, [&](S32 bx, S32 by) {
-                    const int bin = bx + by * f.widthBins;
-                    f.binQueue[sm.warpOfs[warp][bin] + __popc(sm.mask[warp][bin] & ltMask)] = entry;
-                });
-            __syncthreads();
+            __syncwarp();
         }
     }
 }
@@ -200,52 +297,70 @@ __device__ __forceinline__ BinWindow binWindow(const crb_frame& f, int bin) {
     return w;
 }
 
-template <int SamplesLog2>
-__global__ void __launch_bounds__(kThreads) coarseCountKernel(const __grid_constant__ crb_frame f) {
-    __shared__ int s_count[CR_BIN_SQR];
-    if (f.atomics->overflow != 0) return;
-    const int numItems = f.atomics->numCoarseItems;
-    for (int item = blockIdx.x; item < numItems; item += gridDim.x) {
-        s_count[threadIdx.x] = 0;
-        __syncthreads();
-        const crb_item it = f.items[item];
-        const BinWindow w = binWindow(f, it.bin);
-        for (int e = threadIdx.x; e < it.count; e += kThreads) {
-            const S32 entry = __ldg(&f.binQueue[it.first + e]);
-            const uint4 h = __ldg(&f.triHeader[resolveDataIdx(entry, f.triHeader)]);
-            const TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
-            forEachCell<SamplesLog2, CR_TILE_LOG2>(fp, w.tx0, w.ty0, w.tx1, w.ty1,
-                                                   [&](S32 tx, S32 ty) { atomicAdd(&s_count[(tx - w.tx0) + ((ty - w.ty0) << CR_BIN_LOG2)], 1); });
-        }
-        __syncthreads();
-        f.tileCountMat[(size_t)item * CR_BIN_SQR + threadIdx.x] = s_count[threadIdx.x];
-        __syncthreads();
+// Exclusive scan of one int per thread over the 256 threads of group 0 of a CTA (other groups
+// pass 0 and only take part in the barriers).  *total = sum.  s_warp holds kWarps + 1 ints.
+__device__ __forceinline__ int blockExclusiveScan256g(int v, int group, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (kWarps - 1);
+    int wt;
+    const int ex = warpExclusiveScan(v, lane, &wt);
+    if (group == 0 && lane == 0) s_warp[warp] = wt;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t;
+        const int w = lane < kWarps ? s_warp[lane] : 0;
+        const int e = warpExclusiveScan(w, lane, &t);
+        if (lane < kWarps) s_warp[lane] = e;
+        if (lane == 0) s_warp[kWarps] = t;
     }
+    __syncthreads();
+    const int res = s_warp[warp] + ex;
+    *total = s_warp[kWarps];
+    __syncthreads();
+    return res;
 }
 
-__global__ void __launch_bounds__(kThreads) coarseScanKernel(const __grid_constant__ crb_frame f) {
+// One CTA per bin.  Thread (g, t) owns tile t of the bin and the g-th quarter of the bin's work
+// items: the four quarters are prefix-summed concurrently and stitched through shared memory, so the
+// serial chain over the items of a crowded bin is four times shorter.
+constexpr int kScanGroups = 4;
+__global__ void __launch_bounds__(kThreads * kScanGroups) coarseScanKernel(const __grid_constant__ crb_frame f) {
     __shared__ int s_warp[kWarps + 1];
     __shared__ int s_base[2];
+    __shared__ int s_group[kScanGroups][kCells];
     if (f.atomics->overflow != 0) return;
-    const int bin = blockIdx.x;
+    const int bin = blockIdx.x, t = threadIdx.x & (kCells - 1), g = threadIdx.x >> 8;
     const int itemBase = f.binItemBase[bin], numItems = f.binItemCount[bin];
-    // thread t owns tile t of the bin: exclusive prefix over the bin's items (coalesced rows)
-    int run = 0;
-    for (int k = 0; k < numItems; k++) {
-        int* p = &f.tileCountMat[(size_t)(itemBase + k) * CR_BIN_SQR + threadIdx.x];
+    const int perGroup = (numItems + kScanGroups - 1) / kScanGroups;
+    const int k0 = min(g * perGroup, numItems), k1 = min(k0 + perGroup, numItems);
+    int* const col = &f.tileCountMat[(size_t)itemBase * CR_BIN_SQR + t];
+    int sum = 0;
+    for (int k = k0; k < k1; k++) sum += col[(size_t)k * CR_BIN_SQR];
+    s_group[g][t] = sum;
+    __syncthreads();
+    int run = 0, tileTotal = 0;
+#pragma unroll
+    for (int i = 0; i < kScanGroups; i++) {
+        const int v = s_group[i][t];
+        if (i < g) run += v;
+        tileTotal += v;
+    }
+    for (int k = k0; k < k1; k++) {
+        int* p = &col[(size_t)k * CR_BIN_SQR];
         const int c = *p;
         *p = run;
         run += c;
     }
+    // the first group finishes the bin: tile offsets inside the bin's block of the tile queue
+    // (block barriers below are reached by all threads; only group 0 contributes / writes)
     int binSum;
-    const int ofs = blockExclusiveScan(run, s_warp, &binSum);
+    const int ofs = blockExclusiveScan256g(g == 0 ? tileTotal : 0, g, s_warp, &binSum);
 
     const BinWindow w = binWindow(f, bin);
-    const int tx = w.tx0 + (threadIdx.x & (CR_BIN_SIZE - 1)), ty = w.ty0 + (threadIdx.x >> CR_BIN_LOG2);
+    const int tx = w.tx0 + (t & (CR_BIN_SIZE - 1)), ty = w.ty0 + (t >> CR_BIN_LOG2);
     const bool inside = tx <= w.tx1 && ty <= w.ty1;
-    const bool active = inside && (run > 0 || f.deferredClear != 0);
+    const bool active = inside && (tileTotal > 0 || f.deferredClear != 0);
     int numActive;
-    const int activeOfs = blockExclusiveScan(active ? 1 : 0, s_warp, &numActive);
+    const int activeOfs = blockExclusiveScan256g((g == 0 && active) ? 1 : 0, g, s_warp, &numActive);
     if (threadIdx.x == 0) {
         const int base = atomicAdd(&f.atomics->numTileEntries, binSum);
         if (base + binSum > f.maxTileEntries) atomicOr(&f.atomics->overflow, 4);
@@ -253,63 +368,53 @@ __global__ void __launch_bounds__(kThreads) coarseScanKernel(const __grid_consta
         s_base[1] = atomicAdd(&f.atomics->numActiveTiles, numActive);
     }
     __syncthreads();
-    if (inside) {
-        const int g = tx + ty * f.widthTiles;
-        f.tileStart[g] = s_base[0] + ofs;
-        f.tileCount[g] = run;
-        if (active) f.activeTiles[s_base[1] + activeOfs] = g;
+    if (g == 0 && inside) {
+        const int gi = tx + ty * f.widthTiles;
+        f.tileStart[gi] = s_base[0] + ofs;
+        f.tileCount[gi] = tileTotal;
+        if (active) {
+            f.activeTiles[s_base[1] + activeOfs] = gi;
+            f.activeRecs[s_base[1] + activeOfs] = make_int4(gi, s_base[0] + ofs, tileTotal, 0);
+        }
     }
 }
 
+// One warp per work item.  Entries are loaded two batches ahead, headers one batch ahead.
 template <int SamplesLog2>
-__global__ void __launch_bounds__(kThreads) coarseScatterKernel(const __grid_constant__ crb_frame f) {
-    __shared__ ScatterSmem sm;
-    if (f.atomics->overflow != 0) return;
-    const int numItems = f.atomics->numCoarseItems;
+__global__ void __launch_bounds__(kThreads, 4) coarseScatterKernel(const __grid_constant__ crb_frame f) {
+    __shared__ WarpCells s_cells[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * kWarps + warp;
+    if (f.atomics->overflow != 0 || item >= f.atomics->numCoarseItems) return;
+    WarpCells& wc = s_cells[warp];
     const unsigned ltMask = laneMaskLt();
-    for (int item = blockIdx.x; item < numItems; item += gridDim.x) {
-        const crb_item it = f.items[item];
-        const BinWindow w = binWindow(f, it.bin);
-        {
-            const int tx = w.tx0 + (threadIdx.x & (CR_BIN_SIZE - 1)), ty = w.ty0 + (threadIdx.x >> CR_BIN_LOG2);
-            int cur = 0;
-            if (tx <= w.tx1 && ty <= w.ty1) cur = f.tileStart[tx + ty * f.widthTiles] + f.tileCountMat[(size_t)item * CR_BIN_SQR + threadIdx.x];
-            sm.cursor[threadIdx.x] = cur;
-        }
-        __syncthreads();
-        for (int b = 0; b < it.count; b += kThreads) {
-            for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&sm.mask[0][0])[i] = 0;
-            __syncthreads();
-            const int e = b + threadIdx.x;
-            int entry = -1;
-            TriFootprint fp;
-            fp.empty = true;
-            if (e < it.count) {
-                entry = __ldg(&f.binQueue[it.first + e]);
-                const uint4 h = __ldg(&f.triHeader[resolveDataIdx(entry, f.triHeader)]);
-                fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
-                forEachCell<SamplesLog2, CR_TILE_LOG2>(fp, w.tx0, w.ty0, w.tx1, w.ty1,
-                                                       [&](S32 tx, S32 ty) { atomicOr(&sm.mask[warp][(tx - w.tx0) + ((ty - w.ty0) << CR_BIN_LOG2)], 1u << lane); });
-            }
-            __syncthreads();
-            {
-                int run = sm.cursor[threadIdx.x];
+    const crb_item it = f.items[item];
+    const int32_t* __restrict__ src = f.binQueue + it.first;
+    S32 entryCur = lane < it.count ? __ldg(&src[lane]) : -1;
+    S32 entryNext = 32 + lane < it.count ? __ldg(&src[32 + lane]) : -1;
+    uint4 hCur = make_uint4(0, 0, 0, 0);
+    if (entryCur >= 0) hCur = __ldg(&f.triHeader[resolveDataIdx(entryCur, f.triHeader)]);
+
+    const BinWindow w = binWindow(f, it.bin);
 #pragma unroll
-                for (int k = 0; k < kWarps; k++) {
-                    sm.warpOfs[k][threadIdx.x] = run;
-                    run += __popc(sm.mask[k][threadIdx.x]);
-                }
-                sm.cursor[threadIdx.x] = run;
-            }
-            __syncthreads();
-            if (entry >= 0)
-                forEachCell<SamplesLog2, CR_TILE_LOG2>(fp, w.tx0, w.ty0, w.tx1, w.ty1, [&](S32 tx, S32 ty) {
-                    const int t = (tx - w.tx0) + ((ty - w.ty0) << CR_BIN_LOG2);
-                    f.tileQueue[sm.warpOfs[warp][t] + __popc(sm.mask[warp][t] & ltMask)] = entry;
-                });
-            __syncthreads();
-        }
+    for (int i = 0; i < kCells / 32; i++) {
+        const int t = lane + 32 * i;
+        const int tx = w.tx0 + (t & (CR_BIN_SIZE - 1)), ty = w.ty0 + (t >> CR_BIN_LOG2);
+        int cur = 0;
+        if (tx <= w.tx1 && ty <= w.ty1) cur = f.tileStart[tx + ty * f.widthTiles] + f.tileCountMat[(size_t)item * CR_BIN_SQR + t];
+        wc.cursor[t] = cur;
+        wc.mask[t] = 0;
+    }
+    __syncwarp();
+    const CellIndexer cellOf = {w.tx0, w.ty0, CR_BIN_LOG2, 0};
+#pragma unroll 1
+    for (int b = 0; b < it.count; b += 32) {
+        uint4 hNext = make_uint4(0, 0, 0, 0);
+        if (entryNext >= 0) hNext = __ldg(&f.triHeader[resolveDataIdx(entryNext, f.triHeader)]);
+        const S32 entryNext2 = b + 64 + lane < it.count ? __ldg(&src[b + 64 + lane]) : -1;
+        const TriFootprint fp = footprintOf<SamplesLog2>(f, entryCur, hCur);
+        scatterBatch<SamplesLog2, CR_TILE_LOG2>(wc, f.tileQueue, entryCur, fp, lane, ltMask, w.tx0, w.ty0, w.tx1, w.ty1, cellOf, [](S32, S32, int) {});
+        entryCur = entryNext; hCur = hNext; entryNext = entryNext2;
     }
 }
 
@@ -319,24 +424,23 @@ inline int checkLaunch() { return cudaGetLastError() == cudaSuccess ? CRB_OK : C
 
 extern "C" int crb_launch_bin_raster(const crb_frame* f, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    binScanKernel<<<f->numBins, kThreads, 0, s>>>(*f);
+    binScanKernel<<<f->numBins, kScanThreads, 0, s>>>(*f);
     if (f->numTris > 0) {
-        if (f->samplesLog2 == 0) binScatterKernel<0><<<f->numChunks, kThreads, 0, s>>>(*f);
-        else binScatterKernel<1><<<f->numChunks, kThreads, 0, s>>>(*f);
+        const int grid = (f->numChunks + kWarps - 1) / kWarps;
+        if (f->samplesLog2 == 0) binScatterKernel<0><<<grid, kThreads, 0, s>>>(*f);
+        else binScatterKernel<1><<<grid, kThreads, 0, s>>>(*f);
     }
     return checkLaunch();
 }
 
 extern "C" int crb_launch_coarse_raster(const crb_frame* f, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    const int grid = max(1, min(f->maxItems, f->numSMs * 4));
-    if (f->samplesLog2 == 0) coarseCountKernel<0><<<grid, kThreads, 0, s>>>(*f);
-    else coarseCountKernel<1><<<grid, kThreads, 0, s>>>(*f);
-    coarseScanKernel<<<f->numBins, kThreads, 0, s>>>(*f);
+    const int grid = max(1, (f->maxItems + kWarps - 1) / kWarps);
+    coarseScanKernel<<<f->numBins, kThreads * kScanGroups, 0, s>>>(*f);
     if (f->samplesLog2 == 0) coarseScatterKernel<0><<<grid, kThreads, 0, s>>>(*f);
     else coarseScatterKernel<1><<<grid, kThreads, 0, s>>>(*f);
     return checkLaunch();
 }
 
 extern "C" int crb_bin_launches(const crb_frame* f) { return f->numTris > 0 ? 2 : 1; }
-extern "C" int crb_coarse_launches(const crb_frame*) { return 3; }
+extern "C" int crb_coarse_launches(const crb_frame*) { return 2; }

@@ -72,7 +72,7 @@ struct crb_ctx {
     DevBuf triSubtris, triHeader, triData;
     DevBuf binCountMat, binStart, binTotal, binQueue;
     DevBuf items, binItemBase, binItemCount, tileCountMat;
-    DevBuf tileQueue, tileStart, tileCount, activeTiles;
+    DevBuf tileQueue, tileStart, tileCount, activeTiles, activeRecs;
     DevBuf atomics;
     crb_atomics* hostAtomics = nullptr;  // pinned
     DevBuf hostVerts, hostIdx;           // device staging for crb_draw_triangles_host
@@ -154,7 +154,11 @@ int prepareFrame(crb_ctx* c) {
     f.depthBuffer = c->depth;
     f.surfacePitch = f.widthPixels << c->samplesLog2;
 
-    f.numChunks = (c->numTris + CRB_CHUNK_TRIS - 1) / CRB_CHUNK_TRIS;
+    f.ctasPerChunk = 1;
+    while (((int64_t)c->numTris + CRB_SETUP_THREADS * f.ctasPerChunk - 1) / (CRB_SETUP_THREADS * f.ctasPerChunk) > CRB_MAX_CHUNKS) f.ctasPerChunk *= 2;
+    f.chunkTris = CRB_SETUP_THREADS * f.ctasPerChunk;
+    f.numChunks = (c->numTris + f.chunkTris - 1) / f.chunkTris;
+    f.matPitch = (f.numChunks + 3) & ~3;
     f.maxSubtris = c->maxSubtris;
     f.maxBinEntries = c->maxBinEntries;
     f.maxTileEntries = c->maxTileEntries;
@@ -164,7 +168,7 @@ int prepareFrame(crb_ctx* c) {
     CRB_CUDA(c, c->triSubtris.reserve((size_t)c->maxSubtris));
     CRB_CUDA(c, c->triHeader.reserve((size_t)c->maxSubtris * 16));
     CRB_CUDA(c, c->triData.reserve((size_t)c->maxSubtris * 64));
-    CRB_CUDA(c, c->binCountMat.reserve((size_t)std::max(1, f.numBins * f.numChunks) * 4));
+    CRB_CUDA(c, c->binCountMat.reserve((size_t)std::max(4, f.numBins * f.matPitch) * 4));
     CRB_CUDA(c, c->binStart.reserve(CR_MAXBINS_SQR * 4));
     CRB_CUDA(c, c->binTotal.reserve(CR_MAXBINS_SQR * 4));
     CRB_CUDA(c, c->binItemBase.reserve(CR_MAXBINS_SQR * 4));
@@ -176,6 +180,7 @@ int prepareFrame(crb_ctx* c) {
     CRB_CUDA(c, c->tileStart.reserve(CR_MAXTILES_SQR * 4));
     CRB_CUDA(c, c->tileCount.reserve(CR_MAXTILES_SQR * 4));
     CRB_CUDA(c, c->activeTiles.reserve(CR_MAXTILES_SQR * 4));
+    CRB_CUDA(c, c->activeRecs.reserve(CR_MAXTILES_SQR * 16));
 
     f.triSubtris = (uint8_t*)c->triSubtris.ptr;
     f.triHeader = (uint4*)c->triHeader.ptr;
@@ -192,6 +197,7 @@ int prepareFrame(crb_ctx* c) {
     f.tileStart = (int32_t*)c->tileStart.ptr;
     f.tileCount = (int32_t*)c->tileCount.ptr;
     f.activeTiles = (int32_t*)c->activeTiles.ptr;
+    f.activeRecs = (int4*)c->activeRecs.ptr;
     f.atomics = (crb_atomics*)c->atomics.ptr;
     return CRB_OK;
 }
@@ -200,6 +206,11 @@ int prepareFrame(crb_ctx* c) {
 int launchStages(crb_ctx* c, cudaStream_t s) {
     const crb_frame* f = &c->frame;
     CRB_CUDA(c, cudaMemsetAsync(c->atomics.ptr, 0, sizeof(crb_atomics), s));
+    // bin counts: padding columns must read 0; with several setup CTAs per chunk they ADD into the matrix.
+    // tile counts: accumulated with global reductions by the bin scatter pass.
+    if (f->numTris > 0 && (f->ctasPerChunk > 1 || f->matPitch != f->numChunks))
+        CRB_CUDA(c, cudaMemsetAsync(f->binCountMat, 0, (size_t)f->matPitch * f->numBins * 4, s));
+    CRB_CUDA(c, cudaMemsetAsync(f->tileCountMat, 0, (size_t)f->maxItems * CR_BIN_SQR * 4, s));
     CRB_CUDA(c, cudaEventRecord(c->ev[0], s));
     int rc = c->pipe.triangleSetup(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: triangleSetup launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -267,7 +278,7 @@ int crb_destroy(crb_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
-                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->atomics, &c->hostVerts, &c->hostIdx};
+                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx};
     for (DevBuf* b : bufs) b->release();
     if (c->hostAtomics) cudaFreeHost(c->hostAtomics);
     for (int i = 0; i < 5; i++)

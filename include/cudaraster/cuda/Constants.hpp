@@ -39,8 +39,11 @@
 
 // ---- B200 scheduling constants (new) --------------------------------------------------------
 #define CRB_SETUP_THREADS 256     // threads per setup / bin CTA
-#define CRB_CHUNK_TRIS 1024       // consecutive input triangles owned by one setup/bin CTA
+#ifndef CRB_SETUP_MIN_BLOCKS
+#define CRB_SETUP_MIN_BLOCKS 4    // resident setup CTAs per SM the register allocation must allow
+#endif
+#define CRB_MAX_CHUNKS 16384       // chunkTris = CRB_SETUP_THREADS * 2^k, smallest k with numChunks <= this
 #define CRB_BIN_THREADS 256       // == CR_MAXBINS_SQR: one thread per bin in the scan phases
 #define CRB_COARSE_THREADS 256    // == CR_BIN_SQR: one thread per tile-in-bin in the scan phases
-#define CRB_ITEM_ENTRIES 2048     // bin-queue entries per coarse work item
+#define CRB_ITEM_ENTRIES 256      // bin-queue entries per coarse work item (one warp, 8 batches)
 #define CRB_FINE_WARPS 8          // warps (= tiles in flight) per fine CTA

@@ -248,12 +248,15 @@ struct FineBatch {
 //------------------------------------------------------------------------------------------------
 
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
-__global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
+__global__ void __launch_bounds__(CRB_FINE_WARPS * 32, 4) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
     __shared__ FineBatch s_batch[CRB_FINE_WARPS];
 
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int activeIdx = blockIdx.x * CRB_FINE_WARPS + warp;
+    // {tile, queue start, queue count} in ONE load, issued together with the counters (the slot is
+    // always inside the buffer; it only holds a real record when activeIdx < numActiveTiles)
+    const int4 rec = __ldg(&f.activeRecs[activeIdx]);
     if (f.atomics->overflow != 0) return;
     if (activeIdx >= f.atomics->numActiveTiles) return;
 
@@ -261,10 +264,10 @@ __global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(co
     const bool deferred = !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
 
     FineBatch& sb = s_batch[warp];
-    const int tileIdx = __ldg(&f.activeTiles[activeIdx]);
+    const int tileIdx = rec.x;
     const int tileY = tileIdx / f.widthTiles, tileX = tileIdx - tileY * f.widthTiles;
-    const int queueStart = __ldg(&f.tileStart[tileIdx]);
-    const int queueCount = __ldg(&f.tileCount[tileIdx]);
+    const int queueStart = rec.y;
+    const int queueCount = rec.z;
     const S32* __restrict__ queue = f.tileQueue + queueStart;
 
     // software pipeline: entries two batches ahead, header + depth plane one batch ahead
@@ -354,19 +357,20 @@ __global__ void __launch_bounds__(CRB_FINE_WARPS * 32) fineRasterSingleKernel(co
         cur = nxt;
     }
 
-    if (deferred) {
-        // shade only the visible fragment of each pixel
-#pragma unroll
-        for (int p = 0; p < 2; p++) {
-            const S32 entry = winner[p];
-            if (entry < 0) continue;
-            const S32 dataIdx = resolveDataIdx(entry, f.triHeader);
-            FragmentShaderClass fs;
-            runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, entry >> 3, dataIdx, pixelX, pixelY0 + 4 * p, 0x11u);
-            BlendShaderClass bs;
-            runBlendShader(bs, entry >> 3, pixelX, pixelY0 + 4 * p, 0, fs.m_color, 0u);
-            if (bs.m_writeColor) color[p] = bs.m_color;
-        }
+    if (deferred && (winner[0] & winner[1]) >= 0) {
+        // Shade only the visible fragment of each pixel.  Both pixels are shaded in one straight
+        // line of code (a lane with a single covered pixel shades that fragment twice) so that the
+        // two chains of dependent loads -- plane rows, then vertex varyings -- overlap.
+        const S32 e0 = winner[0] >= 0 ? winner[0] : winner[1], e1 = winner[1] >= 0 ? winner[1] : winner[0];
+        const S32 d0 = resolveDataIdx(e0, f.triHeader), d1 = resolveDataIdx(e1, f.triHeader);
+        FragmentShaderClass fs0, fs1;
+        runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs0, f, e0 >> 3, d0, pixelX, pixelY0 + (winner[0] >= 0 ? 0 : 4), 0x11u);
+        runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs1, f, e1 >> 3, d1, pixelX, pixelY0 + (winner[1] >= 0 ? 4 : 0), 0x11u);
+        BlendShaderClass bs0, bs1;
+        runBlendShader(bs0, e0 >> 3, pixelX, pixelY0, 0, fs0.m_color, 0u);
+        runBlendShader(bs1, e1 >> 3, pixelX, pixelY0 + 4, 0, fs1.m_color, 0u);
+        if (winner[0] >= 0 && bs0.m_writeColor) color[0] = bs0.m_color;
+        if (winner[1] >= 0 && bs1.m_writeColor) color[1] = bs1.m_color;
     }
 
     colorPtr[0] = color[0];

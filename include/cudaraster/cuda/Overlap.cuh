@@ -75,6 +75,23 @@ __device__ __forceinline__ void forEachCell(const TriFootprint& t, S32 winLoX, S
         }
 }
 
+// Cell rectangle of a footprint inside an inclusive cell window: first cell, extent (0 = nothing)
+// and whether cells must be refined with edge tests (decided on the UNclipped footprint, exactly
+// like forEachCell, so that every pass that enumerates the cells of a triangle agrees).
+struct CellRange { S32 x0, y0, nx, ny; bool refine; };
+template <int CellLog2>
+__device__ __forceinline__ CellRange cellRange(const TriFootprint& t, S32 winLoX, S32 winLoY, S32 winHiX, S32 winHiY) {
+    CellRange r;
+    S32 cLoX = t.pxLoX >> CellLog2, cHiX = t.pxHiX >> CellLog2, cLoY = t.pxLoY >> CellLog2, cHiY = t.pxHiY >> CellLog2;
+    r.refine = (cHiX - cLoX > 1) | (cHiY - cLoY > 1);
+    cLoX = max(cLoX, winLoX); cHiX = min(cHiX, winHiX); cLoY = max(cLoY, winLoY); cHiY = min(cHiY, winHiY);
+    r.x0 = cLoX; r.y0 = cLoY;
+    r.nx = t.empty ? 0 : max(cHiX - cLoX + 1, 0);
+    r.ny = t.empty ? 0 : max(cHiY - cLoY + 1, 0);
+    if (r.nx == 0 || r.ny == 0) r.nx = r.ny = 0;
+    return r;
+}
+
 // Resolves a queue entry (triIdx*8 + sub, sub == 7 meaning "the only sub-triangle, stored at
 // triIdx") to the slot of its header/data (reference: BinRaster.inl:190-197).
 __device__ __forceinline__ S32 resolveDataIdx(S32 entry, const uint4* __restrict__ triHeader) {

@@ -69,8 +69,11 @@ struct crb_frame {
     uint4* triData;               // 4 x uint4 per sub-triangle
 
     // ---- bin stage: count matrix -> exclusive offsets, CSR queue
-    int32_t numChunks;            // ceil(numTris / CRB_CHUNK_TRIS)
-    int32_t* binCountMat;         // [numBins][numChunks]; counts, then exclusive prefix over chunks
+    int32_t chunkTris;            // consecutive triangles per chunk = CRB_SETUP_THREADS * ctasPerChunk
+    int32_t ctasPerChunk;         // setup CTAs that share one chunk (power of two; 1 for <= 4M triangles)
+    int32_t numChunks;            // ceil(numTris / chunkTris)
+    int32_t matPitch;             // numChunks rounded up to a multiple of 4
+    int32_t* binCountMat;         // [numBins][matPitch]; counts, then exclusive prefix over chunks
     int32_t* binStart;            // [CR_MAXBINS_SQR]
     int32_t* binTotal;            // [CR_MAXBINS_SQR]
     int32_t maxBinEntries;
@@ -87,6 +90,7 @@ struct crb_frame {
     int32_t* tileStart;           // [CR_MAXTILES_SQR] indexed by global tile index
     int32_t* tileCount;           // [CR_MAXTILES_SQR]
     int32_t* activeTiles;         // [CR_MAXTILES_SQR]
+    int4* activeRecs;             // [CR_MAXTILES_SQR] {tile index, queue start, queue count, 0}: one load per fine warp
 
     crb_atomics* atomics;
     int32_t numSMs;

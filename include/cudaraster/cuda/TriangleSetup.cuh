@@ -6,10 +6,10 @@
 // plane equations, and the triSubtris / triHeader / triData records -- bit for bit.
 //
 // What is different (B200 design, DESIGN.md "setup"):
-//  * one CTA owns a CHUNK of CRB_CHUNK_TRIS consecutive triangles and, besides setting them
-//    up, histograms the bins their sub-triangles touch into shared memory and publishes one
-//    column of the [bin][chunk] count matrix.  That column is all the bin stage needs to place
-//    this chunk's queue entries with a plain scan -- no 16-CTA bin kernel, no segment lists;
+//  * one thread per input triangle; a CTA (= 256 consecutive triangles, one CHUNK or a slice of
+//    one) also histograms the bins its sub-triangles touch in shared memory and publishes one
+//    column of the [bin][chunk] count matrix.  That column is all the bin stage needs to place the
+//    chunk's queue entries with a plain scan -- no 16-CTA bin kernel, no segment lists;
 //  * the frame parameters travel as a __grid_constant__ kernel argument, not through
 //    __constant__ uploads; vertices are read through the read-only path with 128-bit loads;
 //  * the clipper lives in a __noinline__ cold path so the common path needs no local stack.
@@ -204,21 +204,17 @@ __device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, in
 }
 
 template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
-__global__ void __launch_bounds__(CRB_SETUP_THREADS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
+__global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
     __shared__ int s_binCount[CR_MAXBINS_SQR];
     for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
     __syncthreads();
 
-    const int chunk = blockIdx.x;
     const int stride4 = (int)(sizeof(VertexClass) / sizeof(float4));
     const float4* __restrict__ verts = reinterpret_cast<const float4*>(f.vertexBuffer);
     const S32 aabbLimit = (1 << (CR_MAXVIEWPORT_LOG2 + CR_SUBPIXEL_LOG2)) - 1;
 
-#pragma unroll 1
-    for (int r = 0; r < CRB_CHUNK_TRIS / CRB_SETUP_THREADS; r++) {
-        const int tri = chunk * CRB_CHUNK_TRIS + r * CRB_SETUP_THREADS + threadIdx.x;
-        if (tri >= f.numTris) break;
-
+    const int tri = blockIdx.x * CRB_SETUP_THREADS + threadIdx.x;   // one thread per input triangle
+    if (tri < f.numTris) {
         const int3 vidx = make_int3(__ldg(&f.indexBuffer[tri * 3 + 0]), __ldg(&f.indexBuffer[tri * 3 + 1]), __ldg(&f.indexBuffer[tri * 3 + 2]));
         const float4 v0 = __ldg(&verts[(size_t)vidx.x * stride4]);
         const float4 v1 = __ldg(&verts[(size_t)vidx.y * stride4]);
@@ -234,38 +230,46 @@ __global__ void __launch_bounds__(CRB_SETUP_THREADS) triangleSetupKernel(const _
                              ((v0.w < v0.z) & (v1.w < v1.z) & (v2.w < v2.z)) | ((v0.w < -v0.z) & (v1.w < -v1.z) & (v2.w < -v2.z));
         if (outside) {
             f.triSubtris[tri] = 0;
-            continue;
-        }
-
-        // inside the depth range: snap; inside the S16 guard band and small enough -> fast path
-        if ((v0.w >= fabsf(v0.z)) & (v1.w >= fabsf(v1.z)) & (v2.w >= fabsf(v2.z))) {
-            SnappedTri s;
-            snapTriangle(f, v0, v1, v2, s);
-            const S32 loxy = min(s.lo.x, s.lo.y), hixy = max(s.hi.x, s.hi.y);
-            if (loxy >= -32768 && hixy <= 32767 && hixy - loxy <= aabbLimit) {
-                int2 d1, d2;
-                S32 area;
-                const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
-                f.triSubtris[tri] = (res == 0) ? 1 : 0;
-                if (res == 0) {
-                    uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
-                                                                          make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area);
-                    histogramBins<SamplesLog2>(f, h, s_binCount);
+        } else {
+            // inside the depth range: snap; inside the S16 guard band and small enough -> fast path
+            bool done = false;
+            if ((v0.w >= fabsf(v0.z)) & (v1.w >= fabsf(v1.z)) & (v2.w >= fabsf(v2.z))) {
+                SnappedTri s;
+                snapTriangle(f, v0, v1, v2, s);
+                const S32 loxy = min(s.lo.x, s.lo.y), hixy = max(s.hi.x, s.hi.y);
+                if (loxy >= -32768 && hixy <= 32767 && hixy - loxy <= aabbLimit) {
+                    int2 d1, d2;
+                    S32 area;
+                    const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
+                    f.triSubtris[tri] = (res == 0) ? 1 : 0;
+                    if (res == 0) {
+                        uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
+                                                                              make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area);
+                        histogramBins<SamplesLog2>(f, h, s_binCount);
+                    }
+                    done = true;
                 }
-                continue;
             }
+            if (!done) setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, s_binCount);
         }
-        setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, s_binCount);
     }
 
+    // publish this CTA's bin histogram: one column of binCountMat[bin][chunk]
     __syncthreads();
-    for (int b = threadIdx.x; b < f.numBins; b += CRB_SETUP_THREADS) f.binCountMat[(size_t)b * f.numChunks + chunk] = s_binCount[b];
+    int* col = f.binCountMat + blockIdx.x / f.ctasPerChunk;
+    if (f.ctasPerChunk == 1) {
+        for (int b = threadIdx.x; b < f.numBins; b += CRB_SETUP_THREADS) col[(size_t)b * f.matPitch] = s_binCount[b];
+    } else {
+        for (int b = threadIdx.x; b < f.numBins; b += CRB_SETUP_THREADS)
+            if (s_binCount[b] != 0) atomicAdd(&col[(size_t)b * f.matPitch], s_binCount[b]);
+    }
 }
 
 template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
 inline int launchTriangleSetup(const crb_frame* f, void* stream) {
     if (f->numTris <= 0) return CRB_OK;
-    triangleSetupKernel<VertexClass, SamplesLog2, RenderModeFlags><<<f->numChunks, CRB_SETUP_THREADS, 0, (cudaStream_t)stream>>>(*f);
+    const int grid = (f->numTris + CRB_SETUP_THREADS - 1) / CRB_SETUP_THREADS;
+    triangleSetupKernel<VertexClass, SamplesLog2, RenderModeFlags><<<grid, CRB_SETUP_THREADS, 0, (cudaStream_t)stream>>>(*f);
     return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
 }
 
