@@ -74,6 +74,8 @@ def load_library():
         "crb_set_index_buffer": (i32, [vp, vp, i32]),
         "crb_set_subviewport": (i32, [vp, i32, i32, i32, i32]),
         "crb_draw_triangles": (i32, [vp, vp]),
+        "crb_draw_triangles_async": (i32, [vp, vp]),
+        "crb_finish": (i32, [vp, vp]),
         "crb_draw_triangles_host": (i32, [vp, vp, ctypes.c_size_t, vp, i32, vp, vp, vp]),
         "crb_get_stats": (i32, [vp, ctypes.POINTER(f32 * 4)]),
         "crb_get_counters": (i32, [vp, ctypes.POINTER(Atomics)]),
@@ -92,7 +94,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
-                    "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_host", "crb_get_stats", "crb_get_counters",
+                    "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_get_stats", "crb_get_counters",
                     "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download"]
 
 
@@ -222,9 +224,16 @@ class CudaRaster:
     def setSubViewport(self, full_w, full_h, x0, y0):
         self._check(self.lib.crb_set_subviewport(self.ctx, full_w, full_h, x0, y0))
 
-    def drawTriangles(self, stream=None):
+    def drawTriangles(self, stream=None, asynchronous=False):
+        """asynchronous=True enqueues the frame without the blocking counter read-back; call finish()."""
         s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        self._check(self.lib.crb_draw_triangles(self.ctx, ctypes.c_void_p(s)))
+        fn = self.lib.crb_draw_triangles_async if asynchronous else self.lib.crb_draw_triangles
+        self._check(fn(self.ctx, ctypes.c_void_p(s)))
+
+    def finish(self, stream=None):
+        """Synchronizes and checks the counters of all asynchronous frames (raises if one overflowed)."""
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(self.lib.crb_finish(self.ctx, ctypes.c_void_p(s)))
 
     def drawTrianglesHost(self, h_verts, h_idx, num_tris, h_color, h_depth=None, stream=None):
         """Host-buffer entry: pinned torch CPU tensors in, surfaces out (crb_draw_triangles_host)."""

@@ -74,7 +74,8 @@ struct crb_ctx {
     DevBuf items, binItemBase, binItemCount, tileCountMat;
     DevBuf tileQueue, tileStart, tileCount, activeTiles, activeRecs;
     DevBuf atomics;
-    crb_atomics* hostAtomics = nullptr;  // pinned
+    crb_atomics* hostAtomics = nullptr;  // pinned; slot 0 = synchronous draws, slots 1.. = ring of asynchronous frames
+    int pending = 0;                     // asynchronous frames not yet checked by crb_finish
     DevBuf hostVerts, hostIdx;           // device staging for crb_draw_triangles_host
 
     cudaEvent_t ev[5] = {};
@@ -103,6 +104,8 @@ int cudaFail(crb_ctx* c, const char* what, cudaError_t e) { return setError(c, C
         cudaError_t e_ = (call);                                   \
         if (e_ != cudaSuccess) return cudaFail((ctx), #call, e_);  \
     } while (0)
+
+constexpr int kAsyncRing = 64;
 
 int popc8(int v) { return __builtin_popcount((unsigned)v & 0xFF); }
 
@@ -267,8 +270,8 @@ int crb_create(int device, crb_ctx** out) {
     for (int i = 0; i < 5; i++)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
     if (c->atomics.reserve(sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
-    if (cudaMallocHost((void**)&c->hostAtomics, sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
-    std::memset(c->hostAtomics, 0, sizeof(crb_atomics));
+    if (cudaMallocHost((void**)&c->hostAtomics, sizeof(crb_atomics) * (1 + kAsyncRing)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    std::memset(c->hostAtomics, 0, sizeof(crb_atomics) * (1 + kAsyncRing));
     *out = c;
     return CRB_OK;
 }
@@ -432,6 +435,58 @@ int crb_draw_triangles(crb_ctx* c, void* stream) {
         if (a.overflow & (2 | 8)) c->maxBinEntries = std::max(c->maxBinEntries, a.numBinEntries + a.numBinEntries / 16 + 16384);
         if (a.overflow & 4) c->maxTileEntries = std::max(c->maxTileEntries, a.numTileEntries + a.numTileEntries / 16 + 65536);
     }
+    c->deferredClear = false;
+    c->drawn = true;
+    return CRB_OK;
+}
+
+int crb_finish(crb_ctx* c, void* stream) {
+    if (!c) return CRB_ERR_INVALID;
+    CRB_CUDA(c, cudaSetDevice(c->device));
+    CRB_CUDA(c, cudaStreamSynchronize((cudaStream_t)stream));
+    int overflowed = 0;
+    for (int i = 0; i < c->pending; i++) {
+        crb_atomics a = c->hostAtomics[1 + i];
+        a.numSubtris += c->numTris;
+        c->lastAtomics = a;
+        if (a.overflow == 0) continue;
+        overflowed++;
+        if (a.overflow & 1) c->maxSubtris = std::max(c->maxSubtris, a.numSubtris + 4096);
+        if (a.overflow & (2 | 8)) c->maxBinEntries = std::max(c->maxBinEntries, a.numBinEntries + a.numBinEntries / 16 + 16384);
+        if (a.overflow & 4) c->maxTileEntries = std::max(c->maxTileEntries, a.numTileEntries + a.numTileEntries / 16 + 65536);
+    }
+    const int n = c->pending;
+    c->pending = 0;
+    if (overflowed) return setError(c, CRB_ERR_OVERFLOW, "CudaRaster: %d of %d asynchronous frames overflowed a work buffer; capacities grown, redraw", overflowed, n);
+    return CRB_OK;
+}
+
+int crb_draw_triangles_async(crb_ctx* c, void* stream) {
+    if (!c) return CRB_ERR_INVALID;
+    int rc = validateDraw(c);
+    if (rc != CRB_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CUDA(c, cudaSetDevice(c->device));
+    if (c->fullWidth > 0 && (c->subX0 + c->width > c->fullWidth || c->subY0 + c->height > c->fullHeight))
+        return setError(c, CRB_ERR_INVALID, "CudaRaster: sub-viewport exceeds the full frame!");
+    if (c->pending == kAsyncRing) {
+        rc = crb_finish(c, stream);
+        if (rc != CRB_OK) return rc;
+    }
+    const int numTris = c->numTris;
+    const int numTilesEst = (((c->width + 7) >> 3) * ((c->height + 7) >> 3));
+    c->maxSubtris = std::max(c->maxSubtris, numTris + 4096);
+    c->maxBinEntries = std::max(c->maxBinEntries, numTris + numTris / 4 + 16384);
+    c->maxTileEntries = std::max(c->maxTileEntries, std::max(numTilesEst, numTris * 2) + 65536);
+    if (c->maxSubtris > CR_MAXSUBTRIS_SIZE) return setError(c, CRB_ERR_LIMIT, "CudaRaster: CR_MAXSUBTRIS_SIZE exceeded!");
+    c->maxItems = c->maxBinEntries / CRB_ITEM_ENTRIES + CR_MAXBINS_SQR + 1;
+    c->launchCount = 0;
+    rc = prepareFrame(c);
+    if (rc != CRB_OK) return rc;
+    rc = launchStages(c, s);
+    if (rc != CRB_OK) return rc;
+    CRB_CUDA(c, cudaMemcpyAsync(&c->hostAtomics[1 + c->pending], c->atomics.ptr, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
+    c->pending++;
     c->deferredClear = false;
     c->drawn = true;
     return CRB_OK;

@@ -26,7 +26,8 @@ typedef enum crb_status {
     CRB_ERR_INVALID = 1,      /* bad argument / state (message in crb_last_error) */
     CRB_ERR_CUDA = 2,         /* a CUDA runtime call failed                         */
     CRB_ERR_NO_DEVICE = 3,    /* no CUDA device: the product has no CPU path        */
-    CRB_ERR_LIMIT = 4         /* a format limit was exceeded (CR_MAXSUBTRIS_SIZE...) */
+    CRB_ERR_LIMIT = 4,        /* a format limit was exceeded (CR_MAXSUBTRIS_SIZE...) */
+    CRB_ERR_OVERFLOW = 5      /* crb_finish: an asynchronous frame overflowed a work buffer and must be redrawn */
 } crb_status;
 
 /* Render-mode flags: cuda/PixelPipe.hpp:30-35. */
@@ -129,6 +130,16 @@ int crb_set_subviewport(crb_ctx* ctx, int fullWidth, int fullHeight, int x0, int
  * stages on `stream` (NULL = default stream), reads the counters back and, if a queue
  * overflowed, grows the buffers and re-runs the frame, like the reference's retry loop. */
 int crb_draw_triangles(crb_ctx* ctx, void* stream);
+
+/* Asynchronous variant (new; the reference blocks on the counter read-back every frame,
+ * CudaRaster.cpp:326): enqueues one frame with the CURRENT work-buffer capacities and returns without
+ * synchronizing, so consecutive frames run back to back on the GPU.  The counters of every frame
+ * are copied to pinned host memory; crb_finish() synchronizes `stream` and checks them: CRB_OK, or
+ * CRB_ERR_OVERFLOW if some frame overflowed a queue (its output is incomplete; the capacities
+ * have been grown, redraw it -- a synchronous crb_draw_triangles() of the same scene first makes
+ * that impossible).  At most 64 frames may be pending; the 65th call finishes implicitly. */
+int crb_draw_triangles_async(crb_ctx* ctx, void* stream);
+int crb_finish(crb_ctx* ctx, void* stream);
 
 /* The same call for HOST buffers (the reference's Buffer class mirrors host memory to the device
  * on demand, gpu/Buffer.cpp:235-346): uploads vertices + indices, draws with a deferred clear if

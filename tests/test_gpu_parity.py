@@ -176,3 +176,20 @@ def test_c2_full_size_properties(raster, crb):
     assert c["overflow"] == 0 and c["numActiveTiles"] == 240 * 135 and c["numTileEntries"] >= c["numBinEntries"] > 900000
     g = util.draw_gold(v, i, w, h, "gouraud", 3)
     _check_surfaces(cc, cd, g, lsb=1)
+
+
+def test_async_frames_match_sync(raster, crb):
+    """crb_draw_triangles_async + crb_finish: frames enqueued back to back equal the synchronous result;
+    an overflowing asynchronous frame is reported by finish()."""
+    import torch
+    w, h = 640, 360
+    v, i = crb.scenes.random_soup(20000, seed=5, stride_floats=8, size=0.3)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)           # synchronous: sizes the buffers
+    for _ in range(3):
+        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+        raster.drawTriangles(asynchronous=True)
+    raster.finish()
+    torch.cuda.synchronize()
+    color, depth = raster._keep["color"], raster._keep["depth"]
+    assert np.array_equal(color.numpy(), cc) and np.array_equal(depth.numpy(), cd)
+    assert raster.getCounters()["overflow"] == 0
