@@ -131,24 +131,45 @@ int prepareFrame(crb_ctx* c) {
     f.samplesLog2 = c->samplesLog2;
 
     if (c->fullWidth > 0) {
-        // sort-first window: snap in the full-frame grid, shift to this viewport's centre
+        // Sort-first window.  Triangles are set up in a PARENT viewport of at most
+        // 2048^2 px (the whole frame when it fits; otherwise the cell of an even grid over the frame
+        // that holds the window) exactly as an unsplit render of that viewport would set them up --
+        // snapped once in the subpixel grid of the full frame -- and the surface is a scissor
+        // rectangle inside it.  All windows of one parent therefore produce identical pixels.
+        const int ncx = (c->fullWidth + CR_MAXVIEWPORT_SIZE - 1) / CR_MAXVIEWPORT_SIZE, ncy = (c->fullHeight + CR_MAXVIEWPORT_SIZE - 1) / CR_MAXVIEWPORT_SIZE;
+        const int cellW = (((c->fullWidth + ncx - 1) / ncx) + 7) & ~7, cellH = (((c->fullHeight + ncy - 1) / ncy) + 7) & ~7;
+        const int px0 = (c->subX0 / cellW) * cellW, py0 = (c->subY0 / cellH) * cellH;
+        const int pw = std::min(cellW, c->fullWidth - px0), ph = std::min(cellH, c->fullHeight - py0);
+        if (c->subX0 + c->width > px0 + pw || c->subY0 + c->height > py0 + ph)
+            return setError(c, CRB_ERR_INVALID, "CudaRaster: a sort-first window must lie inside one %dx%d cell of the frame!", cellW, cellH);
+        f.windowed = 1;
         f.fullWidth = c->fullWidth;
         f.fullHeight = c->fullHeight;
-        f.centerOfsX = c->subX0 * CR_SUBPIXEL_SIZE + c->width * (CR_SUBPIXEL_SIZE / 2) - c->fullWidth * (CR_SUBPIXEL_SIZE / 2);
-        f.centerOfsY = c->subY0 * CR_SUBPIXEL_SIZE + c->height * (CR_SUBPIXEL_SIZE / 2) - c->fullHeight * (CR_SUBPIXEL_SIZE / 2);
-        f.subX0 = c->subX0;
-        f.subY0 = c->subY0;
-        f.clipLoX = (float)(2.0 * c->subX0 / c->fullWidth - 1.0);
-        f.clipHiX = (float)(2.0 * (c->subX0 + c->width) / c->fullWidth - 1.0);
-        f.clipLoY = (float)(2.0 * c->subY0 / c->fullHeight - 1.0);
-        f.clipHiY = (float)(2.0 * (c->subY0 + c->height) / c->fullHeight - 1.0);
+        f.viewportWidth = pw;
+        f.viewportHeight = ph;
+        f.centerOfsX = px0 * CR_SUBPIXEL_SIZE + pw * (CR_SUBPIXEL_SIZE / 2) - c->fullWidth * (CR_SUBPIXEL_SIZE / 2);
+        f.centerOfsY = py0 * CR_SUBPIXEL_SIZE + ph * (CR_SUBPIXEL_SIZE / 2) - c->fullHeight * (CR_SUBPIXEL_SIZE / 2);
+        f.subX0 = c->subX0 - px0;
+        f.subY0 = c->subY0 - py0;
+        f.clipLoX = (float)(2.0 * px0 / c->fullWidth - 1.0);
+        f.clipHiX = (float)(2.0 * (px0 + pw) / c->fullWidth - 1.0);
+        f.clipLoY = (float)(2.0 * py0 / c->fullHeight - 1.0);
+        f.clipHiY = (float)(2.0 * (py0 + ph) / c->fullHeight - 1.0);
+        f.cullLoX = (float)(2.0 * c->subX0 / c->fullWidth - 1.0);
+        f.cullHiX = (float)(2.0 * (c->subX0 + c->width) / c->fullWidth - 1.0);
+        f.cullLoY = (float)(2.0 * c->subY0 / c->fullHeight - 1.0);
+        f.cullHiY = (float)(2.0 * (c->subY0 + c->height) / c->fullHeight - 1.0);
     } else {
+        f.windowed = 0;
         f.fullWidth = c->width;
         f.fullHeight = c->height;
         f.centerOfsX = f.centerOfsY = 0;
-        f.clipLoX = f.clipLoY = -1.0f;
-        f.clipHiX = f.clipHiY = 1.0f;
+        f.subX0 = f.subY0 = 0;
+        f.clipLoX = f.clipLoY = f.cullLoX = f.cullLoY = -1.0f;
+        f.clipHiX = f.clipHiY = f.cullHiX = f.cullHiY = 1.0f;
     }
+    f.originX = f.viewportWidth * (CR_SUBPIXEL_SIZE / 2) - f.subX0 * CR_SUBPIXEL_SIZE;
+    f.originY = f.viewportHeight * (CR_SUBPIXEL_SIZE / 2) - f.subY0 * CR_SUBPIXEL_SIZE;
 
     f.deferredClear = c->deferredClear ? 1 : 0;
     f.clearColor = c->clearColor;

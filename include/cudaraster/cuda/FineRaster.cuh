@@ -134,8 +134,8 @@ __device__ __forceinline__ U32 fineRefill(const crb_frame& f, FineTriRec* recs, 
         const S32 dataIdx = resolveDataIdx(entry, f.triHeader);
         const uint4 h = __ldg(&f.triHeader[dataIdx]);
         // sample-space origin: centre of pixel (0,0) of the tile, viewport-centred subpixels
-        const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1));
-        const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1));
+        const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
+        const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
         S32 a[3], b[3], c[3];
         setupTileEdges(h, bx, by, a, b, c);
         // sample offsets inside the tile span [-8, 120] subpixels on both axes
@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, 4) fineRasterSingleKernel
     }
 
     // sample-space origin: centre of pixel (0,0) of the tile, viewport-centred subpixels
-    const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1));
-    const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1));
+    const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
+    const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
 
     for (int base = 0; base < queueCount; base += 32) {
         // ---- issue the loads of the batches ahead

@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRaster
                 const S32 entry = __ldg(&f.tileQueue[queueStart + (int)win - 1]);
                 const S32 dataIdx = resolveDataIdx(entry, f.triHeader);
                 const uint4 h = __ldg(&f.triHeader[dataIdx]);
-                const S32 bx = (pixelX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1));
-                const S32 by = (pixelY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - (f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1));
+                const S32 bx = (pixelX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
+                const S32 by = (pixelY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
                 S32 a[3], b[3], c[3];
                 setupTileEdges(h, bx, by, a, b, c);
                 const U32 cover = pixelSampleMask<SamplesLog2>(a, b, c);

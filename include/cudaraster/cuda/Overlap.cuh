@@ -14,7 +14,7 @@
 namespace FW {
 
 struct TriFootprint {
-    S32 x0, y0, x1, y1, x2, y2;      // vertices, viewport-corner subpixels
+    S32 x0, y0, x1, y1, x2, y2;      // vertices, surface-corner subpixels
     S32 pxLoX, pxLoY, pxHiX, pxHiY;  // inclusive pixel range that can contain covered samples
     bool empty;
 };
@@ -23,7 +23,7 @@ struct TriFootprint {
 template <int SamplesLog2>
 __device__ __forceinline__ TriFootprint triFootprint(U32 hx, U32 hy, U32 hz, const crb_frame& f) {
     TriFootprint t;
-    const S32 ox = f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1), oy = f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1);
+    const S32 ox = f.originX, oy = f.originY;
     t.x0 = (S32)(S16)(hx & 0xFFFF) + ox; t.y0 = ((S32)hx >> 16) + oy;
     t.x1 = (S32)(S16)(hy & 0xFFFF) + ox; t.y1 = ((S32)hy >> 16) + oy;
     t.x2 = (S32)(S16)(hz & 0xFFFF) + ox; t.y2 = ((S32)hz >> 16) + oy;

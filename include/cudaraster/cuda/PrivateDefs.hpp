@@ -46,15 +46,20 @@ struct crb_frame {
     const int32_t* indexBuffer;   // numTris x int3
 
     // ---- viewport (CRParams: viewportWidth .. numTiles)
-    int32_t viewportWidth, viewportHeight;   // surface size before rounding
+    int32_t viewportWidth, viewportHeight;   // size of the viewport the triangles are set up in: the surface itself, or the PARENT
+                                             // frame (<= 2048^2) of a sort-first window; header coordinates are relative to its centre
     int32_t widthPixels, heightPixels;       // rounded to tiles
     int32_t widthBins, heightBins, numBins;
     int32_t widthTiles, heightTiles, numTiles;
     int32_t samplesLog2;
-    // sort-first window: snap grid of the full frame, integer centre offset, clip window in NDC
+    // sort-first window: vertices are snapped in the grid of the FULL frame and shifted by the integer
+    // offset of the parent viewport's centre; the surface is a scissor rectangle inside the parent viewport.
     int32_t fullWidth, fullHeight, centerOfsX, centerOfsY;
-    int32_t subX0, subY0;                    // pixel origin of this viewport in the full frame
-    float clipLoX, clipHiX, clipLoY, clipHiY;
+    int32_t windowed;                        // 1 = sort-first window (surface != parent viewport)
+    int32_t subX0, subY0;                    // pixel origin of the surface (scissor) inside the parent viewport, multiples of 8
+    int32_t originX, originY;                // header subpixel coordinate + origin = subpixel position relative to the surface corner
+    float clipLoX, clipHiX, clipLoY, clipHiY;   // parent viewport in full-frame NDC: the window triangles are clipped against
+    float cullLoX, cullHiX, cullLoY, cullHiY;   // surface (scissor) in full-frame NDC: triangles wholly outside are culled early
 
     int32_t deferredClear;
     uint32_t clearColor, clearDepth;

@@ -78,11 +78,11 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
     int2 wv0 = make_int2(0, 0);
     if ((RenderModeFlags & (CRB_FLAG_DEPTH | CRB_FLAG_LERP)) != 0) {
         areaRcp = __frcp_rn((F32)area);
-        // Plane equations are set up in FULL-FRAME viewport-corner coordinates and translated
-        // to this viewport below, so a sort-first split renders the same depth / barycentrics as
-        // the unsplit frame.  For a plain viewport this is the reference's wv0.
-        wv0.x = s.p0.x + f.centerOfsX + (f.fullWidth << (CR_SUBPIXEL_LOG2 - 1));
-        wv0.y = s.p0.y + f.centerOfsY + (f.fullHeight << (CR_SUBPIXEL_LOG2 - 1));
+        // Plane equations are set up in viewport-corner coordinates (the reference's wv0) and, for
+        // a sort-first window, translated to the surface below: every window of one parent
+        // viewport therefore renders the very same depth / barycentrics as the unsplit viewport.
+        wv0.x = s.p0.x + (f.viewportWidth << (CR_SUBPIXEL_LOG2 - 1));
+        wv0.y = s.p0.y + (f.viewportHeight << (CR_SUBPIXEL_LOG2 - 1));
     }
 
     U32 zmin = 0;
@@ -225,9 +225,17 @@ __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) trian
         const F32 wx0l = __fmul_rn(v0.w, f.clipLoX), wx1l = __fmul_rn(v1.w, f.clipLoX), wx2l = __fmul_rn(v2.w, f.clipLoX);
         const F32 wy0h = __fmul_rn(v0.w, f.clipHiY), wy1h = __fmul_rn(v1.w, f.clipHiY), wy2h = __fmul_rn(v2.w, f.clipHiY);
         const F32 wy0l = __fmul_rn(v0.w, f.clipLoY), wy1l = __fmul_rn(v1.w, f.clipLoY), wy2l = __fmul_rn(v2.w, f.clipLoY);
-        const bool outside = ((wx0h < v0.x) & (wx1h < v1.x) & (wx2h < v2.x)) | ((wx0l > v0.x) & (wx1l > v1.x) & (wx2l > v2.x)) |
-                             ((wy0h < v0.y) & (wy1h < v1.y) & (wy2h < v2.y)) | ((wy0l > v0.y) & (wy1l > v1.y) & (wy2l > v2.y)) |
-                             ((v0.w < v0.z) & (v1.w < v1.z) & (v2.w < v2.z)) | ((v0.w < -v0.z) & (v1.w < -v1.z) & (v2.w < -v2.z));
+        bool outside = ((wx0h < v0.x) & (wx1h < v1.x) & (wx2h < v2.x)) | ((wx0l > v0.x) & (wx1l > v1.x) & (wx2l > v2.x)) |
+                       ((wy0h < v0.y) & (wy1h < v1.y) & (wy2h < v2.y)) | ((wy0l > v0.y) & (wy1l > v1.y) & (wy2l > v2.y)) |
+                       ((v0.w < v0.z) & (v1.w < v1.z) & (v2.w < v2.z)) | ((v0.w < -v0.z) & (v1.w < -v1.z) & (v2.w < -v2.z));
+        if (f.windowed) {
+            // sort-first window: also cull what lies wholly outside the surface rectangle (a pure cull:
+            // a half-space that holds all three vertices holds the triangle, whatever the sign of w)
+            outside |= ((__fmul_rn(v0.w, f.cullHiX) < v0.x) & (__fmul_rn(v1.w, f.cullHiX) < v1.x) & (__fmul_rn(v2.w, f.cullHiX) < v2.x)) |
+                       ((__fmul_rn(v0.w, f.cullLoX) > v0.x) & (__fmul_rn(v1.w, f.cullLoX) > v1.x) & (__fmul_rn(v2.w, f.cullLoX) > v2.x)) |
+                       ((__fmul_rn(v0.w, f.cullHiY) < v0.y) & (__fmul_rn(v1.w, f.cullHiY) < v1.y) & (__fmul_rn(v2.w, f.cullHiY) < v2.y)) |
+                       ((__fmul_rn(v0.w, f.cullLoY) > v0.y) & (__fmul_rn(v1.w, f.cullLoY) > v1.y) & (__fmul_rn(v2.w, f.cullLoY) > v2.y));
+        }
         if (outside) {
             f.triSubtris[tri] = 0;
         } else {

@@ -19,7 +19,9 @@ class Config(ctypes.Structure):
                 ("clearColor", ctypes.c_uint32), ("clearDepth", ctypes.c_uint32), ("numThreads", ctypes.c_int32),
                 ("fullWidth", ctypes.c_int32), ("fullHeight", ctypes.c_int32), ("centerOfsX", ctypes.c_int32), ("centerOfsY", ctypes.c_int32),
                 ("clipLoX", ctypes.c_float), ("clipHiX", ctypes.c_float), ("clipLoY", ctypes.c_float), ("clipHiY", ctypes.c_float),
-                ("subX0", ctypes.c_int32), ("subY0", ctypes.c_int32)]
+                ("subX0", ctypes.c_int32), ("subY0", ctypes.c_int32), ("vpWidth", ctypes.c_int32), ("vpHeight", ctypes.c_int32),
+                ("cullLoX", ctypes.c_float), ("cullHiX", ctypes.c_float), ("cullLoY", ctypes.c_float), ("cullHiY", ctypes.c_float),
+                ("windowed", ctypes.c_int32)]
 
 
 class Counts(ctypes.Structure):
@@ -69,6 +71,16 @@ def lib():
     return _LIB
 
 
+def parent_cell(full, x0, size, limit=2048):
+    """(origin, extent) of the parent viewport of a window [x0, x0+size) along one axis of a `full` px frame."""
+    n = -(-full // limit)
+    cell = (-(-full // n) + 7) & ~7
+    p0 = (x0 // cell) * cell
+    pw = min(cell, full - p0)
+    assert x0 + size <= p0 + pw, "a sort-first window must lie inside one parent cell"
+    return p0, pw
+
+
 def make_config(width, height, samples_log2=0, flags=FLAG_DEPTH, vertex_stride=16, shader="passthrough", blend="BlendReplace",
                 clear=None, threads=1, sub=None):
     """clear = (abgr, encodedDepth) or None; sub = (fullW, fullH, x0, y0) for a sort-first window."""
@@ -81,19 +93,30 @@ def make_config(width, height, samples_log2=0, flags=FLAG_DEPTH, vertex_stride=1
     c.numThreads = threads
     if sub is None:
         c.fullWidth, c.fullHeight, c.centerOfsX, c.centerOfsY = width, height, 0, 0
-        c.clipLoX = c.clipLoY = -1.0
-        c.clipHiX = c.clipHiY = 1.0
+        c.vpWidth, c.vpHeight = width, height
+        c.clipLoX = c.clipLoY = c.cullLoX = c.cullLoY = -1.0
+        c.clipHiX = c.clipHiY = c.cullHiX = c.cullHiY = 1.0
         c.subX0 = c.subY0 = 0
+        c.windowed = 0
     else:
+        # sort-first window: parent viewport = the cell of an even grid of <= 2048 px cells that holds the window
+        # (the whole frame when it fits); same rule as cudaraster-linux_b200/csrc/Context.cu prepareFrame()
         fw, fh, x0, y0 = sub
+        (px0, pw), (py0, ph) = parent_cell(fw, x0, width), parent_cell(fh, y0, height)
         c.fullWidth, c.fullHeight = fw, fh
-        c.subX0, c.subY0 = x0, y0
-        c.centerOfsX = x0 * 16 + width * 8 - fw * 8
-        c.centerOfsY = y0 * 16 + height * 8 - fh * 8
-        c.clipLoX = np.float32(2.0 * x0 / fw - 1.0)
-        c.clipHiX = np.float32(2.0 * (x0 + width) / fw - 1.0)
-        c.clipLoY = np.float32(2.0 * y0 / fh - 1.0)
-        c.clipHiY = np.float32(2.0 * (y0 + height) / fh - 1.0)
+        c.vpWidth, c.vpHeight = pw, ph
+        c.subX0, c.subY0 = x0 - px0, y0 - py0
+        c.centerOfsX = px0 * 16 + pw * 8 - fw * 8
+        c.centerOfsY = py0 * 16 + ph * 8 - fh * 8
+        c.clipLoX = np.float32(2.0 * px0 / fw - 1.0)
+        c.clipHiX = np.float32(2.0 * (px0 + pw) / fw - 1.0)
+        c.clipLoY = np.float32(2.0 * py0 / fh - 1.0)
+        c.clipHiY = np.float32(2.0 * (py0 + ph) / fh - 1.0)
+        c.cullLoX = np.float32(2.0 * x0 / fw - 1.0)
+        c.cullHiX = np.float32(2.0 * (x0 + width) / fw - 1.0)
+        c.cullLoY = np.float32(2.0 * y0 / fh - 1.0)
+        c.cullHiY = np.float32(2.0 * (y0 + height) / fh - 1.0)
+        c.windowed = 1
     return c
 
 

@@ -266,17 +266,27 @@ struct Config {
     S32 deferredClear;
     U32 clearColor, clearDepth;
     S32 numThreads;      // fine-stage worker threads (band parallel); <=1 = scalar
-    // Sort-first sub-viewport support: vertices are snapped once in the
-    // full-frame grid (fullWidth x fullHeight) and the integer offset of this viewport's centre
-    // from the full-frame centre (in subpixels) is subtracted afterwards.  For a plain single
-    // viewport fullWidth = width, fullHeight = height, offsets = 0.
+    // Sort-first window support.  Triangles are set up in a PARENT viewport
+    // (vpWidth x vpHeight <= 2048^2: the whole frame when it fits) exactly as the reference sets
+    // them up for a viewport of that size, except that vertices are snapped once in the grid of
+    // the FULL frame (fullWidth x fullHeight) and shifted by the integer offset of the parent's
+    // centre from the full-frame centre (centerOfs, subpixels).  The surface (width x height) is a
+    // scissor rectangle at pixel (subX0, subY0) of the parent.  Plain single viewport:
+    // vp = full = surface size, offsets = 0.
     S32 fullWidth, fullHeight, centerOfsX, centerOfsY;
-    // Clip window of this viewport in full-frame NDC (x in [clipLoX,clipHiX] * w, same for y).
+    // Clip window = the parent viewport in full-frame NDC (x in [clipLoX,clipHiX] * w, same for y).
     // (-1,+1) for a plain viewport, which makes every expression below bit-identical to the
     // reference's  w < |x|  /  w + x  /  w - x  forms (multiplying by +-1.0f is exact).
     F32 clipLoX, clipHiX, clipLoY, clipHiY;
-    S32 subX0, subY0;    // pixel origin of this viewport inside the full frame (multiples of 8)
+    S32 subX0, subY0;    // pixel origin of the surface inside the parent viewport (multiples of 8)
+    S32 vpWidth, vpHeight;
+    // Cull window = the surface in full-frame NDC: triangles wholly outside it are dropped early.
+    F32 cullLoX, cullHiX, cullLoY, cullHiY;
+    S32 windowed;
 };
+// header subpixel coordinate + origin = subpixel position relative to the surface corner
+static inline S64 originX(const Config& c) { return (S64)c.vpWidth * 8 - (S64)c.subX0 * 16; }
+static inline S64 originY(const Config& c) { return (S64)c.vpHeight * 8 - (S64)c.subY0 * 16; }
 
 struct Counts {  // golden counts that define the algorithmic bytes
     S64 numTris, numSubtris, numVisibleTris;
@@ -315,8 +325,8 @@ static inline int prepareTriangle(const Config& c, const Snapped& s, I2& d1, I2&
     if (area <= 0) return 1;
 
     int sampleSize = 1 << (kSubpixelLog2 - c.samplesLog2);
-    S32 biasX = (c.width << (kSubpixelLog2 - 1)) - (sampleSize >> 1);
-    S32 biasY = (c.height << (kSubpixelLog2 - 1)) - (sampleSize >> 1);
+    S32 biasX = (c.vpWidth << (kSubpixelLog2 - 1)) - (sampleSize >> 1);
+    S32 biasY = (c.vpHeight << (kSubpixelLog2 - 1)) - (sampleSize >> 1);
     S32 lox = wrapS32((S64)s.lo.x + (sampleSize - 1) + biasX) & -sampleSize;
     S32 loy = wrapS32((S64)s.lo.y + (sampleSize - 1) + biasY) & -sampleSize;
     S32 hix = wrapS32((S64)s.hi.x + biasX) & -sampleSize;
@@ -348,11 +358,11 @@ static inline void setupTriangle(const Config& c, TriHeader* th, TriData* td, co
     I2 wv0 = {0, 0};
     if (c.flags & (kFlagDepth | kFlagLerp)) {
         areaRcp = 1.0f / (F32)area;
-        // plane equations are set up in FULL-FRAME viewport-corner coordinates and translated to
-        // this viewport afterwards (exact integer shift), so a sort-first split renders the very
-        // same depth / barycentric values as the unsplit frame.  Plain viewport: identical to
-        // TriangleSetup.inl:127-128.
-        wv0 = {s.p0.x + c.centerOfsX + (c.fullWidth << (kSubpixelLog2 - 1)), s.p0.y + c.centerOfsY + (c.fullHeight << (kSubpixelLog2 - 1))};
+        // plane equations are set up in viewport-corner coordinates (TriangleSetup.inl:127-128) and,
+        // for a sort-first window, translated to the surface afterwards (exact integer shift), so
+        // every window of one parent viewport renders the very same depth / barycentric values
+        // as the unsplit viewport.
+        wv0 = {s.p0.x + (c.vpWidth << (kSubpixelLog2 - 1)), s.p0.y + (c.vpHeight << (kSubpixelLog2 - 1))};
     }
     U3 zp = {0, 0, 0};
     U32 zmin = 0, zslope = 0;
@@ -427,6 +437,13 @@ static inline int setupOneTriangle(const Config& c, const void* verts, const S32
     for (int a = 0; a < 3; a++) {
         if ((v0[3] * hi[a] < v0[a]) & (v1[3] * hi[a] < v1[a]) & (v2[3] * hi[a] < v2[a])) return 0;
         if ((v0[3] * lo[a] > v0[a]) & (v1[3] * lo[a] > v1[a]) & (v2[3] * lo[a] > v2[a])) return 0;
+    }
+    if (c.windowed) {   // sort-first window: wholly outside the surface rectangle -> culled (pure cull)
+        const F32 clo[2] = {c.cullLoX, c.cullLoY}, chi[2] = {c.cullHiX, c.cullHiY};
+        for (int a = 0; a < 2; a++) {
+            if ((v0[3] * chi[a] < v0[a]) & (v1[3] * chi[a] < v1[a]) & (v2[3] * chi[a] < v2[a])) return 0;
+            if ((v0[3] * clo[a] > v0[a]) & (v1[3] * clo[a] > v1[a]) & (v2[3] * clo[a] > v2[a])) return 0;
+        }
     }
     // (2) inside the depth range and inside the S16 guard band -> fast path (:285-321)
     Snapped s;
@@ -525,8 +542,8 @@ static inline U64 coverTile(const Config& c, const TriHeader& h, int tileX, int 
     U64 m = 0;
     for (int y = 0; y < 8; y++)
         for (int x = 0; x < 8; x++) {
-            S64 sx = (S64)(tileX * 8 + x) * 16 + 8 - (S64)c.width * 8;
-            S64 sy = (S64)(tileY * 8 + y) * 16 + 8 - (S64)c.height * 8;
+            S64 sx = (S64)(tileX * 8 + x) * 16 + 8 - originX(c);
+            S64 sy = (S64)(tileY * 8 + y) * 16 + 8 - originY(c);
             if (sampleInside(e, sx, sy)) m |= (U64)1 << (x + 8 * y);
         }
     return m;
@@ -534,7 +551,7 @@ static inline U64 coverTile(const Config& c, const TriHeader& h, int tileX, int 
 // sample mask of one pixel (bit i = sample i), cuda/Util.inl:340-383
 static inline U32 coverPixelSamples(const Config& c, const Edges& e, int px, int py) {
     const int S = c.samplesLog2, N = 1 << S;
-    S64 cx = (S64)px * 16 + 8 - (S64)c.width * 8, cy = (S64)py * 16 + 8 - (S64)c.height * 8;
+    S64 cx = (S64)px * 16 + 8 - originX(c), cy = (S64)py * 16 + 8 - originY(c);
     U32 m = 0;
     for (int i = 0; i < N; i++) {
         S64 offx = S == 0 ? 0 : (S64)(kMsaaX[S][i] * 2 + 1 - N) * (1 << (kSubpixelLog2 - S - 1));
@@ -657,10 +674,10 @@ static inline void rasterTriangle(const Config& c, const void* verts, const TriH
     Edges e;
     edgesFromHeader(h, e);
     // tile bbox from the snapped vertices (viewport-corner subpixels), then exact tests per sample
-    S64 minx = std::min(std::min(h.v0x, h.v1x), h.v2x) + (S64)c.width * 8;
-    S64 maxx = std::max(std::max(h.v0x, h.v1x), h.v2x) + (S64)c.width * 8;
-    S64 miny = std::min(std::min(h.v0y, h.v1y), h.v2y) + (S64)c.height * 8;
-    S64 maxy = std::max(std::max(h.v0y, h.v1y), h.v2y) + (S64)c.height * 8;
+    S64 minx = std::min(std::min(h.v0x, h.v1x), h.v2x) + originX(c);
+    S64 maxx = std::max(std::max(h.v0x, h.v1x), h.v2x) + originX(c);
+    S64 miny = std::min(std::min(h.v0y, h.v1y), h.v2y) + originY(c);
+    S64 maxy = std::max(std::max(h.v0y, h.v1y), h.v2y) + originY(c);
     if (maxx < 0 || maxy < 0) return;
     int tx0 = (int)std::max<S64>(minx >> 7, 0), tx1 = (int)std::min<S64>(maxx >> 7, s.roundedW / 8 - 1);
     int ty0 = (int)std::max<S64>(miny >> 7, tileRowLo), ty1 = (int)std::min<S64>(maxy >> 7, tileRowHi - 1);
@@ -779,7 +796,7 @@ static inline S32 renderFrame(const Config& c, const void* verts, const S32* ind
                 nsub++;
                 S32 di = n == 1 ? tri : (S32)hdr[(size_t)tri].misc + sub;
                 const TriHeader& h = hdr[(size_t)di];
-                S64 v0x = h.v0x + (S64)c.width * 8, v0y = h.v0y + (S64)c.height * 8;
+                S64 v0x = h.v0x + originX(c), v0y = h.v0y + originY(c);
                 S64 d01x = h.v1x - h.v0x, d01y = h.v1y - h.v0y, d02x = h.v2x - h.v0x, d02y = h.v2y - h.v0y;
                 S64 lox = v0x + std::min<S64>(0, std::min(d01x, d02x)), hix = v0x + std::max<S64>(0, std::max(d01x, d02x));
                 S64 loy = v0y + std::min<S64>(0, std::min(d01y, d02y)), hiy = v0y + std::max<S64>(0, std::max(d01y, d02y));

@@ -7,7 +7,7 @@ using namespace gold;
 
 extern "C" {
 
-int gold_abi_version(void) { return 3; }
+int gold_abi_version(void) { return 4; }
 int gold_sizeof_config(void) { return (int)sizeof(Config); }
 int gold_sizeof_counts(void) { return (int)sizeof(Counts); }
 
@@ -44,12 +44,12 @@ void gold_setup_pleq(const float* values, const int* v0, const int* d1, const in
 // 8x8 pixel-centre coverage of tile (tileX,tileY) for a header in a width x height viewport
 unsigned long long gold_cover_tile(const void* header, int width, int height, int tileX, int tileY) {
     Config c{};
-    c.width = width; c.height = height;
+    c.width = c.vpWidth = width; c.height = c.vpHeight = height;
     return coverTile(c, *(const TriHeader*)header, tileX, tileY);
 }
 unsigned gold_cover_samples(const void* header, int width, int height, int samplesLog2, int px, int py) {
     Config c{};
-    c.width = width; c.height = height; c.samplesLog2 = samplesLog2;
+    c.width = c.vpWidth = width; c.height = c.vpHeight = height; c.samplesLog2 = samplesLog2;
     Edges e;
     edgesFromHeader(*(const TriHeader*)header, e);
     return coverPixelSamples(c, e, px, py);

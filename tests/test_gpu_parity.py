@@ -193,3 +193,26 @@ def test_async_frames_match_sync(raster, crb):
     color, depth = raster._keep["color"], raster._keep["depth"]
     assert np.array_equal(color.numpy(), cc) and np.array_equal(depth.numpy(), cd)
     assert raster.getCounters()["overflow"] == 0
+
+
+def test_4k_sort_first_windows(raster, crb):
+    """BASELINE config 5(i) shape: a 3840x2160 frame (beyond the 2048 px viewport limit) as 8 windows
+    of 960x1080; every window bit-exact against the oracle, and the 2x2 split gives the same frame."""
+    from cudaraster_linux_b200 import multigpu
+    fw, fh = 3840, 2160
+    v, i = crb.scenes.grid_gouraud(300, 200)
+    frames = {}
+    for parts in (8, 4):
+        color = np.zeros((fh, fw), np.uint32)
+        depth = np.zeros((fh, fw), np.uint32)
+        for (x0, y0, w, h) in multigpu.split_frame(fw, fh, parts):
+            cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0))
+            if parts == 8:
+                g = util.draw_gold(v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0))
+                _check_surfaces(cc, cd, g, lsb=1)
+            color[y0:y0 + h, x0:x0 + w] = cc[:h, :w]
+            depth[y0:y0 + h, x0:x0 + w] = cd[:h, :w]
+        frames[parts] = (color, depth)
+    raster.setSubViewport(0, 0, 0, 0)
+    assert np.array_equal(frames[8][0], frames[4][0]) and np.array_equal(frames[8][1], frames[4][1])
+    assert (frames[8][1] < 0xFFFFBB3F).mean() > 0.9
