@@ -1,0 +1,83 @@
+// The reference's demo frame (test/App.cpp:208-241 cube, test/SceneCR.cpp:243-317 render) written
+// against the kept host API (include/cudaraster/CudaRaster.hpp) -- no GL, no GLUT:
+//   vertex shader kernel -> deferredClear -> setVertexBuffer/setIndexBuffer -> drawTriangles -> getStats.
+// Usage: cube <libuserpipes.so> <out.raw> [width height]
+// Writes width, height (int32) then the colour and depth surfaces (U32 each) to out.raw.
+#include <cudaraster/CudaRaster.hpp>
+
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+using namespace FW;
+
+typedef int (*VertexShaderFn)(const float*, const void*, void*, int, void*);
+
+static void mul(float* o, const float* a, const float* b) {  // column-major o = a * b
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) {
+            float s = 0.0f;
+            for (int k = 0; k < 4; k++) s += a[k * 4 + r] * b[c * 4 + k];
+            o[c * 4 + r] = s;
+        }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) { printf("usage: cube <libuserpipes.so> <out.raw> [w h]\n"); return 2; }
+    const int w = argc > 4 ? atoi(argv[3]) : 1024, h = argc > 4 ? atoi(argv[4]) : 768;
+
+    static const float pos[8][3] = {{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
+    static const int idx[12][3] = {{7, 3, 1}, {7, 1, 5}, {7, 5, 6}, {6, 5, 4}, {6, 4, 2}, {2, 4, 0}, {2, 0, 3}, {3, 0, 1}, {3, 7, 6}, {3, 6, 2}, {5, 1, 0}, {5, 0, 4}};
+
+    // perspective(60 deg, w/h, 0.1, 100) * lookAt((2,2,4) -> origin)
+    const float f = 1.0f / tanf(30.0f * 3.14159265f / 180.0f), zn = 0.1f, zf = 100.0f, asp = (float)w / (float)h;
+    const float proj[16] = {f / asp, 0, 0, 0, 0, f, 0, 0, 0, 0, -(zf + zn) / (zf - zn), -1, 0, 0, -2 * zf * zn / (zf - zn), 0};
+    const float eye[3] = {2, 2, 4};
+    float fw[3] = {-eye[0], -eye[1], -eye[2]};
+    const float fl = sqrtf(fw[0] * fw[0] + fw[1] * fw[1] + fw[2] * fw[2]);
+    for (float& v : fw) v /= fl;
+    float s[3] = {fw[1] * 0 - fw[2] * 1, fw[2] * 0 - fw[0] * 0, fw[0] * 1 - fw[1] * 0};  // f x up(0,1,0)
+    const float sl = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+    for (float& v : s) v /= sl;
+    const float u[3] = {s[1] * fw[2] - s[2] * fw[1], s[2] * fw[0] - s[0] * fw[2], s[0] * fw[1] - s[1] * fw[0]};
+    const float view[16] = {s[0], u[0], -fw[0], 0, s[1], u[1], -fw[1], 0, s[2], u[2], -fw[2], 0,
+                            -(s[0] * eye[0] + s[1] * eye[1] + s[2] * eye[2]), -(u[0] * eye[0] + u[1] * eye[1] + u[2] * eye[2]), fw[0] * eye[0] + fw[1] * eye[1] + fw[2] * eye[2], 1};
+    float mvp[16];
+    mul(mvp, proj, view);
+
+    CudaRaster cr;
+    cr.init();
+    CudaSurface color(Vec2i(w, h), CudaSurface::FORMAT_RGBA8), depth(Vec2i(w, h), CudaSurface::FORMAT_DEPTH32);
+    CudaModule module(argv[1]);
+    VertexShaderFn vs = (VertexShaderFn)dlsym(module.getHandle(), "userLaunchVertexShader");
+    if (!vs) fail("cube: userLaunchVertexShader not found in %s", argv[1]);
+
+    Buffer inVerts(pos, sizeof(pos)), indices(idx, sizeof(idx)), shadedVerts;
+    shadedVerts.resizeDiscard(8 * 32);  // sizeof(GouraudVertex)
+    if (vs(mvp, inVerts.getCudaPtr(), shadedVerts.getCudaPtr(), 8, NULL) != 0) fail("cube: vertex shader launch failed");
+
+    cr.setSurfaces(&color, &depth);
+    cr.setPixelPipe(&module, "PixelPipe_user");
+    cr.deferredClear(Vec4f(0.2f, 0.4f, 0.8f, 1.0f));
+    cr.setVertexBuffer(&shadedVerts, 0);
+    cr.setIndexBuffer(&indices, 0, 12);
+    cr.drawTriangles();
+    const CudaRaster::Stats st = cr.getStats();
+    printf("CudaRaster: setup = %.3f ms, bin = %.3f ms, coarse = %.3f ms, fine = %.3f ms\n", st.setupTime * 1e3f, st.binTime * 1e3f, st.coarseTime * 1e3f, st.fineTime * 1e3f);
+    printf("%s", cr.getProfilingInfo().c_str());
+
+    std::vector<U32> hc(color.getSizeBytes() / 4), hd(depth.getSizeBytes() / 4);
+    color.download(hc.data());
+    depth.download(hd.data());
+    std::vector<float> hv(8 * 8);
+    shadedVerts.getRange(hv.data(), 0, 8 * 32);
+    FILE* fp = fopen(argv[2], "wb");
+    if (!fp) fail("cube: cannot write %s", argv[2]);
+    const int dims[2] = {color.getTextureSize().x, color.getTextureSize().y};
+    fwrite(dims, 4, 2, fp);
+    fwrite(hc.data(), 4, hc.size(), fp);
+    fwrite(hd.data(), 4, hd.size(), fp);
+    fwrite(hv.data(), 4, hv.size(), fp);
+    fclose(fp);
+    return 0;
+}
