@@ -59,9 +59,17 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--frames", type=int, default=7)
     ap.add_argument("--check", action="store_true", help="compare depth/colour with the CPU oracle")
+    ap.add_argument("--check-setup", action="store_true", help="compare triSubtris/triHeader/triData with the CPU oracle, bit for bit")
     args = ap.parse_args()
     import bench
-    desc, verts, idx, w, h, shader, s_log2, flags, _ = bench.make_scene(args.workload)
+    if args.workload.startswith("soup"):
+        # parity scene: mixed sizes, frustum-crossing and w <= 0 triangles (exercises the clipper)
+        import cudaraster_linux_b200 as crb
+        shader, flags, s_log2 = {"soup": ("gouraud", 3, 0), "soup_msaa": ("gouraud", 3, 2), "soup_pass": ("passthrough", 1, 0)}[args.workload]
+        w, h, desc = 640, 360, args.workload
+        verts, idx = crb.scenes.random_soup(20000, seed=1237, stride_floats=8 if shader == "gouraud" else 4)
+    else:
+        desc, verts, idx, w, h, shader, s_log2, flags, _ = bench.make_scene(args.workload)
     pipe = "ref_%s_s%d_f%d_BlendReplace" % (shader, s_log2, flags)
     lib = load()
     names = [lib.crref_pipe_name(i).decode() for i in range(lib.crref_num_pipes())]
@@ -74,6 +82,21 @@ def main():
     out = {"status": "ok", "what": "reference kernels rebuilt for sm_100a behind oracle/ref_kernels/shim.h, launch shapes of CudaRaster.cpp:593-655",
            "stage_ms": dict(zip(("triangleSetup", "binRaster", "coarseRaster", "fineRaster"), med)), "frame_ms": sum(med),
            "Mtris/s": idx.shape[0] / (sum(med) * 1e-3) / 1e6, "atomics": atomics}
+    if args.check_setup:
+        from tests import util
+        n = idx.shape[0]
+        nsub = atomics[0]
+        sub = np.zeros(n, np.uint8)
+        hdr = np.zeros((nsub, 4), np.uint32)
+        dat = np.zeros((nsub, 16), np.uint32)
+        if lib.crref_get_setup_output(n, nsub, sub.ctypes.data, hdr.ctypes.data, dat.ctypes.data) != 0:
+            raise RuntimeError(lib.crref_last_error().decode())
+        gs = util.gold_setup(verts, idx, w, h, shader, flags, s_log2)
+        try:
+            n_single, n_multi = util.compare_setup({"triSubtris": sub, "triHeader": hdr, "triData": dat, "counters": {"numSubtris": nsub}}, gs, n, flags)
+            out["setup"] = {"status": "bit-exact", "single": n_single, "clipped": n_multi, "numSubtris": int(nsub)}
+        except AssertionError as e:
+            out["setup"] = {"status": "mismatch: %s" % str(e)[:200]}
     if args.check:
         from tests import util
         g = util.draw_gold(verts, idx, w, h, shader, flags, s_log2)

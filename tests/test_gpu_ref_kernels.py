@@ -1,0 +1,37 @@
+"""GPU: the REFERENCE's own CUDA kernels, rebuilt for sm_100a from the sources under /root/reference
+(oracle/_ref/libcrref_cuda.so, built in the container by oracle/Makefile and shipped to the box),
+as a second oracle.  Run in a subprocess with a timeout: the Fermi code is implicitly
+warp-synchronous and is not guaranteed to terminate on Blackwell.
+
+What is asserted: the reference's TRIANGLE SETUP kernel (per-thread code) produces bit-identical
+triSubtris / triHeader / triData to the CPU oracle -- this pins the oracle's snap / cull / clip /
+plane-equation arithmetic to the reference's real device code.  The later stages are reported, not
+asserted: they mis-execute on sm_100a (profiles/r1_ref_kernels.md)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(workload):
+    lib = os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref/libcrref_cuda.so not built (needs /root/reference at build time)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "2", "--check", "--check-setup"],
+                       capture_output=True, text=True, timeout=300)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, "reference kernels failed: rc=%d %s" % (r.returncode, (r.stderr or r.stdout)[-500:])
+    return json.loads(lines[-1])
+
+
+@pytest.mark.parametrize("workload", ["soup", "soup_pass", "soup_msaa"])
+def test_reference_setup_kernel_matches_oracle(workload):
+    out = _run(workload)
+    print(json.dumps(out))
+    assert out["setup"]["status"] == "bit-exact", out["setup"]
+    assert out["setup"]["single"] > 1000 and out["setup"]["clipped"] > 100
