@@ -234,10 +234,12 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
     const int chunk = blockIdx.x * kWarps + warp;
     if (chunk >= f.numChunks) return;
     const int triBegin = chunk * f.chunkTris, triEnd = min(triBegin + f.chunkTris, f.numTris);
-    // first batch in flight while the cursors are set up (a header slot of a culled triangle holds
-    // stale data, which is never interpreted: n == 0 makes the lane idle)
-    int nNext = triBegin + lane < triEnd ? (int)f.triSubtris[triBegin + lane] : 0;
-    uint4 hNext = triBegin + lane < triEnd ? __ldg(&f.triHeader[triBegin + lane]) : make_uint4(0, 0, 0, 0);
+    // triSubtris runs two batches ahead, headers one batch ahead and only for surviving triangles
+    // (on a cull-heavy scene most header slots are never written and must not be fetched)
+    auto loadN = [&](int t) { return t < triEnd ? (int)f.triSubtris[t] : 0; };
+    auto loadH = [&](int t, int n) { return n == 1 ? __ldg(&f.triHeader[t]) : make_uint4(0, 0, 0, 0); };
+    int nCur = loadN(triBegin + lane), nNext = loadN(triBegin + 32 + lane);
+    uint4 hCur = loadH(triBegin + lane, nCur);
     if (f.atomics->overflow != 0) return;
     WarpCells& wc = s_cells[warp];
     const unsigned ltMask = laneMaskLt();
@@ -251,12 +253,11 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
 #pragma unroll 1
     for (int t0 = triBegin; t0 < triEnd; t0 += 32) {
         const int tri = t0 + lane;
-        const int n = nNext;
-        const uint4 h = hNext;
-        if (t0 + 32 + lane < triEnd) {
-            nNext = (int)f.triSubtris[t0 + 32 + lane];
-            hNext = __ldg(&f.triHeader[t0 + 32 + lane]);
-        } else nNext = 0;
+        const int n = nCur;
+        const uint4 h = hCur;
+        hCur = loadH(t0 + 32 + lane, nNext);
+        nCur = nNext;
+        nNext = loadN(t0 + 64 + lane);
         if (__all_sync(0xFFFFFFFFu, n <= 1)) {
             const S32 entry = n == 1 ? tri * 8 + 7 : -1;
             const TriFootprint fp = footprintOf<SamplesLog2>(f, entry, h);

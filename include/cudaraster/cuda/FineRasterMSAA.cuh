@@ -40,30 +40,51 @@ __device__ __forceinline__ U32 pixelSampleMask(const S32 (&a)[3], const S32 (&b)
     return m;
 }
 
+// Per-warp staging of the current batch for the multi-sample kernel: edge equations relative to
+// the centre of pixel (0,0) of the tile (needed again per fragment for the exact sample test),
+// depth plane relative to the tile, queue entry and record slot.  Lane-indexed SoA.
+struct FineBatchMSAA {
+    S32 a0[32], b0[32], c0[32], a1[32], b1[32], c1[32], a2[32], b2[32], c2[32];
+    U32 zx[32], zy[32], zb[32];
+    S32 entry[32];
+    S32 dataIdx[32];
+};
+
+// Same scheme as the single-sample kernel (FineRaster.cuh): lane j builds a 64-bit PIXEL mask of
+// triangle j -- conservative: the edge functions are relaxed by the largest sample offset, so the
+// mask is a superset of the pixels with a covered sample -- two warp transposes hand every lane
+// the triangles touching its two pixels, and the ownership loop tests the N samples of those
+// fragments exactly, in queue order.
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
 __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRasterMultiKernel(const __grid_constant__ crb_frame f) {
     constexpr int N = 1 << SamplesLog2;
     constexpr int kWarps = FineWarps<SamplesLog2>::Value;
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
-    __shared__ __align__(16) FineTriRec s_recs[kWarps][32];
+    constexpr S32 kMaxOfs = (N - 1) << (CR_SUBPIXEL_LOG2 - SamplesLog2 - 1);   // largest |sample offset| from the pixel centre, subpixels
+    __shared__ FineBatchMSAA s_batch[kWarps];
     __shared__ U32 s_depth[kWarps][N * CR_TILE_SQR];
-    __shared__ U32 s_aux[kWarps][N * CR_TILE_SQR];   // colour (immediate mode) or winner position (deferred mode)
+    __shared__ U32 s_aux[kWarps][N * CR_TILE_SQR];   // colour (immediate mode) or winner entry + 1 (deferred mode)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int activeIdx = blockIdx.x * kWarps + warp;
+    const int4 rec = __ldg(&f.activeRecs[activeIdx]);
     if (f.atomics->overflow != 0) return;
     if (activeIdx >= f.atomics->numActiveTiles) return;
 
     BlendShaderClass blendProbe;
     const bool deferred = !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
 
-    FineTriRec* recs = s_recs[warp];
+    FineBatchMSAA& sb = s_batch[warp];
     U32* tDepth = s_depth[warp];
     U32* tAux = s_aux[warp];
-    const int tileIdx = __ldg(&f.activeTiles[activeIdx]);
+    const int tileIdx = rec.x;
     const int tileY = tileIdx / f.widthTiles, tileX = tileIdx - tileY * f.widthTiles;
-    const int queueStart = __ldg(&f.tileStart[tileIdx]);
-    const int queueCount = __ldg(&f.tileCount[tileIdx]);
+    const int queueCount = rec.z;
+    const S32* __restrict__ queue = f.tileQueue + rec.y;
+
+    S32 entryB = (32 + lane < queueCount) ? __ldg(&queue[32 + lane]) : -1;
+    FineFetch cur;
+    fineFetch<RenderModeFlags>(cur, f, lane < queueCount ? __ldg(&queue[lane]) : -1);
 
     const int lx = lane & 7, ly = lane >> 3;
     const int pixelX = (tileX << CR_TILE_LOG2) + lx;
@@ -89,59 +110,102 @@ __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRaster
         }
     __syncwarp();
 
+    const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
+    const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
     const S32 sx0 = lx << CR_SUBPIXEL_LOG2;
     const S32 sy0 = ly << CR_SUBPIXEL_LOG2;
 
     for (int base = 0; base < queueCount; base += 32) {
-        U32 liveMask = fineRefill<SamplesLog2, RenderModeFlags>(f, recs, queueStart + base, queueCount - base, tileX, tileY);
-        while (liveMask) {
-            const int j = __ffs(liveMask) - 1;
-            liveMask &= liveMask - 1;
-            const uint4 r0 = reinterpret_cast<const uint4*>(&recs[j])[0];
-            const uint4 r1 = reinterpret_cast<const uint4*>(&recs[j])[1];
-            const uint4 r2 = reinterpret_cast<const uint4*>(&recs[j])[2];
-            const S32 ea[3] = {(S32)r0.x, (S32)r0.w, (S32)r1.z}, eb[3] = {(S32)r0.y, (S32)r1.x, (S32)r1.w};
+        FineFetch nxt;
+        fineFetch<RenderModeFlags>(nxt, f, entryB);
+        entryB = (base + 64 + lane < queueCount) ? __ldg(&queue[base + 64 + lane]) : -1;
+
+        // ---- (1) lane j: conservative pixel mask of triangle j
+        U32 tileZMax = 0xFFFFFFFFu;
+        if (kDepth) {
+            U32 m = 0;
 #pragma unroll
-            for (int p = 0; p < 2; p++) {
-                // edge values at the centre of pixel p, then per-sample offsets
-                const S32 sy = sy0 + p * (4 << CR_SUBPIXEL_LOG2);
-                const S32 ec[3] = {(S32)r0.z + ea[0] * sx0 + eb[0] * sy, (S32)r1.y + ea[1] * sx0 + eb[1] * sy, (S32)r2.x + ea[2] * sx0 + eb[2] * sy};
-                const U32 cover = pixelSampleMask<SamplesLog2>(ea, eb, ec);
-                if (cover == 0) continue;
-                const int qBase = lane + 32 * p;
-                const U32 zPix = r2.w + r2.y * (U32)(lx * N) + r2.z * (U32)((ly + 4 * p) * N);
+            for (int i = 0; i < N; i++) m = max(m, max(tDepth[i * CR_TILE_SQR + lane], tDepth[i * CR_TILE_SQR + lane + 32]));
+            tileZMax = __reduce_max_sync(0xFFFFFFFFu, m);
+        }
+        U32 maskLo = 0, maskHi = 0;
+        if (cur.entry >= 0) {
+            S32 a[3], b[3], c[3];
+            setupTileEdges(cur.h, bx, by, a, b, c);
+            sb.a0[lane] = a[0]; sb.b0[lane] = b[0]; sb.c0[lane] = c[0];
+            sb.a1[lane] = a[1]; sb.b1[lane] = b[1]; sb.c1[lane] = c[1];
+            sb.a2[lane] = a[2]; sb.b2[lane] = b[2]; sb.c2[lane] = c[2];
+            if (!kDepth || (cur.h.w & 0xFFFFF000u) < tileZMax) {
+                const S32 y0 = (S32)cur.h.x >> 16, y1 = (S32)cur.h.y >> 16, y2 = (S32)cur.h.z >> 16;
+                const int rowLo = max((min(min(y0, y1), y2) - by - kMaxOfs + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0);
+                const int rowHi = min((max(max(y0, y1), y2) - by + kMaxOfs) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
+                // relax every edge by its largest possible gain over the sample offsets (|ox|, |oy| <= kMaxOfs);
+                // c is clamped to +-2^30 and the relaxation is < 2^21, so nothing wraps
+                S32 cr[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) cr[i] = c[i] + (abs(a[i]) + abs(b[i])) * kMaxOfs;
+                coverTileRows(a, b, cr, rowLo, rowHi, maskLo, maskHi);
+            }
+        }
+        if (kDepth) {
+            sb.zx[lane] = cur.z.x; sb.zy[lane] = cur.z.y;
+            sb.zb[lane] = cur.z.z + cur.z.x * (U32)(tileX << (CR_TILE_LOG2 + SamplesLog2)) + cur.z.y * (U32)(tileY << (CR_TILE_LOG2 + SamplesLog2));
+        }
+        sb.entry[lane] = cur.entry;
+        sb.dataIdx[lane] = cur.dataIdx;
+        __syncwarp();
+
+        // ---- (2) transpose
+        const U32 cover[2] = {warpTranspose32(maskLo, lane), warpTranspose32(maskHi, lane)};
+
+        // ---- (3) ownership loop, queue order
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            U32 w = cover[p];
+            const S32 sy = sy0 + p * (4 << CR_SUBPIXEL_LOG2);
+            const int qBase = lane + 32 * p;
+            while (w) {
+                const int j = __ffs(w) - 1;
+                w &= w - 1;
+                const S32 ea[3] = {sb.a0[j], sb.a1[j], sb.a2[j]}, eb[3] = {sb.b0[j], sb.b1[j], sb.b2[j]};
+                const S32 ec[3] = {sb.c0[j] + ea[0] * sx0 + eb[0] * sy, sb.c1[j] + ea[1] * sx0 + eb[1] * sy, sb.c2[j] + ea[2] * sx0 + eb[2] * sy};
+                const U32 cov = pixelSampleMask<SamplesLog2>(ea, eb, ec);
+                if (cov == 0) continue;
+                const U32 zxv = sb.zx[j], zyv = sb.zy[j];
+                const U32 zPix = sb.zb[j] + zxv * (U32)(lx * N) + zyv * (U32)((ly + 4 * p) * N);
                 U32 pass = 0;
                 U32 z[N];
 #pragma unroll
                 for (int i = 0; i < N; i++) {
-                    z[i] = zPix + r2.y * (U32)msaaSampleX(SamplesLog2, i) + r2.z * (U32)i;
-                    if (((cover >> i) & 1) && (!kDepth || z[i] < tDepth[i * CR_TILE_SQR + qBase])) pass |= 1u << i;
+                    z[i] = zPix + zxv * (U32)msaaSampleX(SamplesLog2, i) + zyv * (U32)i;
+                    if (((cov >> i) & 1) && (!kDepth || z[i] < tDepth[i * CR_TILE_SQR + qBase])) pass |= 1u << i;
                 }
                 if (pass == 0) continue;
+                const S32 entry = sb.entry[j];
                 if (deferred) {
 #pragma unroll
                     for (int i = 0; i < N; i++)
                         if ((pass >> i) & 1) {
                             if (kDepth) tDepth[i * CR_TILE_SQR + qBase] = z[i];
-                            tAux[i * CR_TILE_SQR + qBase] = (U32)(base + j + 1);
+                            tAux[i * CR_TILE_SQR + qBase] = (U32)entry + 1u;
                         }
                 } else {
-                    const uint4 r3 = reinterpret_cast<const uint4*>(&recs[j])[3];
                     FragmentShaderClass fs;
-                    runFragmentShader<VertexClass, FragmentShaderClass, SamplesLog2, RenderModeFlags>(fs, f, (int)r3.y, (int)r3.x, pixelX, pixelY0 + 4 * p, centroidCode<SamplesLog2>(cover));
+                    runFragmentShader<VertexClass, FragmentShaderClass, SamplesLog2, RenderModeFlags>(fs, f, entry >> 3, sb.dataIdx[j], pixelX, pixelY0 + 4 * p, centroidCode<SamplesLog2>(cov));
                     if (fs.m_discard) continue;
 #pragma unroll
                     for (int i = 0; i < N; i++)
                         if ((pass >> i) & 1) {
                             if (kDepth) tDepth[i * CR_TILE_SQR + qBase] = z[i];
                             BlendShaderClass bs;
-                            runBlendShader(bs, (int)r3.y, pixelX, pixelY0 + 4 * p, i, fs.m_color, tAux[i * CR_TILE_SQR + qBase]);
+                            runBlendShader(bs, entry >> 3, pixelX, pixelY0 + 4 * p, i, fs.m_color, tAux[i * CR_TILE_SQR + qBase]);
                             if (bs.m_writeColor) tAux[i * CR_TILE_SQR + qBase] = bs.m_color;
                         }
                 }
             }
         }
         __syncwarp();
+        cur = nxt;
     }
 
     // ---- resolve + write back
@@ -160,16 +224,16 @@ __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRaster
                     if (tAux[i * CR_TILE_SQR + qBase] == win) group |= 1u << i;
                 handled |= group;
                 // shade this (triangle, pixel) once, at the centroid of its COVERAGE mask
-                const S32 entry = __ldg(&f.tileQueue[queueStart + (int)win - 1]);
+                const S32 entry = (S32)(win - 1u);
                 const S32 dataIdx = resolveDataIdx(entry, f.triHeader);
                 const uint4 h = __ldg(&f.triHeader[dataIdx]);
-                const S32 bx = (pixelX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
-                const S32 by = (pixelY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
+                const S32 px = (pixelX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
+                const S32 py = (pixelY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
                 S32 a[3], b[3], c[3];
-                setupTileEdges(h, bx, by, a, b, c);
-                const U32 cover = pixelSampleMask<SamplesLog2>(a, b, c);
+                setupTileEdges(h, px, py, a, b, c);
+                const U32 cov = pixelSampleMask<SamplesLog2>(a, b, c);
                 FragmentShaderClass fs;
-                runFragmentShader<VertexClass, FragmentShaderClass, SamplesLog2, RenderModeFlags>(fs, f, entry >> 3, dataIdx, pixelX, pixelY, centroidCode<SamplesLog2>(cover));
+                runFragmentShader<VertexClass, FragmentShaderClass, SamplesLog2, RenderModeFlags>(fs, f, entry >> 3, dataIdx, pixelX, pixelY, centroidCode<SamplesLog2>(cov));
                 for (int i = i0; i < N; i++)
                     if ((group >> i) & 1) {
                         BlendShaderClass bs;
