@@ -7,7 +7,7 @@ using namespace gold;
 
 extern "C" {
 
-int gold_abi_version(void) { return 4; }
+int gold_abi_version(void) { return 5; }
 int gold_sizeof_config(void) { return (int)sizeof(Config); }
 int gold_sizeof_counts(void) { return (int)sizeof(Counts); }
 
@@ -53,6 +53,21 @@ unsigned gold_cover_samples(const void* header, int width, int height, int sampl
     Edges e;
     edgesFromHeader(*(const TriHeader*)header, e);
     return coverPixelSamples(c, e, px, py);
+}
+
+// One fragment-shader run (FineRaster.inl:49-119): colour + centre / centroid barycentrics.  Returns 1 when discarded.
+int gold_run_shader(const Config* c, const void* verts, const void* triData, int dataIdx, int px, int py, unsigned centroid, unsigned* color, float* bary6) {
+    const TriData& d = ((const TriData*)triData)[dataIdx];
+    const int S = c->samplesLog2;
+    if (bary6) {
+        Bary a = computeBary(d, (px * 2 + 1) << S, (py * 2 + 1) << S);
+        Bary b = S == 0 ? a : computeBary(d, (px << (S + 1)) + (S32)(centroid & 0xF), (py << (S + 1)) + (S32)(centroid >> 4));
+        bary6[0] = a.b0; bary6[1] = a.b1; bary6[2] = a.b2; bary6[3] = b.b0; bary6[4] = b.b1; bary6[5] = b.b2;
+    }
+    U32 col = 0;
+    bool keep = runShader(*c, verts, d, dataIdx, px, py, centroid, col);
+    *color = col;
+    return keep ? 0 : 1;
 }
 
 // ---- stages -------------------------------------------------------------------------------------

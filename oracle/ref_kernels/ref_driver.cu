@@ -18,7 +18,16 @@
 #include <string>
 #include <vector>
 
+// The reference chains inline-asm statements through the CARRY FLAG (add.cc / addc in cuda/Util.hpp:85-87,
+// used by cover8x8_lookupMask, Util.inl:249-271) without marking them volatile.  nvcc 12.9 treats such
+// statements as pure: it DELETES the add.cc whose register result is dead and reorders the rest, so the LUT
+// coverage path of the reference is miscompiled by today's toolchain (seen in the PTX: the seven add.cc of
+// cover8x8_lookupMask are gone, the addc read a stale flag; on the GPU 8 315 of 60 599 triangle/tile
+// masks come out wrong).  Making every asm statement of the reference volatile restores the order the
+// source spells out.  This is a toolchain shim like the texture/vote shims in shim.h, not an algorithm change.
+#define asm asm volatile
 #include <cudaraster/cuda/PixelPipe.inl>
+#undef asm
 
 // ---- the reference's own test shaders (test/shader/PassThrough.cu:44-56 is re-stated here because
 // that file also drags in the GLUT demo's constants; GouraudShader comes from PixelPipe.inl) -----
@@ -255,5 +264,137 @@ extern "C" int crref_get_setup_output(int numTris, int numSubtris, unsigned char
     CK(cudaMemcpy(subtris, b_triSubtris.p, (size_t)numTris, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(header, b_triHeader.p, (size_t)numSubtris * sizeof(FW::CRTriangleHeader), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(data, b_triData.p, (size_t)numSubtris * sizeof(FW::CRTriangleData), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+//------------------------------------------------------------------------------------------------
+// Per-thread harness around the reference's own DEVICE FUNCTIONS (no warp-synchronous code
+// involved, so these do run correctly on sm_100a): the LUT coverage path the reference's fine raster
+// really uses (FineRaster.inl:245-282 -> Util.inl:148-271), its MSAA sample coverage
+// (FineRaster.inl:286-309 -> Util.inl:361-383), its fragment-shader front end (FineRaster.inl:49-119,
+// PixelPipe.inl:43-69) and its blend shaders (PixelPipe.inl:73-85, Util.inl:42-60).  The parity tests
+// compare the CPU oracle with these, value for value (tests/test_gpu_ref_kernels.py).
+//------------------------------------------------------------------------------------------------
+
+namespace {
+
+// pairs[i] = {header index, tileX, tileY}; one thread per pair.  lutDump (optional) receives the 768 LUT words.
+__global__ void refCoverTilesKernel(const uint4* headers, const int3* pairs, int n, FW::U64* exact, FW::U64* conservative, FW::U64* lutDump) {
+    __shared__ volatile FW::U64 s_lut[CR_COVER8X8_LUT_SIZE];
+    FW::cover8x8_setupLUT(s_lut);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lutDump && blockIdx.x == 0)
+        for (int k = threadIdx.x; k < CR_COVER8X8_LUT_SIZE; k += blockDim.x) lutDump[k] = s_lut[k];
+    if (i >= n) return;
+    const int3 p = pairs[i];
+    const uint4 h = headers[p.x];
+    exact[i] = FW::trianglePixelCoverage<0>(h, p.y, p.z, s_lut);
+    conservative[i] = FW::trianglePixelCoverage<1>(h, p.y, p.z, s_lut);
+}
+
+// pairs[i] = {header index, pixelX, pixelY}
+template <int S>
+__global__ void refCoverSamplesKernel(const uint4* headers, const int3* pairs, int n, FW::U32* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int3 p = pairs[i];
+    out[i] = FW::triangleSampleCoverage<S>(headers[p.x], p.y, p.z);
+}
+
+// frags[i] = {dataIdx, pixelX, pixelY, centroid code}; triData / vertices come through the texture shims.
+template <class V, class FS, int S, FW::U32 Flags>
+__global__ void refShadeKernel(const int4* frags, int n, FW::U32* colorOut, float* baryOut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 q = frags[i];
+    FS fs;
+    FW::runFragmentShader<V, FS, S, Flags>(fs, q.x, q.x, q.y, q.z, (FW::U32)q.w, nullptr);
+    colorOut[i] = fs.m_color;
+    if (baryOut) {
+        baryOut[i * 6 + 0] = fs.m_center.x;   baryOut[i * 6 + 1] = fs.m_center.y;   baryOut[i * 6 + 2] = fs.m_center.z;
+        baryOut[i * 6 + 3] = fs.m_centroid.x; baryOut[i * 6 + 4] = fs.m_centroid.y; baryOut[i * 6 + 5] = fs.m_centroid.z;
+    }
+}
+
+template <class B>
+__global__ void refBlendKernel(const FW::U32* src, const FW::U32* dst, int n, FW::U32* out, int* write) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    B bs;
+    FW::runBlendShader<B>(bs, i, i & 2047, i >> 11, i & 7, src[i], dst[i]);
+    out[i] = bs.m_color;
+    write[i] = bs.m_writeColor ? 1 : 0;
+}
+
+int setViewport(int width, int height) {
+    FW::CRParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.viewportWidth = width;
+    p.viewportHeight = height;
+    CK(cudaMemcpyToSymbol(c_crParams, &p, sizeof(p)));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int crref_cover_tiles(const void* d_headers, const int* d_pairs, int n, int width, int height, unsigned long long* d_exact,
+                                 unsigned long long* d_conservative, unsigned long long* d_lutDump) {
+    if (setViewport(width, height)) return 2;
+    refCoverTilesKernel<<<(n + 255) / 256, 256>>>((const uint4*)d_headers, (const int3*)d_pairs, n, (FW::U64*)d_exact, (FW::U64*)d_conservative, (FW::U64*)d_lutDump);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int crref_cover_samples(const void* d_headers, const int* d_pairs, int n, int width, int height, int samplesLog2, unsigned* d_out) {
+    if (setViewport(width, height)) return 2;
+    const int g = (n + 255) / 256;
+    switch (samplesLog2) {
+        case 1: refCoverSamplesKernel<1><<<g, 256>>>((const uint4*)d_headers, (const int3*)d_pairs, n, d_out); break;
+        case 2: refCoverSamplesKernel<2><<<g, 256>>>((const uint4*)d_headers, (const int3*)d_pairs, n, d_out); break;
+        case 3: refCoverSamplesKernel<3><<<g, 256>>>((const uint4*)d_headers, (const int3*)d_pairs, n, d_out); break;
+        default: snprintf(g_err, sizeof(g_err), "samplesLog2 must be 1..3"); return 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// Gouraud front end: the reference's runFragmentShader + GouraudShader for (samplesLog2, Depth|Lerp).
+extern "C" int crref_shade_gouraud(const void* d_triData, const void* d_verts, const int* d_frags, int n, int samplesLog2, unsigned* d_color, float* d_bary) {
+    cr_texture<float4, 1> tv = {(const float4*)d_verts};
+    cr_texture<uint4, 1> td = {(const uint4*)d_triData};
+    CK(cudaMemcpyToSymbol(t_vertexBuffer, &tv, sizeof(tv)));
+    CK(cudaMemcpyToSymbol(t_triData, &td, sizeof(td)));
+    FW::CRParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.vertexBuffer = (CUdeviceptr)d_verts;
+    CK(cudaMemcpyToSymbol(c_crParams, &p, sizeof(p)));
+    const int g = (n + 127) / 128;
+    switch (samplesLog2) {
+        case 0: refShadeKernel<FW::GouraudVertex, FW::GouraudShader, 0, 3><<<g, 128>>>((const int4*)d_frags, n, d_color, d_bary); break;
+        case 1: refShadeKernel<FW::GouraudVertex, FW::GouraudShader, 1, 3><<<g, 128>>>((const int4*)d_frags, n, d_color, d_bary); break;
+        case 2: refShadeKernel<FW::GouraudVertex, FW::GouraudShader, 2, 3><<<g, 128>>>((const int4*)d_frags, n, d_color, d_bary); break;
+        case 3: refShadeKernel<FW::GouraudVertex, FW::GouraudShader, 3, 3><<<g, 128>>>((const int4*)d_frags, n, d_color, d_bary); break;
+        default: snprintf(g_err, sizeof(g_err), "samplesLog2 must be 0..3"); return 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// blend: 0 Replace, 1 SrcOver, 2 Additive, 3 DepthOnly (the order of the oracle's blend ids)
+extern "C" int crref_blend(int blend, const unsigned* d_src, const unsigned* d_dst, int n, unsigned* d_out, int* d_write) {
+    const int g = (n + 255) / 256;
+    switch (blend) {
+        case 0: refBlendKernel<FW::BlendReplace><<<g, 256>>>(d_src, d_dst, n, d_out, d_write); break;
+        case 1: refBlendKernel<FW::BlendSrcOver><<<g, 256>>>(d_src, d_dst, n, d_out, d_write); break;
+        case 2: refBlendKernel<FW::BlendAdditive><<<g, 256>>>(d_src, d_dst, n, d_out, d_write); break;
+        case 3: refBlendKernel<FW::BlendDepthOnly><<<g, 256>>>(d_src, d_dst, n, d_out, d_write); break;
+        default: snprintf(g_err, sizeof(g_err), "unknown blend"); return 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
     return 0;
 }

@@ -35,3 +35,25 @@ def test_reference_setup_kernel_matches_oracle(workload):
     print(json.dumps(out))
     assert out["setup"]["status"] == "bit-exact", out["setup"]
     assert out["setup"]["single"] > 1000 and out["setup"]["clipped"] > 100
+
+
+@pytest.mark.parametrize("size", [(2048, 2048), (1920, 1080), (640, 360)])
+def test_reference_device_functions_match_oracle(size):
+    """The oracle's coverage rule, MSAA sample coverage, barycentrics / Gouraud colour and blend
+    arithmetic against the reference's OWN device functions (the LUT coverage path of its fine raster
+    included) executed per thread on the GPU: bit-exact (colour within 1 LSB)."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref/libcrref_cuda.so not built (needs /root/reference at build time)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_devfuncs.py"), "--width", str(size[0]), "--height", str(size[1]), "--tris", "24000"],
+                       capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, "harness failed: rc=%d %s" % (r.returncode, (r.stderr or r.stdout)[-800:])
+    out = json.loads(lines[-1])
+    print(json.dumps(out))
+    assert out["status"] == "ok", out
+    assert out["cover8x8_exact_fast"]["mismatch"] == 0 and out["cover8x8_exact_fast"]["nonempty"] > 5000
+    for s in (1, 2, 3):
+        assert out["coverMSAA_fast_s%d" % s]["mismatch"] == 0 and out["coverMSAA_fast_s%d" % s]["partial"] > 100
+    for s in (0, 1, 2, 3):
+        assert out["shade_gouraud_s%d" % s]["bary_bit_mismatch"] == 0 and out["shade_gouraud_s%d" % s]["color_max_lsb"] <= 1
