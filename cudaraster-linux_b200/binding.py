@@ -36,7 +36,8 @@ class WorkBuffers(ctypes.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "libcrb200.so")
+    # CRB200_LIBRARY: an experiment build of the same library (tools/build_variant.sh); never a different implementation
+    return os.environ.get("CRB200_LIBRARY") or os.path.join(_HERE, "libcrb200.so")
 
 
 def build_library(verbose=False):
@@ -77,7 +78,10 @@ def load_library():
         "crb_draw_triangles_async": (i32, [vp, vp]),
         "crb_finish": (i32, [vp, vp]),
         "crb_draw_triangles_host": (i32, [vp, vp, ctypes.c_size_t, vp, i32, vp, vp, vp]),
+        "crb_draw_triangles_host_async": (i32, [vp, vp, ctypes.c_size_t, vp, i32, vp, vp, vp]),
         "crb_get_stats": (i32, [vp, ctypes.POINTER(f32 * 4)]),
+        "crb_set_stage_timing": (i32, [vp, i32]),
+        "crb_get_stage_timing": (i32, [vp, ctypes.POINTER(ctypes.c_double * 4), ctypes.POINTER(i32)]),
         "crb_get_counters": (i32, [vp, ctypes.POINTER(Atomics)]),
         "crb_get_profiling_info": (i32, [vp, ctypes.c_char_p, ctypes.c_size_t]),
         "crb_get_launch_count": (i32, [vp]),
@@ -94,8 +98,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
-                    "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_get_stats", "crb_get_counters",
-                    "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download"]
+                    "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
+                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download"]
 
 
 def pipe_name(base, samples_log2, flags, blend="BlendReplace"):
@@ -242,10 +246,27 @@ class CudaRaster:
             self.ctx, h_verts.data_ptr(), h_verts.numel() * h_verts.element_size(), h_idx.data_ptr(), int(num_tris), h_color.data_ptr(),
             None if h_depth is None else h_depth.data_ptr(), ctypes.c_void_p(s)))
 
+    def drawTrianglesHostAsync(self, h_verts, h_idx, num_tris, h_color, h_depth=None, stream=None):
+        """Pipelined host-buffer entry (crb_draw_triangles_host_async): returns at once; call finish()."""
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(self.lib.crb_draw_triangles_host_async(
+            self.ctx, h_verts.data_ptr(), h_verts.numel() * h_verts.element_size(), h_idx.data_ptr(), int(num_tris), h_color.data_ptr(),
+            None if h_depth is None else h_depth.data_ptr(), ctypes.c_void_p(s)))
+
     def getStats(self):
         out = (ctypes.c_float * 4)()
         self._check(self.lib.crb_get_stats(self.ctx, ctypes.byref(out)))
         return {"setupTime": out[0], "binTime": out[1], "coarseTime": out[2], "fineTime": out[3]}
+
+    def setStageTiming(self, enable):
+        """Asynchronous frames also record the five stage events (off by default: it splits the kernel chain)."""
+        self._check(self.lib.crb_set_stage_timing(self.ctx, 1 if enable else 0))
+
+    def getStageTiming(self):
+        """Mean ms per stage over the asynchronous frames finished since setStageTiming(True)."""
+        out, n = (ctypes.c_double * 4)(), ctypes.c_int(0)
+        self._check(self.lib.crb_get_stage_timing(self.ctx, ctypes.byref(out), ctypes.byref(n)))
+        return {"triangleSetup": out[0], "binRaster": out[1], "coarseRaster": out[2], "fineRaster": out[3], "frames": n.value}
 
     def getProfilingInfo(self):
         buf = ctypes.create_string_buffer(2048)

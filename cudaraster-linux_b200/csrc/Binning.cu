@@ -142,8 +142,10 @@ __device__ __forceinline__ TriFootprint footprintOf(const crb_frame& f, S32 entr
 __global__ void __launch_bounds__(kScanThreads) binScanKernel(const __grid_constant__ crb_frame f) {
     __shared__ int s_warp[33];
     __shared__ int s_base[2];
+    gridDepLaunchDependents();
     if (threadIdx.x < 33) s_warp[threadIdx.x] = 0;
     __syncthreads();
+    gridDepWait();
     const int bin = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // thread t owns the 4-aligned run of chunks [first, first + perThread): 128-bit loads, coalesced
     const int perThread = (((f.numChunks + kScanThreads - 1) / kScanThreads) + 3) & ~3;
@@ -180,6 +182,10 @@ __global__ void __launch_bounds__(kScanThreads) binScanKernel(const __grid_const
             o.y = run; run += v.y;
             o.z = run; run += v.z;
             o.w = run; run += v.w;
+            // padding columns keep reading 0 in the next frame (nothing else ever writes them)
+            if (c + 1 >= f.numChunks) o.y = 0;
+            if (c + 2 >= f.numChunks) o.z = 0;
+            if (c + 3 >= f.numChunks) o.w = 0;
             *reinterpret_cast<int4*>(row + c) = o;
         }
     }
@@ -232,6 +238,8 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
     __shared__ int s_list[kWarps][kMaxListEntries];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = blockIdx.x * kWarps + warp;
+    gridDepLaunchDependents();
+    gridDepWait();
     if (chunk >= f.numChunks) return;
     const int triBegin = chunk * f.chunkTris, triEnd = min(triBegin + f.chunkTris, f.numTris);
     // triSubtris runs two batches ahead, headers one batch ahead and only for surviving triangles
@@ -244,8 +252,11 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
     WarpCells& wc = s_cells[warp];
     const unsigned ltMask = laneMaskLt();
     for (int b = lane; b < f.numBins; b += 32) {
-        wc.cursor[b] = __ldg(&f.binStart[b]) + f.binCountMat[(size_t)b * f.matPitch + chunk];
+        int* cell = &f.binCountMat[(size_t)b * f.matPitch + chunk];
+        wc.cursor[b] = __ldg(&f.binStart[b]) + *cell;
         wc.mask[b] = 0;
+        // several setup CTAs ADD into one column: the last reader leaves it zeroed for the next frame
+        if (f.ctasPerChunk > 1) *cell = 0;
     }
     __syncwarp();
     const CellIndexer cellOf = {0, 0, -1, f.widthBins};
@@ -328,6 +339,8 @@ __global__ void __launch_bounds__(kThreads * kScanGroups) coarseScanKernel(const
     __shared__ int s_warp[kWarps + 1];
     __shared__ int s_base[2];
     __shared__ int s_group[kScanGroups][kCells];
+    gridDepLaunchDependents();
+    gridDepWait();
     if (f.atomics->overflow != 0) return;
     const int bin = blockIdx.x, t = threadIdx.x & (kCells - 1), g = threadIdx.x >> 8;
     const int itemBase = f.binItemBase[bin], numItems = f.binItemCount[bin];
@@ -386,6 +399,8 @@ __global__ void __launch_bounds__(kThreads, 4) coarseScatterKernel(const __grid_
     __shared__ WarpCells s_cells[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kWarps + warp;
+    gridDepLaunchDependents();
+    gridDepWait();
     if (f.atomics->overflow != 0 || item >= f.atomics->numCoarseItems) return;
     WarpCells& wc = s_cells[warp];
     const unsigned ltMask = laneMaskLt();
@@ -402,7 +417,9 @@ __global__ void __launch_bounds__(kThreads, 4) coarseScatterKernel(const __grid_
         const int t = lane + 32 * i;
         const int tx = w.tx0 + (t & (CR_BIN_SIZE - 1)), ty = w.ty0 + (t >> CR_BIN_LOG2);
         int cur = 0;
-        if (tx <= w.tx1 && ty <= w.ty1) cur = f.tileStart[tx + ty * f.widthTiles] + f.tileCountMat[(size_t)item * CR_BIN_SQR + t];
+        int* cell = &f.tileCountMat[(size_t)item * CR_BIN_SQR + t];
+        if (tx <= w.tx1 && ty <= w.ty1) cur = f.tileStart[tx + ty * f.widthTiles] + *cell;
+        *cell = 0;   // last reader of the row: the count matrix is all zero again when the frame ends (no memset per frame)
         wc.cursor[t] = cur;
         wc.mask[t] = 0;
     }
@@ -425,22 +442,20 @@ inline int checkLaunch() { return cudaGetLastError() == cudaSuccess ? CRB_OK : C
 
 extern "C" int crb_launch_bin_raster(const crb_frame* f, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    binScanKernel<<<f->numBins, kScanThreads, 0, s>>>(*f);
-    if (f->numTris > 0) {
+    cudaError_t e = launchChained(binScanKernel, f->numBins, kScanThreads, s, *f);
+    if (e == cudaSuccess && f->numTris > 0) {
         const int grid = (f->numChunks + kWarps - 1) / kWarps;
-        if (f->samplesLog2 == 0) binScatterKernel<0><<<grid, kThreads, 0, s>>>(*f);
-        else binScatterKernel<1><<<grid, kThreads, 0, s>>>(*f);
+        e = f->samplesLog2 == 0 ? launchChained(binScatterKernel<0>, grid, kThreads, s, *f) : launchChained(binScatterKernel<1>, grid, kThreads, s, *f);
     }
-    return checkLaunch();
+    return e == cudaSuccess ? checkLaunch() : CRB_ERR_CUDA;
 }
 
 extern "C" int crb_launch_coarse_raster(const crb_frame* f, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = max(1, (f->maxItems + kWarps - 1) / kWarps);
-    coarseScanKernel<<<f->numBins, kThreads * kScanGroups, 0, s>>>(*f);
-    if (f->samplesLog2 == 0) coarseScatterKernel<0><<<grid, kThreads, 0, s>>>(*f);
-    else coarseScatterKernel<1><<<grid, kThreads, 0, s>>>(*f);
-    return checkLaunch();
+    cudaError_t e = launchChained(coarseScanKernel, f->numBins, kThreads * kScanGroups, s, *f);
+    if (e == cudaSuccess) e = f->samplesLog2 == 0 ? launchChained(coarseScatterKernel<0>, grid, kThreads, s, *f) : launchChained(coarseScatterKernel<1>, grid, kThreads, s, *f);
+    return e == cudaSuccess ? checkLaunch() : CRB_ERR_CUDA;
 }
 
 extern "C" int crb_bin_launches(const crb_frame* f) { return f->numTris > 0 ? 2 : 1; }

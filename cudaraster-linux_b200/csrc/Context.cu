@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -78,11 +79,35 @@ struct crb_ctx {
     int pending = 0;                     // asynchronous frames not yet checked by crb_finish
     DevBuf hostVerts, hostIdx;           // device staging for crb_draw_triangles_host
 
+    // Between frames the count matrices are all zero and the counter block of the NEXT frame is zeroed by
+    // the fine raster kernel (double-buffered), so a steady-state frame enqueues kernels only.  needReset
+    // forces the memsets: first frame, reallocation, layout change, overflow, any failed launch.
+    bool needReset = true;
+    int atomicsParity = 0;
+    int lastNumBins = -1, lastMatPitch = -1, lastNumChunks = -1, lastCtasPerChunk = -1;
+    int debugFlags = 0;
+    bool chainLaunches = true;           // programmatic dependent launch between the kernels of a frame (CRB_NO_PDL=1 turns it off)
+    bool stageTiming = false;            // asynchronous frames: record the five stage events too (crb_set_stage_timing)
+    static constexpr int kTimingRing = 64;
+    cudaEvent_t ringEv[kTimingRing][5] = {};
+    double stageSumMs[4] = {0, 0, 0, 0};
+    int stageFrames = 0;
+
+    // crb_draw_triangles_host_async: upload / render / download of consecutive frames overlap
+    struct HostPipeline {
+        bool init = false;
+        cudaStream_t up = nullptr, down = nullptr;
+        DevBuf verts[2], idx[2];
+        cudaEvent_t uploaded[2] = {}, rendered[2] = {}, downloaded = nullptr;
+        long long frames = 0;
+    } hp;
+
     cudaEvent_t ev[5] = {};
     crb_frame frame{};
     crb_atomics lastAtomics{};
     int launchCount = 0;
     bool drawn = false;
+    bool evRecorded = false;             // ev[] hold a synchronous frame
 };
 
 namespace {
@@ -188,6 +213,11 @@ int prepareFrame(crb_ctx* c) {
     f.maxTileEntries = c->maxTileEntries;
     f.maxItems = c->maxItems;
     f.numSMs = c->numSMs;
+    f.chainLaunches = c->chainLaunches ? 1 : 0;
+    f.debugFlags = c->debugFlags;
+
+    const void* oldBinMat = c->binCountMat.ptr;
+    const void* oldTileMat = c->tileCountMat.ptr;
 
     CRB_CUDA(c, c->triSubtris.reserve((size_t)c->maxSubtris));
     CRB_CUDA(c, c->triHeader.reserve((size_t)c->maxSubtris * 16));
@@ -222,33 +252,43 @@ int prepareFrame(crb_ctx* c) {
     f.tileCount = (int32_t*)c->tileCount.ptr;
     f.activeTiles = (int32_t*)c->activeTiles.ptr;
     f.activeRecs = (int4*)c->activeRecs.ptr;
-    f.atomics = (crb_atomics*)c->atomics.ptr;
+    f.atomics = (crb_atomics*)c->atomics.ptr + c->atomicsParity;
+    f.nextAtomics = (crb_atomics*)c->atomics.ptr + (c->atomicsParity ^ 1);
+    if (oldBinMat != c->binCountMat.ptr || oldTileMat != c->tileCountMat.ptr || c->lastNumBins != f.numBins || c->lastMatPitch != f.matPitch ||
+        c->lastNumChunks != f.numChunks || c->lastCtasPerChunk != f.ctasPerChunk)
+        c->needReset = true;
+    c->lastNumBins = f.numBins; c->lastMatPitch = f.matPitch; c->lastNumChunks = f.numChunks; c->lastCtasPerChunk = f.ctasPerChunk;
     return CRB_OK;
 }
 
-// Enqueues one frame (reference: CudaRaster::launchStages, CudaRaster.cpp:508-665).
-int launchStages(crb_ctx* c, cudaStream_t s) {
+// Enqueues one frame (reference: CudaRaster::launchStages, CudaRaster.cpp:508-665).  ev = the five
+// stage events to record (nullptr: none -- asynchronous frames run as an unbroken chain of kernels).
+int launchStages(crb_ctx* c, cudaStream_t s, cudaEvent_t* ev) {
     const crb_frame* f = &c->frame;
-    CRB_CUDA(c, cudaMemsetAsync(c->atomics.ptr, 0, sizeof(crb_atomics), s));
-    // bin counts: padding columns must read 0; with several setup CTAs per chunk they ADD into the matrix.
-    // tile counts: accumulated with global reductions by the bin scatter pass.
-    if (f->numTris > 0 && (f->ctasPerChunk > 1 || f->matPitch != f->numChunks))
-        CRB_CUDA(c, cudaMemsetAsync(f->binCountMat, 0, (size_t)f->matPitch * f->numBins * 4, s));
-    CRB_CUDA(c, cudaMemsetAsync(f->tileCountMat, 0, (size_t)f->maxItems * CR_BIN_SQR * 4, s));
-    CRB_CUDA(c, cudaEventRecord(c->ev[0], s));
+    if (c->needReset) {
+        CRB_CUDA(c, cudaMemsetAsync(c->atomics.ptr, 0, 2 * sizeof(crb_atomics), s));
+        CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, c->binCountMat.cap, s));
+        CRB_CUDA(c, cudaMemsetAsync(c->tileCountMat.ptr, 0, c->tileCountMat.cap, s));
+        c->needReset = false;
+    }
+    c->needReset = true;   // until every launch of this frame went through
+    if (ev) CRB_CUDA(c, cudaEventRecord(ev[0], s));
     int rc = c->pipe.triangleSetup(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: triangleSetup launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
-    CRB_CUDA(c, cudaEventRecord(c->ev[1], s));
+    if (ev) CRB_CUDA(c, cudaEventRecord(ev[1], s));
     rc = c->pipe.binRaster(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: binRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
-    CRB_CUDA(c, cudaEventRecord(c->ev[2], s));
+    if (ev) CRB_CUDA(c, cudaEventRecord(ev[2], s));
     rc = c->pipe.coarseRaster(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: coarseRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
-    CRB_CUDA(c, cudaEventRecord(c->ev[3], s));
+    if (ev) CRB_CUDA(c, cudaEventRecord(ev[3], s));
     rc = c->pipe.fineRaster(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: fineRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
-    CRB_CUDA(c, cudaEventRecord(c->ev[4], s));
+    if (ev) CRB_CUDA(c, cudaEventRecord(ev[4], s));
+    if (ev == c->ev) c->evRecorded = true;
     c->launchCount += (f->numTris > 0 ? 1 : 0) + crb_bin_launches(f) + crb_coarse_launches(f) + 1;
+    c->needReset = false;
+    c->atomicsParity ^= 1;   // the fine raster kernel zeroed the other block for the next frame
     return CRB_OK;
 }
 
@@ -290,7 +330,14 @@ int crb_create(int device, crb_ctx** out) {
     c->numSMs = prop.multiProcessorCount;
     for (int i = 0; i < 5; i++)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
-    if (c->atomics.reserve(sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    for (int i = 0; i < crb_ctx::kTimingRing; i++)
+        for (int k = 0; k < 5; k++)
+            if (cudaEventCreate(&c->ringEv[i][k]) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    if (c->atomics.reserve(2 * sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    const char* noPdl = getenv("CRB_NO_PDL");
+    c->chainLaunches = !(noPdl && noPdl[0] == '1');
+    const char* dbg = getenv("CRB_DEBUG_FLAGS");
+    c->debugFlags = dbg ? atoi(dbg) : 0;
     if (cudaMallocHost((void**)&c->hostAtomics, sizeof(crb_atomics) * (1 + kAsyncRing)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
     std::memset(c->hostAtomics, 0, sizeof(crb_atomics) * (1 + kAsyncRing));
     *out = c;
@@ -304,9 +351,23 @@ int crb_destroy(crb_ctx* c) {
     DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
                       &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx};
     for (DevBuf* b : bufs) b->release();
+    if (c->hp.init) {
+        cudaStreamDestroy(c->hp.up);
+        cudaStreamDestroy(c->hp.down);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(c->hp.uploaded[i]);
+            cudaEventDestroy(c->hp.rendered[i]);
+            c->hp.verts[i].release();
+            c->hp.idx[i].release();
+        }
+        cudaEventDestroy(c->hp.downloaded);
+    }
     if (c->hostAtomics) cudaFreeHost(c->hostAtomics);
     for (int i = 0; i < 5; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < crb_ctx::kTimingRing; i++)
+        for (int k = 0; k < 5; k++)
+            if (c->ringEv[i][k]) cudaEventDestroy(c->ringEv[i][k]);
     delete c;
     return CRB_OK;
 }
@@ -441,15 +502,16 @@ int crb_draw_triangles(crb_ctx* c, void* stream) {
         c->maxItems = c->maxBinEntries / CRB_ITEM_ENTRIES + CR_MAXBINS_SQR + 1;
         rc = prepareFrame(c);
         if (rc != CRB_OK) return rc;
-        rc = launchStages(c, s);
+        rc = launchStages(c, s, c->ev);
         if (rc != CRB_OK) return rc;
         // counters back to the host (reference: CudaRaster.cpp:326 -- one blocking round trip per frame)
-        CRB_CUDA(c, cudaMemcpyAsync(c->hostAtomics, c->atomics.ptr, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(c, cudaMemcpyAsync(c->hostAtomics, c->frame.atomics, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
         CRB_CUDA(c, cudaStreamSynchronize(s));
         crb_atomics a = *c->hostAtomics;
         a.numSubtris += numTris;
         c->lastAtomics = a;
         if (a.overflow == 0) break;
+        c->needReset = true;   // the kernels of an overflowed frame return early and leave the count matrices dirty
         if (attempt > 8) return setError(c, CRB_ERR_LIMIT, "CudaRaster: work buffers keep overflowing (flags %d)", a.overflow);
         // grow and rerun ALL stages (CudaRaster.cpp:328-338)
         if (a.overflow & 1) c->maxSubtris = std::max(c->maxSubtris, a.numSubtris + 4096);
@@ -467,6 +529,13 @@ int crb_finish(crb_ctx* c, void* stream) {
     CRB_CUDA(c, cudaStreamSynchronize((cudaStream_t)stream));
     int overflowed = 0;
     for (int i = 0; i < c->pending; i++) {
+        if (c->stageTiming) {
+            for (int k = 0; k < 4; k++) {
+                float ms = 0.0f;
+                if (cudaEventElapsedTime(&ms, c->ringEv[i][k], c->ringEv[i][k + 1]) == cudaSuccess) c->stageSumMs[k] += ms;
+            }
+            c->stageFrames++;
+        }
         crb_atomics a = c->hostAtomics[1 + i];
         a.numSubtris += c->numTris;
         c->lastAtomics = a;
@@ -478,6 +547,7 @@ int crb_finish(crb_ctx* c, void* stream) {
     }
     const int n = c->pending;
     c->pending = 0;
+    if (overflowed) c->needReset = true;
     if (overflowed) return setError(c, CRB_ERR_OVERFLOW, "CudaRaster: %d of %d asynchronous frames overflowed a work buffer; capacities grown, redraw", overflowed, n);
     return CRB_OK;
 }
@@ -504,9 +574,9 @@ int crb_draw_triangles_async(crb_ctx* c, void* stream) {
     c->launchCount = 0;
     rc = prepareFrame(c);
     if (rc != CRB_OK) return rc;
-    rc = launchStages(c, s);
+    rc = launchStages(c, s, c->stageTiming ? c->ringEv[c->pending] : nullptr);
     if (rc != CRB_OK) return rc;
-    CRB_CUDA(c, cudaMemcpyAsync(&c->hostAtomics[1 + c->pending], c->atomics.ptr, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
+    CRB_CUDA(c, cudaMemcpyAsync(&c->hostAtomics[1 + c->pending], c->frame.atomics, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
     c->pending++;
     c->deferredClear = false;
     c->drawn = true;
@@ -537,16 +607,83 @@ int crb_draw_triangles_host(crb_ctx* c, const void* h_vertices, size_t vertexByt
     return CRB_OK;
 }
 
+int crb_draw_triangles_host_async(crb_ctx* c, const void* h_vertices, size_t vertexBytes, const int32_t* h_indices, int numTris, uint32_t* h_color,
+                                  uint32_t* h_depth, void* stream) {
+    if (!c) return CRB_ERR_INVALID;
+    if (!c->color) return setError(c, CRB_ERR_INVALID, "CudaRaster: Surfaces not set!");
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CUDA(c, cudaSetDevice(c->device));
+    crb_ctx::HostPipeline& hp = c->hp;
+    if (!hp.init) {
+        CRB_CUDA(c, cudaStreamCreateWithFlags(&hp.up, cudaStreamNonBlocking));
+        CRB_CUDA(c, cudaStreamCreateWithFlags(&hp.down, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CRB_CUDA(c, cudaEventCreateWithFlags(&hp.uploaded[i], cudaEventDisableTiming));
+            CRB_CUDA(c, cudaEventCreateWithFlags(&hp.rendered[i], cudaEventDisableTiming));
+        }
+        CRB_CUDA(c, cudaEventCreateWithFlags(&hp.downloaded, cudaEventDisableTiming));
+        hp.init = true;
+    }
+    const int slot = (int)(hp.frames & 1);
+    const size_t idxBytes = (size_t)numTris * 12;
+    if (std::max<size_t>(vertexBytes, 16) > hp.verts[slot].cap || std::max<size_t>(idxBytes, 16) > hp.idx[slot].cap) {
+        CRB_CUDA(c, cudaDeviceSynchronize());   // growing a staging buffer frees memory frames in flight may read
+        CRB_CUDA(c, hp.verts[slot].reserve(std::max<size_t>(vertexBytes, 16)));
+        CRB_CUDA(c, hp.idx[slot].reserve(std::max<size_t>(idxBytes, 16)));
+    }
+    // upload: the slot was last read by the frame before the previous one
+    if (hp.frames >= 2) CRB_CUDA(c, cudaStreamWaitEvent(hp.up, hp.rendered[slot], 0));
+    CRB_CUDA(c, cudaMemcpyAsync(hp.verts[slot].ptr, h_vertices, vertexBytes, cudaMemcpyHostToDevice, hp.up));
+    CRB_CUDA(c, cudaMemcpyAsync(hp.idx[slot].ptr, h_indices, idxBytes, cudaMemcpyHostToDevice, hp.up));
+    CRB_CUDA(c, cudaEventRecord(hp.uploaded[slot], hp.up));
+    // render on the caller's stream: needs this frame's upload, and the previous frame's surfaces downloaded
+    // (the previous frame's download is already ordered before it, see the end of this function)
+    CRB_CUDA(c, cudaStreamWaitEvent(s, hp.uploaded[slot], 0));
+    c->vertices = hp.verts[slot].ptr;
+    c->vertexBytes = vertexBytes;
+    c->indices = (const int32_t*)hp.idx[slot].ptr;
+    c->numTris = numTris;
+    c->verticesSet = c->indicesSet = true;
+    int rc = crb_draw_triangles_async(c, stream);
+    if (rc != CRB_OK) return rc;
+    CRB_CUDA(c, cudaEventRecord(hp.rendered[slot], s));
+    // download
+    CRB_CUDA(c, cudaStreamWaitEvent(hp.down, hp.rendered[slot], 0));
+    const size_t surfBytes = (size_t)c->frame.surfacePitch * c->frame.heightPixels * 4;
+    if (h_color) CRB_CUDA(c, cudaMemcpyAsync(h_color, c->color, surfBytes, cudaMemcpyDeviceToHost, hp.down));
+    if (h_depth) CRB_CUDA(c, cudaMemcpyAsync(h_depth, c->depth, surfBytes, cudaMemcpyDeviceToHost, hp.down));
+    CRB_CUDA(c, cudaEventRecord(hp.downloaded, hp.down));
+    // later work on the caller's stream (and crb_finish) sees the downloaded frame
+    CRB_CUDA(c, cudaStreamWaitEvent(s, hp.downloaded, 0));
+    hp.frames++;
+    return CRB_OK;
+}
+
 int crb_get_stats(crb_ctx* c, float out[4]) {
     if (!c || !out) return CRB_ERR_INVALID;
     out[0] = out[1] = out[2] = out[3] = 0.0f;
-    if (!c->drawn) return CRB_OK;
+    if (!c->drawn || !c->evRecorded) return CRB_OK;
     CRB_CUDA(c, cudaEventSynchronize(c->ev[4]));
     for (int i = 0; i < 4; i++) {
         float ms = 0.0f;
         CRB_CUDA(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
         out[i] = ms * 1.0e-3f;  // seconds, like CudaRaster::Stats
     }
+    return CRB_OK;
+}
+
+int crb_set_stage_timing(crb_ctx* c, int enable) {
+    if (!c) return CRB_ERR_INVALID;
+    c->stageTiming = enable != 0;
+    c->stageSumMs[0] = c->stageSumMs[1] = c->stageSumMs[2] = c->stageSumMs[3] = 0.0;
+    c->stageFrames = 0;
+    return CRB_OK;
+}
+
+int crb_get_stage_timing(crb_ctx* c, double outMeanMs[4], int* outFrames) {
+    if (!c || !outMeanMs) return CRB_ERR_INVALID;
+    for (int k = 0; k < 4; k++) outMeanMs[k] = c->stageFrames > 0 ? c->stageSumMs[k] / c->stageFrames : 0.0;
+    if (outFrames) *outFrames = c->stageFrames;
     return CRB_OK;
 }
 

@@ -148,9 +148,25 @@ int crb_finish(crb_ctx* ctx, void* stream);
 int crb_draw_triangles_host(crb_ctx* ctx, const void* h_vertices, size_t vertexBytes, const int32_t* h_indices, int numTris,
                             uint32_t* h_color, uint32_t* h_depth, void* stream);
 
+/* Pipelined variant of crb_draw_triangles_host for streams of frames: the upload of frame k+1 (own
+ * copy stream, double-buffered staging), the rendering of frame k (crb_draw_triangles_async on `stream`)
+ * and the download of frame k-1 (own copy stream) overlap.  Returns without blocking; the host output
+ * buffers are valid after crb_finish(ctx, stream) (or after synchronising `stream`), which also reports
+ * work-buffer overflow like crb_draw_triangles_async.  Host buffers must be pinned and must stay
+ * untouched until then.  The deferred clear, pipe and surfaces are those set when the call is made. */
+int crb_draw_triangles_host_async(crb_ctx* ctx, const void* h_vertices, size_t vertexBytes, const int32_t* h_indices, int numTris,
+                                  uint32_t* h_color, uint32_t* h_depth, void* stream);
+
 /* CudaRaster::getStats (CudaRaster.cpp:346-363): seconds per stage of the last draw
  * {setup, bin, coarse, fine}.  Synchronizes. */
 int crb_get_stats(crb_ctx* ctx, float outSeconds[4]);
+/* Stage timing of ASYNCHRONOUS frames (the profiling hooks of CudaRaster.cpp:593-661 for the
+ * non-blocking entry): when enabled, crb_draw_triangles_async records the five stage events as well
+ * (this splits the kernel chain, so it is off by default) and crb_finish accumulates them;
+ * crb_get_stage_timing returns the mean milliseconds per stage over the frames finished since
+ * crb_set_stage_timing was last called. */
+int crb_set_stage_timing(crb_ctx* ctx, int enable);
+int crb_get_stage_timing(crb_ctx* ctx, double outMeanMs[4], int* outFrames);
 /* g_crAtomics read-back (CudaRaster.cpp:326). */
 int crb_get_counters(crb_ctx* ctx, crb_atomics* out);
 /* CudaRaster::getProfilingInfo, ProfilingMode_Default report (CudaRaster.cpp:367-422). */

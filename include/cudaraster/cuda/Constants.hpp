@@ -46,4 +46,6 @@
 #define CRB_BIN_THREADS 256       // == CR_MAXBINS_SQR: one thread per bin in the scan phases
 #define CRB_COARSE_THREADS 256    // == CR_BIN_SQR: one thread per tile-in-bin in the scan phases
 #define CRB_ITEM_ENTRIES 256      // bin-queue entries per coarse work item (one warp, 8 batches)
-#define CRB_FINE_WARPS 8          // warps (= tiles in flight) per fine CTA
+#ifndef CRB_FINE_WARPS
+#define CRB_FINE_WARPS 2          // warps (= tiles) per fine CTA: small CTAs, so a long tile does not hold idle warps' slots (measured 1/2/4/8: 51.2/51.1/51.5/53.3 us on C2)
+#endif

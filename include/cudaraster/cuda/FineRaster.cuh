@@ -211,6 +211,43 @@ __device__ __forceinline__ void coverTileRows(const S32 (&a)[3], const S32 (&b)[
     }
 }
 
+// Coverage of a SMALL triangle: its pixel-centre bounding box inside the tile is at most 4x4 pixels
+// (corner pixel (colLo, rowLo), nc x nr pixels) and its extent is below 64 px, so every edge function
+// fits S32 and the 16 candidate pixels are evaluated in straight-line code -- no per-lane loop whose
+// trip count the warp would have to take the maximum of.  Same rule as coverTileRows, bit for bit.
+// (x*, y*) = vertices in viewport-centred subpixels, (bx, by) = centre of the tile's pixel (0,0).
+__device__ __forceinline__ void coverSmall4x4(S32 x0, S32 y0, S32 x1, S32 y1, S32 x2, S32 y2, S32 bx, S32 by, int colLo, int rowLo, int nc, int nr, U32& maskLo, U32& maskHi) {
+    const S32 px = bx + (colLo << CR_SUBPIXEL_LOG2), py = by + (rowLo << CR_SUBPIXEL_LOG2);
+    const S32 dx0 = x1 - x0, dy0 = y1 - y0, dx1 = x2 - x1, dy1 = y2 - y1, dx2 = x0 - x2, dy2 = y0 - y2;
+    // E_i at the corner pixel; stepping one pixel right adds -dy*16, one pixel up adds dx*16
+    S32 e0 = (x0 - px) * dy0 - (y0 - py) * dx0 - ((dy0 > 0 || (dy0 == 0 && dx0 <= 0)) ? 1 : 0);
+    S32 e1 = (x1 - px) * dy1 - (y1 - py) * dx1 - ((dy1 > 0 || (dy1 == 0 && dx1 <= 0)) ? 1 : 0);
+    S32 e2 = (x0 - px) * dy2 - (y0 - py) * dx2 - ((dy2 > 0 || (dy2 == 0 && dx2 <= 0)) ? 1 : 0);
+    const S32 a0 = -(dy0 << CR_SUBPIXEL_LOG2), a1 = -(dy1 << CR_SUBPIXEL_LOG2), a2 = -(dy2 << CR_SUBPIXEL_LOG2);
+    const S32 b0 = dx0 << CR_SUBPIXEL_LOG2, b1 = dx1 << CR_SUBPIXEL_LOG2, b2 = dx2 << CR_SUBPIXEL_LOG2;
+    U32 acc = 0;   // byte r = row rowLo + r, bit x = column colLo + x
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        // walk from column 3 down to 0 so that the funnel shift leaves column 0 in bit 0
+        S32 t0 = e0 + 3 * a0, t1 = e1 + 3 * a1, t2 = e2 + 3 * a2;
+        U32 row = 0;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            row = __funnelshift_l(~(U32)(t0 | t1 | t2), row, 1);
+            t0 -= a0; t1 -= a1; t2 -= a2;
+        }
+        acc |= row << (8 * r);
+        e0 += b0; e1 += b1; e2 += b2;
+    }
+    // pixels beyond the clipped box lie outside the tile (or outside the triangle): drop them
+    const U32 colMask = (1u << nc) - 1u;
+    acc &= colMask * 0x01010101u;
+    acc &= nr >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nr)) - 1u);
+    const unsigned long long m = (unsigned long long)acc << (8 * rowLo + colLo);
+    maskLo = (U32)m;
+    maskHi = (U32)(m >> 32);
+}
+
 // One queued sub-triangle as the refill stage fetched it.
 struct FineFetch {
     S32 entry;     // triIdx*8 + sub, < 0 = none
@@ -248,12 +285,16 @@ struct FineBatch {
 //------------------------------------------------------------------------------------------------
 
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
-__global__ void __launch_bounds__(CRB_FINE_WARPS * 32, 4) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
+static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, 32 / CRB_FINE_WARPS) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
     __shared__ FineBatch s_batch[CRB_FINE_WARPS];
 
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int activeIdx = blockIdx.x * CRB_FINE_WARPS + warp;
+    gridDepLaunchDependents();
+    gridDepWait();
+    // last kernel of the frame: hand the next frame a zeroed counter block (no memset between frames)
+    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = 0;
     // {tile, queue start, queue count} in ONE load, issued together with the counters (the slot is
     // always inside the buffer; it only holds a real record when activeIdx < numActiveTiles)
     const int4 rec = __ldg(&f.activeRecs[activeIdx]);
@@ -307,13 +348,23 @@ __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, 4) fineRasterSingleKernel
         U32 tileZMax = 0xFFFFFFFFu;
         if (kDepth) tileZMax = __reduce_max_sync(0xFFFFFFFFu, max(depth[0], depth[1]));
         U32 maskLo = 0, maskHi = 0;
-        if (cur.entry >= 0 && (!kDepth || (cur.h.w & 0xFFFFF000u) < tileZMax)) {
-            const S32 y0 = (S32)cur.h.x >> 16, y1 = (S32)cur.h.y >> 16, y2 = (S32)cur.h.z >> 16;
-            const int rowLo = max((min(min(y0, y1), y2) - by + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0);
-            const int rowHi = min((max(max(y0, y1), y2) - by) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
-            S32 a[3], b[3], c[3];
-            setupTileEdges(cur.h, bx, by, a, b, c);
-            coverTileRows(a, b, c, rowLo, rowHi, maskLo, maskHi);
+        {
+            const S32 x0 = (S32)(S16)(cur.h.x & 0xFFFF), y0 = (S32)cur.h.x >> 16;
+            const S32 x1 = (S32)(S16)(cur.h.y & 0xFFFF), y1 = (S32)cur.h.y >> 16;
+            const S32 x2 = (S32)(S16)(cur.h.z & 0xFFFF), y2 = (S32)cur.h.z >> 16;
+            const S32 loX = min(min(x0, x1), x2), hiX = max(max(x0, x1), x2), loY = min(min(y0, y1), y2), hiY = max(max(y0, y1), y2);
+            // pixel centres of the tile inside the triangle's bounding box
+            const int colLo = max((loX - bx + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0), colHi = min((hiX - bx) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
+            const int rowLo = max((loY - by + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0), rowHi = min((hiY - by) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
+            const bool live = cur.entry >= 0 && (!kDepth || (cur.h.w & 0xFFFFF000u) < tileZMax) && colLo <= colHi && rowLo <= rowHi;
+            const bool small = (colHi - colLo < 4) & (rowHi - rowLo < 4) & (hiX - loX < (64 << CR_SUBPIXEL_LOG2)) & (hiY - loY < (64 << CR_SUBPIXEL_LOG2));
+            if ((f.debugFlags & 1) == 0 && __all_sync(0xFFFFFFFFu, !live || small)) {
+                if (live) coverSmall4x4(x0, y0, x1, y1, x2, y2, bx, by, colLo, rowLo, colHi - colLo + 1, rowHi - rowLo + 1, maskLo, maskHi);
+            } else if (live) {
+                S32 a[3], b[3], c[3];
+                setupTileEdges(cur.h, bx, by, a, b, c);
+                coverTileRows(a, b, c, rowLo, rowHi, maskLo, maskHi);
+            }
         }
         if (kDepth) {
             sb.zx[lane] = cur.z.x; sb.zy[lane] = cur.z.y;

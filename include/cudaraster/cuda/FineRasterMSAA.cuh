@@ -56,7 +56,7 @@ struct FineBatchMSAA {
 // the triangles touching its two pixels, and the ownership loop tests the N samples of those
 // fragments exactly, in queue order.
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
-__global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRasterMultiKernel(const __grid_constant__ crb_frame f) {
+static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRasterMultiKernel(const __grid_constant__ crb_frame f) {
     constexpr int N = 1 << SamplesLog2;
     constexpr int kWarps = FineWarps<SamplesLog2>::Value;
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRaster
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int activeIdx = blockIdx.x * kWarps + warp;
+    gridDepLaunchDependents();
+    gridDepWait();
+    // last kernel of the frame: hand the next frame a zeroed counter block (no memset between frames)
+    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = 0;
     const int4 rec = __ldg(&f.activeRecs[activeIdx]);
     if (f.atomics->overflow != 0) return;
     if (activeIdx >= f.atomics->numActiveTiles) return;
@@ -261,8 +265,8 @@ struct FineRasterLauncher {
         if ((RenderModeFlags & RenderModeFlag_EnableQuads) != 0) return CRB_ERR_INVALID;
         constexpr int kWarps = FineWarps<SamplesLog2>::Value;
         const int blocks = (f->numTiles + kWarps - 1) / kWarps;
-        fineRasterMultiKernel<VertexClass, FragmentShaderClass, BlendShaderClass, SamplesLog2, RenderModeFlags><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(*f);
-        return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+        return launchChained(fineRasterMultiKernel<VertexClass, FragmentShaderClass, BlendShaderClass, SamplesLog2, RenderModeFlags>, blocks, kWarps * 32, (cudaStream_t)stream, *f) == cudaSuccess
+                   ? CRB_OK : CRB_ERR_CUDA;
     }
 };
 
@@ -271,8 +275,8 @@ struct FineRasterLauncher<VertexClass, FragmentShaderClass, BlendShaderClass, 0,
     static int launch(const crb_frame* f, void* stream) {
         if ((RenderModeFlags & RenderModeFlag_EnableQuads) != 0) return CRB_ERR_INVALID;
         const int blocks = (f->numTiles + CRB_FINE_WARPS - 1) / CRB_FINE_WARPS;
-        fineRasterSingleKernel<VertexClass, FragmentShaderClass, BlendShaderClass, RenderModeFlags><<<blocks, CRB_FINE_WARPS * 32, 0, (cudaStream_t)stream>>>(*f);
-        return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+        return launchChained(fineRasterSingleKernel<VertexClass, FragmentShaderClass, BlendShaderClass, RenderModeFlags>, blocks, CRB_FINE_WARPS * 32, (cudaStream_t)stream, *f) == cudaSuccess
+                   ? CRB_OK : CRB_ERR_CUDA;
     }
 };
 

@@ -97,6 +97,9 @@ struct crb_frame {
     int32_t* activeTiles;         // [CR_MAXTILES_SQR]
     int4* activeRecs;             // [CR_MAXTILES_SQR] {tile index, queue start, queue count, 0}: one load per fine warp
 
-    crb_atomics* atomics;
+    crb_atomics* atomics;         // counters of THIS frame (zero when the frame starts)
+    crb_atomics* nextAtomics;     // counters of the next frame: zeroed by this frame's fine raster kernel
     int32_t numSMs;
+    int32_t debugFlags;           // CRB_DEBUG_FLAGS environment variable; bit 0: fine raster always takes the general coverage path
+    int32_t chainLaunches;        // 1 = kernels are launched with programmatic stream serialization (see Util.cuh)
 };

@@ -204,10 +204,12 @@ __device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, in
 }
 
 template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
-__global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
+static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
     __shared__ int s_binCount[CR_MAXBINS_SQR];
+    gridDepLaunchDependents();
     for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
     __syncthreads();
+    gridDepWait();   // the previous frame's kernels still read the work buffers written below
 
     const int stride4 = (int)(sizeof(VertexClass) / sizeof(float4));
     const float4* __restrict__ verts = reinterpret_cast<const float4*>(f.vertexBuffer);
@@ -277,8 +279,7 @@ template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
 inline int launchTriangleSetup(const crb_frame* f, void* stream) {
     if (f->numTris <= 0) return CRB_OK;
     const int grid = (f->numTris + CRB_SETUP_THREADS - 1) / CRB_SETUP_THREADS;
-    triangleSetupKernel<VertexClass, SamplesLog2, RenderModeFlags><<<grid, CRB_SETUP_THREADS, 0, (cudaStream_t)stream>>>(*f);
-    return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+    return launchChained(triangleSetupKernel<VertexClass, SamplesLog2, RenderModeFlags>, grid, CRB_SETUP_THREADS, (cudaStream_t)stream, *f) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
 }
 
 }  // namespace FW

@@ -175,6 +175,31 @@ __device__ __forceinline__ uint3 setupPleq(float3 values, int2 v0, int2 d1, int2
     return p;
 }
 
+// ---- programmatic dependent launch (sm_90+) --------------------------------------------------------
+// Every kernel of a frame is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the
+// next kernel's CTAs become resident (launch latency, prologue, shared-memory initialisation) while
+// the previous kernel drains, and block in gridDepWait() until the previous grid has completed and its
+// memory is visible.  Nothing a kernel does BEFORE gridDepWait() may touch frame memory.
+__device__ __forceinline__ void gridDepLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void gridDepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// (static: every shared object must launch through ITS OWN copy -- nvcc links the CUDA runtime statically
+// into each of them, and a kernel can only be launched by the runtime instance it is registered with)
+template <class Kernel>
+static inline cudaError_t launchChained(Kernel kernel, int grid, int block, cudaStream_t stream, const crb_frame& f) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = f.chainLaunches ? 1 : 0;   // 0 = plain stream order (CRB_NO_PDL=1, a debugging aid)
+    return cudaLaunchKernelEx(&cfg, kernel, f);
+}
+
 // ---- warp helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ U32 laneId() { return threadIdx.x & 31; }
 __device__ __forceinline__ U32 laneMaskLt() { U32 r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }

@@ -216,3 +216,43 @@ def test_4k_sort_first_windows(raster, crb):
     raster.setSubViewport(0, 0, 0, 0)
     assert np.array_equal(frames[8][0], frames[4][0]) and np.array_equal(frames[8][1], frames[4][1])
     assert (frames[8][1] < 0xFFFFBB3F).mean() > 0.9
+
+
+def test_pipelined_host_frames(raster, crb):
+    """crb_draw_triangles_host_async: six DIFFERENT frames in flight (upload / render / download
+    overlapped, double-buffered staging), each landing in its own host buffer, each bit-exact."""
+    import torch
+    w, h = 640, 360
+    scenes = [crb.scenes.random_soup(6000 + 1500 * k, seed=900 + k, stride_floats=8, size=0.25 + 0.05 * k) for k in range(6)]
+    v0, i0 = scenes[-1]
+    util.draw_cuda(raster, crb, v0, i0, w, h, "gouraud", 3)                 # synchronous: sizes the work buffers for the largest frame
+    hv = [torch.from_numpy(v).pin_memory() for v, _ in scenes]
+    hi = [torch.from_numpy(i).pin_memory() for _, i in scenes]
+    hc = [torch.zeros((360, 640), dtype=torch.int32).pin_memory() for _ in scenes]
+    hd = [torch.zeros((360, 640), dtype=torch.int32).pin_memory() for _ in scenes]
+    for k, (v, i) in enumerate(scenes):
+        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+        raster.drawTrianglesHostAsync(hv[k], hi[k], i.shape[0], hc[k], hd[k])
+    raster.finish()
+    for k, (v, i) in enumerate(scenes):
+        g = util.draw_gold(v, i, w, h, "gouraud", 3)
+        _check_surfaces(hc[k].numpy().view(np.uint32), hd[k].numpy().view(np.uint32), g, lsb=1)
+
+
+def test_back_to_back_frames_of_different_shape(raster, crb):
+    """No memset between frames: the count matrices clean themselves and the counters are handed over
+    by the fine raster kernel.  Alternate scenes / viewports / sample counts (layout changes, empty
+    draws, a frame that overflows its queues and is retried) and compare every frame."""
+    cases = [(640, 360, 20000, 0, 0.3), (320, 200, 3000, 0, 0.8), (640, 360, 20000, 2, 0.3), (1920, 1080, 60000, 0, 0.05), (640, 360, 0, 0, 0.3),
+             (640, 360, 25000, 0, 1.5), (320, 200, 3000, 0, 0.8)]
+    for rep in range(2):
+        for w, h, n, s_log2, size in cases:
+            # 1080p: no triangles with a vertex at w ~ 0-.  Their clipped remains can span the whole guard band with an
+            # overflowed depth plane whose values fall BELOW the triangle's own zmin; the outcome then depends on when the
+            # early-Z cull (reference: FineRaster.inl:229-241) samples the tile's max depth, i.e. it is not defined by the
+            # reference's semantics either (DESIGN.md, "known divergences").
+            v, i = crb.scenes.random_soup(max(n, 1), seed=4000 + n + rep, stride_floats=8, size=size, behind_fraction=0.0 if w > 1000 else 0.05)
+            if n == 0:
+                i = i[:0]
+            cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, s_log2)
+            _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, s_log2), lsb=1)

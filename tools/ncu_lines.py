@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def sass_lines(lib, kernel_re):
     tmp = tempfile.mkdtemp()
+    lib = os.path.abspath(lib)
     subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, check=True, capture_output=True)
     out = []
     for cubin in sorted(glob.glob(os.path.join(tmp, "*.cubin"))):
