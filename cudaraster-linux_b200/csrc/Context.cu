@@ -96,7 +96,8 @@ struct crb_ctx {
     // crb_draw_triangles_host_async: upload / render / download of consecutive frames overlap
     struct HostPipeline {
         bool init = false;
-        cudaStream_t up = nullptr, down = nullptr;
+        cudaStream_t up = nullptr, up2 = nullptr, down = nullptr;   // vertices and indices upload concurrently (two DMA queues in flight)
+        cudaEvent_t uploaded2[2] = {};
         DevBuf verts[2], idx[2];
         cudaEvent_t uploaded[2] = {}, rendered[2] = {}, downloaded = nullptr;
         long long frames = 0;
@@ -353,8 +354,10 @@ int crb_destroy(crb_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     if (c->hp.init) {
         cudaStreamDestroy(c->hp.up);
+        cudaStreamDestroy(c->hp.up2);
         cudaStreamDestroy(c->hp.down);
         for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(c->hp.uploaded2[i]);
             cudaEventDestroy(c->hp.uploaded[i]);
             cudaEventDestroy(c->hp.rendered[i]);
             c->hp.verts[i].release();
@@ -616,8 +619,10 @@ int crb_draw_triangles_host_async(crb_ctx* c, const void* h_vertices, size_t ver
     crb_ctx::HostPipeline& hp = c->hp;
     if (!hp.init) {
         CRB_CUDA(c, cudaStreamCreateWithFlags(&hp.up, cudaStreamNonBlocking));
+        CRB_CUDA(c, cudaStreamCreateWithFlags(&hp.up2, cudaStreamNonBlocking));
         CRB_CUDA(c, cudaStreamCreateWithFlags(&hp.down, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
+            CRB_CUDA(c, cudaEventCreateWithFlags(&hp.uploaded2[i], cudaEventDisableTiming));
             CRB_CUDA(c, cudaEventCreateWithFlags(&hp.uploaded[i], cudaEventDisableTiming));
             CRB_CUDA(c, cudaEventCreateWithFlags(&hp.rendered[i], cudaEventDisableTiming));
         }
@@ -632,13 +637,18 @@ int crb_draw_triangles_host_async(crb_ctx* c, const void* h_vertices, size_t ver
         CRB_CUDA(c, hp.idx[slot].reserve(std::max<size_t>(idxBytes, 16)));
     }
     // upload: the slot was last read by the frame before the previous one
-    if (hp.frames >= 2) CRB_CUDA(c, cudaStreamWaitEvent(hp.up, hp.rendered[slot], 0));
+    if (hp.frames >= 2) {
+        CRB_CUDA(c, cudaStreamWaitEvent(hp.up, hp.rendered[slot], 0));
+        CRB_CUDA(c, cudaStreamWaitEvent(hp.up2, hp.rendered[slot], 0));
+    }
     CRB_CUDA(c, cudaMemcpyAsync(hp.verts[slot].ptr, h_vertices, vertexBytes, cudaMemcpyHostToDevice, hp.up));
-    CRB_CUDA(c, cudaMemcpyAsync(hp.idx[slot].ptr, h_indices, idxBytes, cudaMemcpyHostToDevice, hp.up));
+    CRB_CUDA(c, cudaMemcpyAsync(hp.idx[slot].ptr, h_indices, idxBytes, cudaMemcpyHostToDevice, hp.up2));
     CRB_CUDA(c, cudaEventRecord(hp.uploaded[slot], hp.up));
+    CRB_CUDA(c, cudaEventRecord(hp.uploaded2[slot], hp.up2));
     // render on the caller's stream: needs this frame's upload, and the previous frame's surfaces downloaded
     // (the previous frame's download is already ordered before it, see the end of this function)
     CRB_CUDA(c, cudaStreamWaitEvent(s, hp.uploaded[slot], 0));
+    CRB_CUDA(c, cudaStreamWaitEvent(s, hp.uploaded2[slot], 0));
     c->vertices = hp.verts[slot].ptr;
     c->vertexBytes = vertexBytes;
     c->indices = (const int32_t*)hp.idx[slot].ptr;
