@@ -40,12 +40,15 @@
 // ---- B200 scheduling constants (new) --------------------------------------------------------
 #define CRB_SETUP_THREADS 256     // threads per setup / bin CTA
 #ifndef CRB_SETUP_MIN_BLOCKS
-#define CRB_SETUP_MIN_BLOCKS 4    // resident setup CTAs per SM the register allocation must allow
+#define CRB_SETUP_MIN_BLOCKS 5    // resident setup CTAs per SM the register allocation must allow (5 -> 48 registers, 8 B spill; measured 4/5/6: 42.5/39.6/45.0 us on C2)
 #endif
 #define CRB_MAX_CHUNKS 16384       // chunkTris = CRB_SETUP_THREADS * 2^k, smallest k with numChunks <= this
 #define CRB_BIN_THREADS 256       // == CR_MAXBINS_SQR: one thread per bin in the scan phases
 #define CRB_COARSE_THREADS 256    // == CR_BIN_SQR: one thread per tile-in-bin in the scan phases
 #define CRB_ITEM_ENTRIES 256      // bin-queue entries per coarse work item (one warp, 8 batches)
 #ifndef CRB_FINE_WARPS
+#ifndef CRB_FINE_WARPS_PER_SM
+#define CRB_FINE_WARPS_PER_SM 32  // resident fine warps per SM the register allocation must allow (32 -> 64 registers)
+#endif
 #define CRB_FINE_WARPS 2          // warps (= tiles) per fine CTA: small CTAs, so a long tile does not hold idle warps' slots (measured 1/2/4/8: 51.2/51.1/51.5/53.3 us on C2)
 #endif

@@ -285,7 +285,7 @@ struct FineBatch {
 //------------------------------------------------------------------------------------------------
 
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
-static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, 32 / CRB_FINE_WARPS) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
+static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER_SM / CRB_FINE_WARPS) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
     __shared__ FineBatch s_batch[CRB_FINE_WARPS];
 
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;

@@ -140,6 +140,20 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
 template <int SamplesLog2>
 __device__ __forceinline__ void histogramBins(const crb_frame& f, uint4 h, int* s_binCount) {
     TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
+    // footprints of at most 2x2 bins are never refined (Overlap.cuh): the rectangle IS the cell set
+    const CellRange r = cellRange<CR_BIN_LOG2 + CR_TILE_LOG2>(fp, 0, 0, f.widthBins - 1, f.heightBins - 1);
+    if (!r.refine) {
+        if (r.nx > 0) {
+            int* p = &s_binCount[r.x0 + r.y0 * f.widthBins];
+            atomicAdd(p, 1);
+            if (r.nx > 1) atomicAdd(p + 1, 1);
+            if (r.ny > 1) {
+                atomicAdd(p + f.widthBins, 1);
+                if (r.nx > 1) atomicAdd(p + f.widthBins + 1, 1);
+            }
+        }
+        return;
+    }
     forEachCell<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(fp, 0, 0, f.widthBins - 1, f.heightBins - 1,
                                                           [&](S32 bx, S32 by) { atomicAdd(&s_binCount[bx + by * f.widthBins], 1); });
 }
