@@ -252,11 +252,8 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
     WarpCells& wc = s_cells[warp];
     const unsigned ltMask = laneMaskLt();
     for (int b = lane; b < f.numBins; b += 32) {
-        int* cell = &f.binCountMat[(size_t)b * f.matPitch + chunk];
-        wc.cursor[b] = __ldg(&f.binStart[b]) + *cell;
+        wc.cursor[b] = __ldg(&f.binStart[b]) + f.binCountMat[(size_t)b * f.matPitch + chunk];
         wc.mask[b] = 0;
-        // several setup CTAs ADD into one column: the last reader leaves it zeroed for the next frame
-        if (f.ctasPerChunk > 1) *cell = 0;
     }
     __syncwarp();
     const CellIndexer cellOf = {0, 0, -1, f.widthBins};
@@ -269,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
         hCur = loadH(t0 + 32 + lane, nNext);
         nCur = nNext;
         nNext = loadN(t0 + 64 + lane);
+        if ((f.debugFlags & 2) == 0 && __all_sync(0xFFFFFFFFu, n == 0)) continue;   // nothing survived setup in this batch (the common case of a sub-pixel soup)
         if (__all_sync(0xFFFFFFFFu, n <= 1)) {
             const S32 entry = n == 1 ? tri * 8 + 7 : -1;
             const TriFootprint fp = footprintOf<SamplesLog2>(f, entry, h);
@@ -417,9 +415,7 @@ __global__ void __launch_bounds__(kThreads, 4) coarseScatterKernel(const __grid_
         const int t = lane + 32 * i;
         const int tx = w.tx0 + (t & (CR_BIN_SIZE - 1)), ty = w.ty0 + (t >> CR_BIN_LOG2);
         int cur = 0;
-        int* cell = &f.tileCountMat[(size_t)item * CR_BIN_SQR + t];
-        if (tx <= w.tx1 && ty <= w.ty1) cur = f.tileStart[tx + ty * f.widthTiles] + *cell;
-        *cell = 0;   // last reader of the row: the count matrix is all zero again when the frame ends (no memset per frame)
+        if (tx <= w.tx1 && ty <= w.ty1) cur = f.tileStart[tx + ty * f.widthTiles] + f.tileCountMat[(size_t)item * CR_BIN_SQR + t];
         wc.cursor[t] = cur;
         wc.mask[t] = 0;
     }

@@ -204,7 +204,7 @@ int prepareFrame(crb_ctx* c) {
     f.depthBuffer = c->depth;
     f.surfacePitch = f.widthPixels << c->samplesLog2;
 
-    f.ctasPerChunk = 1;
+    f.ctasPerChunk = std::max(1, CRB_MIN_CHUNK_TRIS / CRB_SETUP_THREADS);
     while (((int64_t)c->numTris + CRB_SETUP_THREADS * f.ctasPerChunk - 1) / (CRB_SETUP_THREADS * f.ctasPerChunk) > CRB_MAX_CHUNKS) f.ctasPerChunk *= 2;
     f.chunkTris = CRB_SETUP_THREADS * f.ctasPerChunk;
     f.numChunks = (c->numTris + f.chunkTris - 1) / f.chunkTris;
@@ -272,6 +272,9 @@ int launchStages(crb_ctx* c, cudaStream_t s, cudaEvent_t* ev) {
         CRB_CUDA(c, cudaMemsetAsync(c->tileCountMat.ptr, 0, c->tileCountMat.cap, s));
         c->needReset = false;
     }
+    // several setup CTAs per chunk ADD their bin counts into one column: that (large-scene) layout needs a zeroed matrix.
+    // (Letting the bin scatter zero the cells it reads was measured 3x slower than this memset: 466 vs 169 us on C4.)
+    if (f->numTris > 0 && f->ctasPerChunk > 1) CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, (size_t)f->matPitch * f->numBins * 4, s));
     c->needReset = true;   // until every launch of this frame went through
     if (ev) CRB_CUDA(c, cudaEventRecord(ev[0], s));
     int rc = c->pipe.triangleSetup(f, s);

@@ -38,7 +38,10 @@
 #define CR_BARY_MAX ((1 << (30 - CR_SUBPIXEL_LOG2)) - 1)
 
 // ---- B200 scheduling constants (new) --------------------------------------------------------
-#define CRB_SETUP_THREADS 256     // threads per setup / bin CTA
+#ifndef CRB_SETUP_THREADS
+#define CRB_SETUP_THREADS 256     // threads per setup CTA (one triangle each)
+#endif
+#define CRB_MIN_CHUNK_TRIS 256    // a chunk (one column of the bin count matrix, one warp of the bin scatter) holds at least this many triangles
 #ifndef CRB_SETUP_MIN_BLOCKS
 #define CRB_SETUP_MIN_BLOCKS 5    // resident setup CTAs per SM the register allocation must allow (5 -> 48 registers, 8 B spill; measured 4/5/6: 42.5/39.6/45.0 us on C2)
 #endif

@@ -24,6 +24,21 @@
 
 namespace FW {
 
+// The fine raster kernel is the last kernel of a frame: it leaves the per-frame scratch state the way
+// the next frame expects it, so that a steady-state frame enqueues kernels only (no memsets):
+//  * the counter block of the NEXT frame (double-buffered) is zeroed;
+//  * the rows of the tile count matrix this frame used (one per coarse work item) are zeroed again --
+//    plain coalesced 16-byte stores spread over the whole grid.  (Zeroing each row in the coarse scatter
+//    kernel right after it is read was measured 8 us slower on C2: 31.2 vs 23.5 us for the coarse stage.)
+// Must run after gridDepWait() and before any early return.
+__device__ __forceinline__ void finishFrameState(const crb_frame& f) {
+    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = 0;
+    const int rows = min(f.atomics->numCoarseItems, f.maxItems);
+    const int total = rows * (CR_BIN_SQR / 4);
+    int4* mat = reinterpret_cast<int4*>(f.tileCountMat);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) mat[i] = make_int4(0, 0, 0, 0);
+}
+
 struct FineTriRec {  // 64 B, one per queued triangle of the current batch
     S32 a0, b0, c0, a1;   // edge i: E(sx, sy) = c_i + a_i*sx + b_i*sy >= 0, (sx, sy) = subpixel
     S32 b1, c1, a2, b2;   //         offset of the sample from the centre of the tile's pixel (0,0)
@@ -293,8 +308,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     const int activeIdx = blockIdx.x * CRB_FINE_WARPS + warp;
     gridDepLaunchDependents();
     gridDepWait();
-    // last kernel of the frame: hand the next frame a zeroed counter block (no memset between frames)
-    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = 0;
+    finishFrameState(f);
     // {tile, queue start, queue count} in ONE load, issued together with the counters (the slot is
     // always inside the buffer; it only holds a real record when activeIdx < numActiveTiles)
     const int4 rec = __ldg(&f.activeRecs[activeIdx]);

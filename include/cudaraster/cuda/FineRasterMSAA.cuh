@@ -69,8 +69,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
     const int activeIdx = blockIdx.x * kWarps + warp;
     gridDepLaunchDependents();
     gridDepWait();
-    // last kernel of the frame: hand the next frame a zeroed counter block (no memset between frames)
-    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = 0;
+    finishFrameState(f);
     const int4 rec = __ldg(&f.activeRecs[activeIdx]);
     if (f.atomics->overflow != 0) return;
     if (activeIdx >= f.atomics->numActiveTiles) return;
