@@ -160,7 +160,7 @@ def time_ref_kernels(workload, timeout=240):
     if not os.path.exists(lib):
         return {"status": "not built"}
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "7"],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "7"] + (["--check"] if workload == "c2" else []),
                            capture_output=True, text=True, timeout=timeout)
     except subprocess.TimeoutExpired:
         return {"status": "hang (killed after %d s)" % timeout}

@@ -32,13 +32,17 @@ extern "C" int userLaunchVertexShader(const float* posToClipColumnMajor, const v
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+#ifndef USER_STRIPE_SHIFT
+#define USER_STRIPE_SHIFT 3   // a -D define of the run-time compiler (FW::CudaCompiler::define) changes the checker size
+#endif
+
 // Interpolated colour with a screen-space stripe pattern: exercises m_pixelPos and varyings.
 class FragmentShader_user : public FragmentShaderBase {
 public:
     enum { CanDiscard = 0 };
     __device__ __forceinline__ void run(void) {
         Vec4f c = interpolateVarying(0, m_centroid);
-        if (((m_pixelPos.x >> 3) ^ (m_pixelPos.y >> 3)) & 1) c = Vec4f(c.x * 0.5f, c.y * 0.5f, c.z * 0.5f, 1.0f);
+        if (((m_pixelPos.x >> USER_STRIPE_SHIFT) ^ (m_pixelPos.y >> USER_STRIPE_SHIFT)) & 1) c = Vec4f(c.x * 0.5f, c.y * 0.5f, c.z * 0.5f, 1.0f);
         m_color = toABGR(c);
     }
 };

@@ -1,8 +1,11 @@
 // The reference's demo frame (test/App.cpp:208-241 cube, test/SceneCR.cpp:243-317 render) written
 // against the kept host API (include/cudaraster/CudaRaster.hpp) -- no GL, no GLUT:
 //   vertex shader kernel -> deferredClear -> setVertexBuffer/setIndexBuffer -> drawTriangles -> getStats.
-// Usage: cube <libuserpipes.so> <out.raw> [width height]
+// Usage: cube <libuserpipes.so | UserPipes.cu> <out.raw> [width height [stripeShift]]
+// A .cu argument is compiled at run time with FW::CudaCompiler (cache next to out.raw), the way
+// test/SceneCR.cpp:67-90, :170-179 compiles its shader file, with -DUSER_STRIPE_SHIFT=<stripeShift>.
 // Writes width, height (int32) then the colour and depth surfaces (U32 each) to out.raw.
+#include <cudaraster/CudaCompiler.hpp>
 #include <cudaraster/CudaRaster.hpp>
 
 #include <cmath>
@@ -48,7 +51,19 @@ int main(int argc, char** argv) {
     CudaRaster cr;
     cr.init();
     CudaSurface color(Vec2i(w, h), CudaSurface::FORMAT_RGBA8), depth(Vec2i(w, h), CudaSurface::FORMAT_DEPTH32);
-    CudaModule module(argv[1]);
+    const std::string arg1(argv[1]);
+    CudaCompiler compiler;
+    CudaModule* compiled = NULL;
+    if (arg1.size() > 3 && arg1.substr(arg1.size() - 3) == ".cu") {
+        const std::string outPath(argv[2]);
+        const size_t slash = outPath.find_last_of('/');
+        compiler.setCachePath((slash == std::string::npos ? std::string(".") : outPath.substr(0, slash)) + "/cudacache");
+        compiler.setSourceFile(arg1);
+        compiler.define("USER_STRIPE_SHIFT", argc > 5 ? atoi(argv[5]) : 3);
+        compiled = compiler.compile();
+    }
+    CudaModule preBuilt(compiled ? "" : arg1);
+    CudaModule& module = compiled ? *compiled : preBuilt;
     VertexShaderFn vs = (VertexShaderFn)dlsym(module.getHandle(), "userLaunchVertexShader");
     if (!vs) fail("cube: userLaunchVertexShader not found in %s", argv[1]);
 

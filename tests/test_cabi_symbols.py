@@ -63,3 +63,26 @@ def test_pack_helpers_match_reference_known_answers(crb):
     assert lib.crb_encode_clear_depth(1.0) == 0xFFFFBB3F
     assert lib.crb_encode_clear_depth(0.5) == 0x7FFFFFFF
     assert lib.crb_encode_clear_depth(0.0) == 0x000044C0
+
+
+def test_runtime_pipe_compiler_builds_and_caches(tmp_path):
+    """FW::CudaCompiler (include/cudaraster/CudaCompiler.hpp): compiles a user pixel-pipe source with
+    nvcc for sm_100a into a cached shared object that exports the five by-name symbols of the pipe
+    (CudaRaster.cpp:190-201); a different -D define gives a different cache entry, the same one a hit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "cpp", "compile_pipe")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "examples", "cpp")], check=True, capture_output=True)
+    src = os.path.join(root, "examples", "cpp", "UserPipes.cu")
+    cache = str(tmp_path / "cudacache")
+    r1 = subprocess.run([exe, src, cache, "USER_STRIPE_SHIFT=4"], capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0 and "Compiling" in r1.stdout, r1.stdout + r1.stderr
+    so = r1.stdout.strip().splitlines()[-1]
+    r2 = subprocess.run([exe, src, cache, "USER_STRIPE_SHIFT=4"], capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0 and "cached" in r2.stdout and r2.stdout.strip().splitlines()[-1] == so
+    r3 = subprocess.run([exe, src, cache, "USER_STRIPE_SHIFT=5"], capture_output=True, text=True, timeout=600)
+    assert r3.returncode == 0 and r3.stdout.strip().splitlines()[-1] != so
+    syms = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+    for suffix in ("_triangleSetup", "_binRaster", "_coarseRaster", "_fineRaster", "_spec"):
+        assert "PixelPipe_user" + suffix in syms
