@@ -70,6 +70,55 @@ def gather_frames(frame, gather_list, dst=0):
     dist.gather(frame, gather_list if dist.get_rank() == dst else None, dst=dst)
 
 
+class AsyncFrameGather:
+    """Gather of one frame per rank to `dst`, overlapped with the rendering of the next frame.
+
+    The caller renders frame k into ``surfaces[k % depth]`` on its own stream and calls ``submit(k)``;
+    the gather runs on a side stream (NCCL), and ``before_render(k)`` makes the render stream wait until
+    the gather that last read ``surfaces[k % depth]`` is done.  ``finish()`` joins the side stream.
+    On CPU tensors (gloo tests) everything degenerates to a synchronous gather."""
+
+    def __init__(self, surfaces, world, rank, dst=0):
+        import torch
+        self.torch, self.surfaces, self.world, self.rank, self.dst = torch, list(surfaces), world, rank, dst
+        self.cuda = self.surfaces[0].is_cuda
+        self.recv = [[torch.empty_like(s) for _ in range(world)] if rank == dst else None for s in self.surfaces]
+        if self.cuda:
+            dev = self.surfaces[0].device
+            self.side = torch.cuda.Stream(device=dev)
+            self.rendered = [torch.cuda.Event() for _ in self.surfaces]
+            self.gathered = [None for _ in self.surfaces]
+
+    def before_render(self, k):
+        i = k % len(self.surfaces)
+        if self.cuda and self.gathered[i] is not None:
+            self.torch.cuda.current_stream(self.surfaces[i].device).wait_event(self.gathered[i])
+        return self.surfaces[i]
+
+    def submit(self, k):
+        import torch.distributed as dist
+        i = k % len(self.surfaces)
+        if not self.cuda:
+            dist.gather(self.surfaces[i], self.recv[i], dst=self.dst)
+            return
+        torch = self.torch
+        self.rendered[i].record(torch.cuda.current_stream(self.surfaces[i].device))
+        self.side.wait_event(self.rendered[i])
+        with torch.cuda.stream(self.side):
+            dist.gather(self.surfaces[i], self.recv[i], dst=self.dst)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.gathered[i] = ev
+
+    def finish(self):
+        if self.cuda:
+            self.torch.cuda.current_stream(self.surfaces[0].device).wait_stream(self.side)
+
+    def frames(self, k):
+        """The gathered frames of step k on `dst` (valid after finish() / a later before_render of the same slot)."""
+        return self.recv[k % len(self.surfaces)]
+
+
 def composite_sort_first(local_rects, local_tiles, full_w, full_h, num_rects, dst=0, out=None):
     """Composites sort-first rectangles on rank `dst`.
 

@@ -54,6 +54,16 @@ def _worker(rank, world, port, out_path):
             multigpu.gather_frames(f, lst, dst=0)
             if rank == 0:
                 gathered.append([t.numpy().view(np.uint32) for t in lst])
+        # ---- the double-buffered gather bench.py uses (synchronous on CPU tensors): frame k of every rank lands in slot k % 2
+        surf = [torch.zeros((4, 8), dtype=torch.int32) for _ in range(2)]
+        ag = multigpu.AsyncFrameGather(surf, world, rank, dst=0)
+        ag_ok = True
+        for k in range(5):
+            ag.before_render(k).fill_(100 * k + rank)
+            ag.submit(k)
+            ag.finish()
+            if rank == 0:
+                ag_ok = ag_ok and all(int(t[0, 0]) == 100 * k + r and bool((t == 100 * k + r).all()) for r, t in enumerate(ag.frames(k)))
         if rank == 0:
             full = util.draw_gold(v, i, fw, fh, "gouraud", 3, threads=2)
             ok = np.array_equal(comp_c.numpy().view(np.uint32), full["color"]) and np.array_equal(comp_d.numpy().view(np.uint32), full["depth"])
@@ -63,7 +73,7 @@ def _worker(rank, world, port, out_path):
                     ref = util.draw_gold(crb.scenes.apply_view(v, views[k]), i, 256, 192, "gouraud", 3, threads=2)
                     ok = ok and np.array_equal(frame, ref["color"])
             with open(out_path, "w") as fh_:
-                fh_.write("ok" if ok else "mismatch")
+                fh_.write("ok" if (ok and ag_ok) else "mismatch")
         dist.barrier()
     finally:
         dist.destroy_process_group()
