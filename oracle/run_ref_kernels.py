@@ -21,8 +21,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-def load():
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so"))
+def load(path=None):
+    lib = ctypes.CDLL(path or os.environ.get("CRREF_LIBRARY") or os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so"))
     vp = ctypes.c_void_p
     lib.crref_last_error.restype = ctypes.c_char_p
     lib.crref_pipe_name.restype = ctypes.c_char_p
