@@ -87,6 +87,9 @@ def load_library():
         "crb_get_launch_count": (i32, [vp]),
         "crb_get_work_buffers": (i32, [vp, ctypes.POINTER(WorkBuffers)]),
         "crb_download": (i32, [vp, vp, vp, ctypes.c_size_t]),
+        "crb_resolve_surface": (i32, [vp, i32, i32, i32, vp, i32, i32, vp]),
+        "crb_write_ppm": (i32, [ctypes.c_char_p, vp, i32, i32, i32]),
+        "crb_launch_vertex_shader": (i32, [vp, ctypes.c_char_p, vp, vp, i32, vp, ctypes.c_size_t, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -99,7 +102,8 @@ def load_library():
 EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
-                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download"]
+                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
+                    "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
 def pipe_name(base, samples_log2, flags, blend="BlendReplace"):
@@ -154,6 +158,26 @@ class CudaSurface:
 
     def numpy(self):
         return self.tensor.cpu().numpy().view(np.uint32)
+
+    def resolve(self, flip_y=False, stream=None):
+        """MSAA resolve into a linear [height, width] int32 CUDA tensor (reference: CudaSurface::resolveToScreen,
+        CudaSurface.hpp:73): box filter over the samples of every pixel (crb_resolve_surface)."""
+        import torch
+        lib = load_library()
+        out = torch.empty((self.size[1], self.size[0]), dtype=torch.int32, device=self.tensor.device)
+        s = torch.cuda.current_stream(self.tensor.device).cuda_stream if stream is None else stream
+        rc = lib.crb_resolve_surface(self.tensor.data_ptr(), self.size[0], self.size[1], self.num_samples, out.data_ptr(), self.size[0], 1 if flip_y else 0,
+                                     ctypes.c_void_p(s))
+        if rc != 0:
+            raise CrbError("CudaSurface: resolve failed with status %d" % rc)
+        return out
+
+    def writePPM(self, path):
+        """Resolves and writes the colour image as a binary PPM, top scanline first."""
+        img = np.ascontiguousarray(self.resolve(flip_y=True).cpu().numpy().view(np.uint32))
+        rc = load_library().crb_write_ppm(path.encode(), img.ctypes.data, self.size[0], self.size[1], self.size[0])
+        if rc != 0:
+            raise CrbError("CudaSurface: cannot write %s" % path)
 
 
 class CudaRaster:
@@ -274,6 +298,16 @@ class CudaRaster:
         return buf.value.decode()
 
     # -- extras ------------------------------------------------------------------------------
+    def launchVertexShader(self, module, name, in_vertices, out_vertices, num_vertices, constants, stream=None):
+        """The demo's vertex-shader launch (test/SceneCR.cpp:263-282): `name`_launch of a pixel-pipe module (None = built in);
+        constants = bytes-like block passed by value (the reference's c_constants)."""
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        handle = None if module is None else ctypes.c_void_p(module._handle)
+        blob = bytes(constants)
+        rc = self.lib.crb_launch_vertex_shader(handle, name.encode(), in_vertices.data_ptr(), out_vertices.data_ptr(), int(num_vertices), blob, len(blob), ctypes.c_void_p(s))
+        if rc != 0:
+            raise CrbError("CudaRaster: vertex shader %s failed with status %d" % (name, rc))
+
     def getCounters(self):
         a = Atomics()
         self._check(self.lib.crb_get_counters(self.ctx, ctypes.byref(a)))

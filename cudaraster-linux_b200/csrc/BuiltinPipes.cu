@@ -37,6 +37,18 @@ public:
     }
 };
 
+// Screen-space derivatives of the interpolated colour (RenderModeFlag_EnableQuads; exercises dFdx / dFdy):
+// colour = (8|dFdx c.r| + 8|dFdy c.r|, 8|dFdx c.g| + 8|dFdy c.g|, c.b, c.a).  Oracle: runShaderQuads.
+class FragmentShader_gouraudQuads : public FragmentShaderBase {
+public:
+    enum { CanDiscard = 0 };
+    __device__ __forceinline__ void run(void) {
+        const Vec4f c = interpolateVarying(0, m_centroid);
+        const F32 dxr = dFdx(c.x), dyr = dFdy(c.x), dxg = dFdx(c.y), dyg = dFdy(c.y);
+        m_color = toABGR(Vec4f(__fmaf_rn(fabsf(dyr), 8.0f, __fmul_rn(fabsf(dxr), 8.0f)), __fmaf_rn(fabsf(dyg), 8.0f, __fmul_rn(fabsf(dxg), 8.0f)), c.z, c.w));
+    }
+};
+
 // Phong lighting of test/shader/Shaders.cu:37-51 with a PROCEDURAL checker texture: the
 // reference's textured variant samples a texture atlas asset that is not in the tree.  All
 // arithmetic is spelled out in IEEE single operations so that the CPU oracle
@@ -75,6 +87,7 @@ CR_DEFINE_PIXEL_PIPE(PixelPipe_passthrough, ShadedVertex_passthrough, FragmentSh
 #define CRB_PASSTHROUGH(S, F, BLEND) CRB_PIPE(passthrough, ShadedVertex_passthrough, FragmentShader_passthrough, BLEND, S, F)
 #define CRB_GOURAUD(S, F, BLEND) CRB_PIPE(gouraud, ShadedVertex_gouraud, FragmentShader_gouraud, BLEND, S, F)
 #define CRB_GOURAUD_DISCARD(S, F, BLEND) CRB_PIPE(gouraudDiscard, ShadedVertex_gouraud, FragmentShader_gouraudDiscard, BLEND, S, F)
+#define CRB_GOURAUD_QUADS(S, F, BLEND) CRB_PIPE(gouraudQuads, ShadedVertex_gouraud, FragmentShader_gouraudQuads, BLEND, S, F)
 #define CRB_TEXPHONG(S, F, BLEND) CRB_PIPE(texPhong, ShadedVertex_texPhong, FragmentShader_texPhong, BLEND, S, F)
 
 CRB_PASSTHROUGH(0, 0, BlendReplace)
@@ -100,5 +113,48 @@ CRB_GOURAUD(2, 2, BlendSrcOver)
 CRB_GOURAUD_DISCARD(0, 3, BlendReplace)
 CRB_GOURAUD_DISCARD(2, 3, BlendReplace)
 
+// RenderModeFlag_EnableQuads (flags bit 2): visibility-first and in-order single-sample paths, MSAA, and a
+// discarding shader whose helper lanes must keep running
+CRB_GOURAUD_QUADS(0, 7, BlendReplace)
+CRB_GOURAUD_QUADS(0, 7, BlendSrcOver)
+CRB_GOURAUD_QUADS(0, 6, BlendSrcOver)
+CRB_GOURAUD_QUADS(2, 7, BlendReplace)
+CRB_GOURAUD_QUADS(1, 7, BlendSrcOver)
+CRB_GOURAUD_DISCARD(0, 7, BlendReplace)
+
 CRB_TEXPHONG(0, 3, BlendReplace)
 CRB_TEXPHONG(2, 3, BlendReplace)
+
+// ---- vertex shaders ----------------------------------------------------------------
+// The demo's pass-through vertex shader (test/shader/PassThrough.cu:16-35): clipPos = posToClip * (modelPos, 1).
+// The matrix-vector product is spelled as the fma chain nvcc contracts the reference's generic
+// Matrix::operator* into (framework/base/Math.hpp: r[i] += m(i,j) * v[j], j ascending), so the CPU oracle
+// (oracle/golden.hpp: transformPoint) reproduces it bit for bit.
+struct VsConstants_passthrough { Mat4f posToClip; };                  // test/shader/PassThrough.hpp:15-18
+struct VsInputVertex_passthrough { Vec3f modelPos; };                 // test/shader/PassThrough.hpp:26-29
+struct VsInputVertex_color { Vec3f modelPos; Vec4f color; };
+
+static __device__ __forceinline__ Vec4f transformPoint(const Mat4f& m, const Vec3f& p) {
+    Vec4f r;
+    r.x = __fmaf_rn(m.m[3][0], 1.0f, __fmaf_rn(m.m[2][0], p.z, __fmaf_rn(m.m[1][0], p.y, __fmul_rn(m.m[0][0], p.x))));
+    r.y = __fmaf_rn(m.m[3][1], 1.0f, __fmaf_rn(m.m[2][1], p.z, __fmaf_rn(m.m[1][1], p.y, __fmul_rn(m.m[0][1], p.x))));
+    r.z = __fmaf_rn(m.m[3][2], 1.0f, __fmaf_rn(m.m[2][2], p.z, __fmaf_rn(m.m[1][2], p.y, __fmul_rn(m.m[0][2], p.x))));
+    r.w = __fmaf_rn(m.m[3][3], 1.0f, __fmaf_rn(m.m[2][3], p.z, __fmaf_rn(m.m[1][3], p.y, __fmul_rn(m.m[0][3], p.x))));
+    return r;
+}
+
+struct VertexShader_passthrough {
+    __device__ __forceinline__ void operator()(const VsInputVertex_passthrough& in, ShadedVertex_passthrough& out, const VsConstants_passthrough& c, int) const {
+        out.clipPos = transformPoint(c.posToClip, in.modelPos);
+    }
+};
+// Transform + per-vertex colour carried through (the Gouraud pipe's vertex format).
+struct VertexShader_color {
+    __device__ __forceinline__ void operator()(const VsInputVertex_color& in, ShadedVertex_gouraud& out, const VsConstants_passthrough& c, int) const {
+        out.clipPos = transformPoint(c.posToClip, in.modelPos);
+        out.color = in.color;
+    }
+};
+
+CR_DEFINE_VERTEX_SHADER(vertexShader_passthrough, VsInputVertex_passthrough, ShadedVertex_passthrough, VsConstants_passthrough, VertexShader_passthrough)
+CR_DEFINE_VERTEX_SHADER(vertexShader_color, VsInputVertex_color, ShadedVertex_gouraud, VsConstants_passthrough, VertexShader_color)

@@ -303,7 +303,6 @@ int validateDraw(crb_ctx* c) {
     if (!c->verticesSet || (!c->vertices && c->numTris > 0)) return setError(c, CRB_ERR_INVALID, "CudaRaster: Vertex buffer not set!");
     if (!c->indicesSet || (!c->indices && c->numTris > 0)) return setError(c, CRB_ERR_INVALID, "CudaRaster: Index buffer not set!");
     if (c->spec.samplesLog2 != c->samplesLog2) return setError(c, CRB_ERR_INVALID, "CudaRaster: Mismatch in multisampling between pixel pipe and surface!");
-    if ((c->spec.renderModeFlags & CRB_FLAG_QUADS) != 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: RenderModeFlag_EnableQuads is not supported by the B200 pipeline yet!");
     return CRB_OK;
 }
 
@@ -755,6 +754,38 @@ int crb_get_work_buffers(crb_ctx* c, crb_work_buffers* out) {
     out->tileCount = f.tileCount;
     out->numTiles = f.numTiles;
     out->activeTiles = f.activeTiles;
+    return CRB_OK;
+}
+
+int crb_launch_vertex_shader(void* module, const char* name, const void* d_in, void* d_out, int numVertices, const void* h_constants, size_t constantsBytes, void* stream) {
+    if (!name) return CRB_ERR_INVALID;
+    void* handle = module;
+    if (!handle) {
+        Dl_info info;
+        if (dladdr((const void*)&crb_abi_version, &info) && info.dli_fname) handle = dlopen(info.dli_fname, RTLD_NOW | RTLD_NOLOAD);
+        if (!handle) handle = dlopen(nullptr, RTLD_NOW);
+    }
+    crb_vertex_shader_fn fn = (crb_vertex_shader_fn)dlsym(handle, (std::string(name) + "_launch").c_str());
+    if (!fn) return CRB_ERR_INVALID;
+    return fn(d_in, d_out, numVertices, h_constants, constantsBytes, stream);
+}
+
+int crb_write_ppm(const char* path, const uint32_t* px, int width, int height, int pitch) {
+    if (!path || !px || width <= 0 || height <= 0 || pitch < width) return CRB_ERR_INVALID;
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return CRB_ERR_INVALID;
+    fprintf(fp, "P6\n%d %d\n255\n", width, height);
+    std::vector<unsigned char> row((size_t)width * 3);
+    for (int y = 0; y < height; y++) {
+        for (int x = 0; x < width; x++) {
+            const uint32_t t = px[(size_t)y * pitch + x];
+            row[3 * x + 0] = (unsigned char)(t & 0xFF);
+            row[3 * x + 1] = (unsigned char)((t >> 8) & 0xFF);
+            row[3 * x + 2] = (unsigned char)((t >> 16) & 0xFF);
+        }
+        if (fwrite(row.data(), 1, row.size(), fp) != row.size()) { fclose(fp); return CRB_ERR_INVALID; }
+    }
+    fclose(fp);
     return CRB_OK;
 }
 

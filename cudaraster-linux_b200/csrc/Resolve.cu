@@ -1,0 +1,80 @@
+// MSAA resolve and surface read-back helpers.
+//
+// The reference declares CudaSurface::resolveToScreen (src/cudaraster/CudaSurface.hpp:73: "Resolves MSAA
+// and writes pixels into the current GL render target") but the Linux port dropped its body together
+// with the GL blit; the demo calls its own resolveToScreen() after drawTriangles (test/SceneCR.cpp:297).
+// Here the resolve is a CUDA kernel over the tile-replicated sample layout (sample i of pixel (x, y) at
+// texel ((x>>3)*8N + 8i + (x&7), y), FineRaster.inl:909, :1088-1100) into a LINEAR width x height image:
+// box filter, every 8-bit channel = (sum of the N samples + N/2) >> log2 N (round half up).
+//
+// HBM-bound streaming kernel: one thread resolves 4 horizontally adjacent pixels with 128-bit loads (one
+// per sample) and one 128-bit store; algorithmic bytes = 4 (N + 1) per pixel.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/crb200.h"
+
+namespace {
+
+template <int N>
+__global__ void __launch_bounds__(256) resolveKernel(const uint4* __restrict__ src, int srcPitch4, uint32_t* __restrict__ dst, int dstPitch, int width, int height, int flipY) {
+    // thread -> 4 pixels: x4 = 4-pixel group in the row
+    const int groupsPerRow = (width + 3) >> 2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= groupsPerRow * height) return;
+    const int y = gid / groupsPerRow, x4 = gid - y * groupsPerRow;
+    const int x = x4 << 2;
+    // texel column of sample 0: (x>>3)*8N + (x&7); in uint4 units: (x>>3)*2N + ((x&7)>>2)
+    const uint4* p = src + (size_t)y * srcPitch4 + (size_t)(x >> 3) * (2 * N) + ((x & 7) >> 2);
+    uint32_t rb[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0};   // two 16-bit lanes each: no overflow for N <= 8 (8 * 255 < 65536)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint4 t = __ldg(p + 2 * i);
+        const uint32_t v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            rb[k] += v[k] & 0x00FF00FFu;
+            ga[k] += (v[k] >> 8) & 0x00FF00FFu;
+        }
+    }
+    constexpr int L = N == 1 ? 0 : N == 2 ? 1 : N == 4 ? 2 : 3;
+    constexpr uint32_t half = (uint32_t)(N >> 1) * 0x00010001u;
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t a = ((rb[k] + half) >> L) & 0x00FF00FFu;
+        const uint32_t b = ((ga[k] + half) >> L) & 0x00FF00FFu;
+        out[k] = a | (b << 8);
+    }
+    const int oy = flipY ? height - 1 - y : y;
+    uint32_t* q = dst + (size_t)oy * dstPitch + x;
+    if (x + 3 < width && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+        *reinterpret_cast<uint4*>(q) = make_uint4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (x + k < width) q[k] = out[k];
+    }
+}
+
+}  // namespace
+
+extern "C" int crb_resolve_surface(const void* d_src, int width, int height, int numSamples, void* d_dst, int dstPitch, int flipY, void* stream) {
+    if (!d_src || !d_dst || width <= 0 || height <= 0 || dstPitch < width) return CRB_ERR_INVALID;
+    if (width > CRB_MAX_VIEWPORT || height > CRB_MAX_VIEWPORT) return CRB_ERR_LIMIT;
+    const int roundedW = (width + 7) & ~7;
+    const int srcPitch4 = roundedW * numSamples / 4;
+    const int groups = ((width + 3) >> 2) * height;
+    const int block = 256, grid = (groups + block - 1) / block;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint4* src = (const uint4*)d_src;
+    uint32_t* dst = (uint32_t*)d_dst;
+    switch (numSamples) {
+        case 1: resolveKernel<1><<<grid, block, 0, s>>>(src, srcPitch4, dst, dstPitch, width, height, flipY); break;
+        case 2: resolveKernel<2><<<grid, block, 0, s>>>(src, srcPitch4, dst, dstPitch, width, height, flipY); break;
+        case 4: resolveKernel<4><<<grid, block, 0, s>>>(src, srcPitch4, dst, dstPitch, width, height, flipY); break;
+        case 8: resolveKernel<8><<<grid, block, 0, s>>>(src, srcPitch4, dst, dstPitch, width, height, flipY); break;
+        default: return CRB_ERR_INVALID;
+    }
+    return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}

@@ -46,9 +46,8 @@ def _look_at(eye, center, up):
     return m
 
 
-def cube(width=1024, height=768):
-    """BASELINE config 1: 12 triangles; MVP = perspective(60 deg, w/h, 0.1, 100) * lookAt((0,2,4),(0,0,0),up)
-    (test/App.cpp:83-103); vertex shader = clipPos = MVP * (pos, 1) (test/shader/PassThrough.cu:31-34)."""
+def cube_mvp(width=1024, height=768):
+    """The demo camera's posToClip, column-major m[col][row] (test/App.cpp:83-103)."""
     eye, target = np.array([0, 2, 4], np.float32), np.zeros(3, np.float32)
     d = target - eye
     d = d / np.float32(np.linalg.norm(d))
@@ -66,6 +65,13 @@ def cube(width=1024, height=768):
             for k in range(4):
                 acc = np.float32(acc + proj[k][r] * view[c][k])
             mvp[c][r] = acc
+    return mvp
+
+
+def cube(width=1024, height=768):
+    """BASELINE config 1: 12 triangles; MVP = perspective(60 deg, w/h, 0.1, 100) * lookAt((0,2,4),(0,0,0),up)
+    (test/App.cpp:83-103); vertex shader = clipPos = MVP * (pos, 1) (test/shader/PassThrough.cu:31-34)."""
+    mvp = cube_mvp(width, height)
     verts = np.zeros((8, 4), np.float32)
     for i, p in enumerate(CUBE_POSITIONS):
         for r in range(4):

@@ -7,30 +7,23 @@
 
 using namespace FW;
 
-struct UserConstants { Mat4f posToClip; };
-__constant__ UserConstants c_user;
+struct UserConstants { Mat4f posToClip; };   // the reference's c_constants block (test/shader/PassThrough.hpp:15-18); passed by value
 
 struct InputVertex { Vec3f modelPos; };
 typedef GouraudVertex ShadedVertex_user;   // clipPos + one varying (colour)
 
 // clipPos = posToClip * (modelPos, 1); colour from the position (test/shader/PassThrough.cu:16-35).
-extern "C" __global__ void vertexShader_user(const InputVertex* in, ShadedVertex_user* out, int numVertices) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= numVertices) return;
-    const Vec3f p = in[i].modelPos;
-    out[i].clipPos = c_user.posToClip * Vec4f(p, 1.0f);
-    out[i].color = Vec4f(p.x * 0.5f + 0.5f, p.y * 0.5f + 0.5f, p.z * 0.5f + 0.5f, 1.0f);
-}
+struct VertexShader_user {
+    __device__ __forceinline__ void operator()(const InputVertex& in, ShadedVertex_user& out, const UserConstants& c, int) const {
+        const Vec3f p = in.modelPos;
+        out.clipPos = c.posToClip * Vec4f(p, 1.0f);
+        out.color = Vec4f(p.x * 0.5f + 0.5f, p.y * 0.5f + 0.5f, p.z * 0.5f + 0.5f, 1.0f);
+    }
+};
 
-// Host entry the demo calls instead of cuLaunchGrid on a kernel found by name (test/SceneCR.cpp:275-282).
-extern "C" int userLaunchVertexShader(const float* posToClipColumnMajor, const void* d_in, void* d_out, int numVertices, void* stream) {
-    UserConstants c;
-    for (int col = 0; col < 4; col++)
-        for (int row = 0; row < 4; row++) c.posToClip.m[col][row] = posToClipColumnMajor[col * 4 + row];
-    if (cudaMemcpyToSymbolAsync(c_user, &c, sizeof(c), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return 1;
-    vertexShader_user<<<(numVertices + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const InputVertex*)d_in, (ShadedVertex_user*)d_out, numVertices);
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
-}
+// Emits vertexShader_user_launch, which CudaModule::launchVertexShader("vertexShader_user", ...) finds by name
+// (the reference finds the kernel by name and launches it with cuLaunchGrid, test/SceneCR.cpp:81, :275-282).
+CR_DEFINE_VERTEX_SHADER(vertexShader_user, InputVertex, ShadedVertex_user, UserConstants, VertexShader_user)
 
 #ifndef USER_STRIPE_SHIFT
 #define USER_STRIPE_SHIFT 3   // a -D define of the run-time compiler (FW::CudaCompiler::define) changes the checker size

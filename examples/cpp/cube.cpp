@@ -14,7 +14,7 @@
 
 using namespace FW;
 
-typedef int (*VertexShaderFn)(const float*, const void*, void*, int, void*);
+struct UserConstants { Mat4f posToClip; };   // must match UserPipes.cu
 
 static void mul(float* o, const float* a, const float* b) {  // column-major o = a * b
     for (int c = 0; c < 4; c++)
@@ -64,12 +64,12 @@ int main(int argc, char** argv) {
     }
     CudaModule preBuilt(compiled ? "" : arg1);
     CudaModule& module = compiled ? *compiled : preBuilt;
-    VertexShaderFn vs = (VertexShaderFn)dlsym(module.getHandle(), "userLaunchVertexShader");
-    if (!vs) fail("cube: userLaunchVertexShader not found in %s", argv[1]);
-
     Buffer inVerts(pos, sizeof(pos)), indices(idx, sizeof(idx)), shadedVerts;
     shadedVerts.resizeDiscard(8 * 32);  // sizeof(GouraudVertex)
-    if (vs(mvp, inVerts.getCudaPtr(), shadedVerts.getCudaPtr(), 8, NULL) != 0) fail("cube: vertex shader launch failed");
+    UserConstants constants;
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) constants.posToClip.m[c][r] = mvp[c * 4 + r];
+    module.launchVertexShader("vertexShader_user", inVerts, shadedVerts, 8, constants);   // test/SceneCR.cpp:263-282
 
     cr.setSurfaces(&color, &depth);
     cr.setPixelPipe(&module, "PixelPipe_user");
@@ -94,5 +94,6 @@ int main(int argc, char** argv) {
     fwrite(hd.data(), 4, hd.size(), fp);
     fwrite(hv.data(), 4, hv.size(), fp);
     fclose(fp);
+    color.resolveToFile(std::string(argv[2]) + ".ppm");   // stands in for resolveToScreen (test/SceneCR.cpp:297)
     return 0;
 }

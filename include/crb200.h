@@ -196,6 +196,26 @@ int crb_get_work_buffers(crb_ctx* ctx, crb_work_buffers* out); /* device pointer
  * `bytes` bytes of device memory (a work buffer or a surface) into host memory. */
 int crb_download(crb_ctx* ctx, const void* d_src, void* h_dst, size_t bytes);
 
+/* ---- around the hot path -------------------------------------------------------
+ * MSAA resolve: CudaSurface::resolveToScreen (CudaSurface.hpp:73, body dropped by the Linux port; the demo calls
+ * its own after drawTriangles, test/SceneCR.cpp:297).  Box filter of the numSamples samples of every pixel of a
+ * surface in the layout of crb_set_surfaces into a LINEAR image of dstPitch texels per row: per 8-bit channel
+ * (sum + N/2) >> log2 N.  flipY != 0 writes the top scanline first (image order).  Enqueued on `stream`. */
+int crb_resolve_surface(const void* d_src, int width, int height, int numSamples, void* d_dst, int dstPitch, int flipY, void* stream);
+/* Image writer for golden images / visual diffing: binary PPM (P6) of a HOST 0xAABBGGRR image, rows as given. */
+int crb_write_ppm(const char* path, const uint32_t* h_pixels, int width, int height, int pitch);
+
+/* Vertex-shader stage: the user kernel the demo launches before drawTriangles (test/shader/PassThrough.cu:16-35,
+ * test/shader/Shaders.cu:56-112, launch at test/SceneCR.cpp:263-282).  CR_DEFINE_VERTEX_SHADER (cuda/PixelPipe.inl)
+ * emits `<name>_launch` with this signature; constants (the reference's c_constants block) travel by value as a
+ * kernel argument (<= CRB_MAX_VS_CONSTANTS bytes).  The kernel is enqueued on `stream` with programmatic stream
+ * serialization, so a following crb_draw_triangles_async on the same stream starts its prologue while it drains. */
+#define CRB_MAX_VS_CONSTANTS 1024
+typedef int (*crb_vertex_shader_fn)(const void* d_inVertices, void* d_outVertices, int numVertices, const void* h_constants, size_t constantsBytes, void* stream);
+/* Resolves "<name>_launch" in `module` (NULL = libcrb200.so) and calls it. */
+int crb_launch_vertex_shader(void* module, const char* name, const void* d_inVertices, void* d_outVertices, int numVertices, const void* h_constants,
+                             size_t constantsBytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

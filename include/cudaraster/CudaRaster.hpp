@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../crb200.h"
@@ -100,6 +101,23 @@ public:
     void download(U32* dst) const {
         if (cudaMemcpy(dst, m_ptr, getSizeBytes(), cudaMemcpyDeviceToHost) != cudaSuccess) fail("CudaSurface: cudaMemcpy failed!");
     }
+    // Stand-ins for resolveToScreen (CudaSurface.hpp:73: "Resolves MSAA and writes pixels into the current GL render
+    // target"): box-filter resolve into linear device memory of getSize().x * getSize().y U32, or straight to a PPM file.
+    void resolve(void* d_dst, bool flipY = false, cudaStream_t stream = NULL) const {
+        if (crb_resolve_surface(m_ptr, m_size.x, m_size.y, m_numSamples, d_dst, m_size.x, flipY ? 1 : 0, stream) != CRB_OK) fail("CudaSurface: resolve failed!");
+    }
+    void resolveToFile(const std::string& ppmPath) const {
+        void* d = NULL;
+        const size_t bytes = (size_t)m_size.x * (size_t)m_size.y * sizeof(U32);
+        if (cudaMalloc(&d, bytes) != cudaSuccess) fail("CudaSurface: cudaMalloc failed!");
+        resolve(d, true);
+        U32* h = (U32*)malloc(bytes);
+        if (!h || cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) fail("CudaSurface: cudaMemcpy failed!");
+        cudaFree(d);
+        const int rc = crb_write_ppm(ppmPath.c_str(), h, m_size.x, m_size.y, m_size.x);
+        free(h);
+        if (rc != CRB_OK) fail("CudaSurface: cannot write '%s'!", ppmPath.c_str());
+    }
 
 private:
     CudaSurface(const CudaSurface&);             // forbidden
@@ -122,6 +140,14 @@ public:
     }
     ~CudaModule(void) { if (m_handle) dlclose(m_handle); }
     void* getHandle(void) const { return m_handle; }  // NULL = the pipes built into libcrb200.so
+
+    // The demo's vertex-shader launch (test/SceneCR.cpp:263-282: getGlobal("c_constants") + setParam* + launchKernel):
+    // runs `<name>_launch` (CR_DEFINE_VERTEX_SHADER) over numVertices vertices; the constants block travels by value.
+    template <class Constants>
+    void launchVertexShader(const std::string& name, Buffer& inVertices, Buffer& outVertices, int numVertices, const Constants& constants, cudaStream_t stream = NULL) {
+        if (crb_launch_vertex_shader(m_handle, name.c_str(), inVertices.getCudaPtr(), outVertices.getCudaPtr(), numVertices, &constants, sizeof(Constants), stream) != CRB_OK)
+            fail("CudaModule: vertex shader '%s' not found or failed to launch!", name.c_str());
+    }
 
 private:
     CudaModule(const CudaModule&);             // forbidden

@@ -68,6 +68,9 @@ __device__ __forceinline__ void setupTileEdges(const uint4& h, S32 bx, S32 by, S
     }
 }
 
+// Lanes that own the pixels of this lane's 2x2 quad: pixel (x, y & 3) of a 4-row block sits on lane x + 8*(y & 3).
+__device__ __forceinline__ U32 quadLaneMask() { return 0x303u << (laneId() & 0x16u); }
+
 // Perspective-correct barycentrics from the integer w/u/v planes (reference: FineRaster.inl:21-48).
 template <int SamplesLog2>
 __device__ __forceinline__ void computeBarys(Vec3f& bary, Vec3f& baryDX, Vec3f& baryDY, const int3& wp, const int3& up, const int3& vp, int sampleX, int sampleY) {
@@ -87,6 +90,8 @@ __device__ __forceinline__ void computeBarys(Vec3f& bary, Vec3f& baryDX, Vec3f& 
 template <class VertexClass, class FragmentShaderClass, int SamplesLog2, U32 RenderModeFlags>
 __device__ __forceinline__ void runFragmentShader(FragmentShaderClass& fs, const crb_frame& f, int triIdx, int dataIdx, int pixelX, int pixelY, U32 centroid) {
     const uint4 t3 = __ldg(&f.triData[(size_t)dataIdx * 4 + 3]);  // vb, vi0, vi1, vi2
+    // quads mode: the caller runs this converged on the four lanes of the pixel's 2x2 quad
+    fs.m_quadMask = (RenderModeFlags & RenderModeFlag_EnableQuads) != 0 ? quadLaneMask() : (1u << laneId());
     fs.m_triIdx = triIdx;
     fs.m_vertIdx = Vec3i((S32)t3.y, (S32)t3.z, (S32)t3.w);
     fs.m_pixelPos = Vec2i(pixelX, pixelY);
@@ -304,6 +309,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     __shared__ FineBatch s_batch[CRB_FINE_WARPS];
 
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
+    constexpr bool kQuads = (RenderModeFlags & RenderModeFlag_EnableQuads) != 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int activeIdx = blockIdx.x * CRB_FINE_WARPS + warp;
     gridDepLaunchDependents();
@@ -392,16 +398,26 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         const U32 cover[2] = {warpTranspose32(maskLo, lane), warpTranspose32(maskHi, lane)};
 
         // ---- (3) ownership loop, queue order
+        // Quads mode, in-order shading (reference: FineRaster.inl:396-430, :705-724): the four lanes of a 2x2
+        // quad walk the UNION of their triangle sets together, so that the shader runs converged on the quad
+        // (helper pixels included, whatever their coverage or depth) and dFdx / dFdy can shuffle.
 #pragma unroll
         for (int p = 0; p < 2; p++) {
             U32 w = cover[p];
+            if (kQuads && !deferred) {
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 8);
+            }
             while (w) {
                 const int j = __ffs(w) - 1;
                 w &= w - 1;
+                const bool covered = !(kQuads && !deferred) || ((cover[p] >> j) & 1) != 0;
                 U32 z = 0;
+                bool zkill = false;
                 if (kDepth) {
                     z = sb.zb[j] + sb.zx[j] * (U32)lx + sb.zy[j] * (U32)(ly + 4 * p);
-                    if (z >= depth[p]) continue;
+                    zkill = z >= depth[p];
+                    if (!(kQuads && !deferred) && zkill) continue;
                 }
                 if (deferred) {
                     if (kDepth) depth[p] = z;
@@ -410,7 +426,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
                     const S32 entry = sb.entry[j];
                     FragmentShaderClass fs;
                     runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, entry >> 3, sb.dataIdx[j], pixelX, pixelY0 + 4 * p, 0x11u);
-                    if (fs.m_discard) continue;
+                    if (!covered || zkill || fs.m_discard) continue;
                     if (kDepth) depth[p] = z;
                     BlendShaderClass bs;
                     runBlendShader(bs, entry >> 3, pixelX, pixelY0 + 4 * p, 0, fs.m_color, color[p]);
@@ -422,7 +438,33 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         cur = nxt;
     }
 
-    if (deferred && (winner[0] & winner[1]) >= 0) {
+    if (deferred && kQuads) {
+        // Visibility is resolved; every quad shades each DISTINCT winner of its four pixels once, on all four
+        // lanes (derivatives need the neighbours' values of the same triangle), and a lane keeps the colour
+        // of its own winner.  The shuffles that collect the winners run before any divergence.
+        S32 q[2][4];
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[p][k] = __shfl_sync(0xFFFFFFFFu, winner[p], (lane & 0x16) | (k & 1) | ((k & 2) << 2));
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const S32 e = q[p][k];
+                bool skip = e < 0;
+#pragma unroll
+                for (int kk = 0; kk < k; kk++) skip |= q[p][kk] == e;
+                if (skip) continue;   // uniform over the quad
+                FragmentShaderClass fs;
+                runFragmentShader<VertexClass, FragmentShaderClass, 0, RenderModeFlags>(fs, f, e >> 3, resolveDataIdx(e, f.triHeader), pixelX, pixelY0 + 4 * p, 0x11u);
+                if (winner[p] == e) {
+                    BlendShaderClass bs;
+                    runBlendShader(bs, e >> 3, pixelX, pixelY0 + 4 * p, 0, fs.m_color, 0u);
+                    if (bs.m_writeColor) color[p] = bs.m_color;
+                }
+            }
+    } else if (deferred && (winner[0] & winner[1]) >= 0) {
         // Shade only the visible fragment of each pixel.  Both pixels are shaded in one straight
         // line of code (a lane with a single covered pixel shades that fragment twice) so that the
         // two chains of dependent loads -- plane rows, then vertex varyings -- overlap.

@@ -48,6 +48,7 @@ struct FineBatchMSAA {
     U32 zx[32], zy[32], zb[32];
     S32 entry[32];
     S32 dataIdx[32];
+    U32 zslope[32], zminHdr[32];   // quads mode only: inputs of the reference's per-pixel conservative depth kill
 };
 
 // Same scheme as the single-sample kernel (FineRaster.cuh): lane j builds a 64-bit PIXEL mask of
@@ -60,6 +61,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
     constexpr int N = 1 << SamplesLog2;
     constexpr int kWarps = FineWarps<SamplesLog2>::Value;
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
+    constexpr bool kQuads = (RenderModeFlags & RenderModeFlag_EnableQuads) != 0;
     constexpr S32 kMaxOfs = (N - 1) << (CR_SUBPIXEL_LOG2 - SamplesLog2 - 1);   // largest |sample offset| from the pixel centre, subpixels
     __shared__ FineBatchMSAA s_batch[kWarps];
     __shared__ U32 s_depth[kWarps][N * CR_TILE_SQR];
@@ -75,7 +77,8 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
     if (activeIdx >= f.atomics->numActiveTiles) return;
 
     BlendShaderClass blendProbe;
-    const bool deferred = !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
+    // quads mode shades in order: where a helper pixel is shaded depends on the depth state at that moment (below)
+    const bool deferred = !kQuads && !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
 
     FineBatchMSAA& sb = s_batch[warp];
     U32* tDepth = s_depth[warp];
@@ -117,6 +120,9 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
     const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
     const S32 sx0 = lx << CR_SUBPIXEL_LOG2;
     const S32 sy0 = ly << CR_SUBPIXEL_LOG2;
+    // quads mode: the reference kernel's tileDepth[pixel] -- CR_DEPTH_MAX until the pixel's first ROP of this
+    // draw, then the maximum over its samples (FineRaster.inl:934-935, :1101-1108)
+    U32 pixZMax[2] = {CR_DEPTH_MAX, CR_DEPTH_MAX};
 
     for (int base = 0; base < queueCount; base += 32) {
         FineFetch nxt;
@@ -156,6 +162,10 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
         }
         sb.entry[lane] = cur.entry;
         sb.dataIdx[lane] = cur.dataIdx;
+        if (kQuads && kDepth) {
+            sb.zslope[lane] = cur.z.w;
+            sb.zminHdr[lane] = cur.h.w & 0xFFFFF000u;
+        }
         __syncwarp();
 
         // ---- (2) transpose
@@ -165,6 +175,10 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
 #pragma unroll
         for (int p = 0; p < 2; p++) {
             U32 w = cover[p];
+            if (kQuads) {   // the four lanes of a 2x2 quad walk the union of their sets together (see FineRaster.cuh)
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 8);
+            }
             const S32 sy = sy0 + p * (4 << CR_SUBPIXEL_LOG2);
             const int qBase = lane + 32 * p;
             while (w) {
@@ -173,7 +187,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
                 const S32 ea[3] = {sb.a0[j], sb.a1[j], sb.a2[j]}, eb[3] = {sb.b0[j], sb.b1[j], sb.b2[j]};
                 const S32 ec[3] = {sb.c0[j] + ea[0] * sx0 + eb[0] * sy, sb.c1[j] + ea[1] * sx0 + eb[1] * sy, sb.c2[j] + ea[2] * sx0 + eb[2] * sy};
                 const U32 cov = pixelSampleMask<SamplesLog2>(ea, eb, ec);
-                if (cov == 0) continue;
+                if (!kQuads && cov == 0) continue;
                 const U32 zxv = sb.zx[j], zyv = sb.zy[j];
                 const U32 zPix = sb.zb[j] + zxv * (U32)(lx * N) + zyv * (U32)((ly + 4 * p) * N);
                 U32 pass = 0;
@@ -183,9 +197,34 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
                     z[i] = zPix + zxv * (U32)msaaSampleX(SamplesLog2, i) + zyv * (U32)i;
                     if (((cov >> i) & 1) && (!kDepth || z[i] < tDepth[i * CR_TILE_SQR + qBase])) pass |= 1u << i;
                 }
-                if (pass == 0) continue;
+                if (!kQuads && pass == 0) continue;
                 const S32 entry = sb.entry[j];
-                if (deferred) {
+                if (kQuads) {
+                    // Reference semantics (FineRaster.inl:1034-1111): a pixel the conservative per-pixel depth test
+                    // kills has an EMPTY sample mask -- it is shaded at its centre (as a helper) and gets no ROP;
+                    // a live, covered pixel is shaded at the centroid of its mask and the ROP refreshes its bound.
+                    U32 mask = cov;
+                    if (kDepth && cov != 0) {
+                        const U32 zslope = sb.zslope[j];
+                        const U32 zmin = ((zxv + zyv) << (SamplesLog2 - 1 > 0 ? SamplesLog2 - 1 : 0)) + zPix - zslope;
+                        if ((zmin >= pixZMax[p] && zmin < zmin + zslope * 2u) || sb.zminHdr[j] >= pixZMax[p]) mask = 0;
+                    }
+                    FragmentShaderClass fs;
+                    runFragmentShader<VertexClass, FragmentShaderClass, SamplesLog2, RenderModeFlags>(fs, f, entry >> 3, sb.dataIdx[j], pixelX, pixelY0 + 4 * p, centroidCode<SamplesLog2>(mask));
+                    if (mask == 0 || fs.m_discard) continue;
+                    U32 zmaxNew = 0;
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        if ((pass >> i) & 1) {
+                            if (kDepth) tDepth[i * CR_TILE_SQR + qBase] = z[i];
+                            BlendShaderClass bs;
+                            runBlendShader(bs, entry >> 3, pixelX, pixelY0 + 4 * p, i, fs.m_color, tAux[i * CR_TILE_SQR + qBase]);
+                            if (bs.m_writeColor) tAux[i * CR_TILE_SQR + qBase] = bs.m_color;
+                        }
+                        if (kDepth) zmaxNew = max(zmaxNew, tDepth[i * CR_TILE_SQR + qBase]);
+                    }
+                    if (kDepth && zmaxNew < pixZMax[p]) pixZMax[p] = zmaxNew;
+                } else if (deferred) {
 #pragma unroll
                     for (int i = 0; i < N; i++)
                         if ((pass >> i) & 1) {
@@ -261,7 +300,6 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
 struct FineRasterLauncher {
     static int launch(const crb_frame* f, void* stream) {
-        if ((RenderModeFlags & RenderModeFlag_EnableQuads) != 0) return CRB_ERR_INVALID;
         constexpr int kWarps = FineWarps<SamplesLog2>::Value;
         const int blocks = (f->numTiles + kWarps - 1) / kWarps;
         return launchChained(fineRasterMultiKernel<VertexClass, FragmentShaderClass, BlendShaderClass, SamplesLog2, RenderModeFlags>, blocks, kWarps * 32, (cudaStream_t)stream, *f) == cudaSuccess
@@ -272,7 +310,6 @@ struct FineRasterLauncher {
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
 struct FineRasterLauncher<VertexClass, FragmentShaderClass, BlendShaderClass, 0, RenderModeFlags> {
     static int launch(const crb_frame* f, void* stream) {
-        if ((RenderModeFlags & RenderModeFlag_EnableQuads) != 0) return CRB_ERR_INVALID;
         const int blocks = (f->numTiles + CRB_FINE_WARPS - 1) / CRB_FINE_WARPS;
         return launchChained(fineRasterSingleKernel<VertexClass, FragmentShaderClass, BlendShaderClass, RenderModeFlags>, blocks, CRB_FINE_WARPS * 32, (cudaStream_t)stream, *f) == cudaSuccess
                    ? CRB_OK : CRB_ERR_CUDA;

@@ -13,7 +13,9 @@
 //                                declare `enum { CanDiscard = 0 };` which lets the fine raster
 //                                resolve visibility first and shade only the surviving fragment
 //                                of every sample (identical output, far less shading).
-// Not supported yet: RenderModeFlag_EnableQuads (dFdx/dFdy); launching such a pipe fails.
+//   RenderModeFlag_EnableQuads   dFdx / dFdy are warp shuffles between the four lanes that own the pixels of
+//                                a 2x2 quad (the reference goes through a shared-memory scratch row,
+//                                cuda/PixelPipe.hpp:59-69); like there, they are only valid in quads mode.
 #pragma once
 #include "Util.cuh"
 
@@ -22,7 +24,7 @@ namespace FW {
 enum {
     RenderModeFlag_EnableDepth = 1 << 0,  // depth test + depth write
     RenderModeFlag_EnableLerp = 1 << 1,   // varying interpolation
-    RenderModeFlag_EnableQuads = 1 << 2,  // numerical derivatives (unsupported here)
+    RenderModeFlag_EnableQuads = 1 << 2,  // numerical derivatives in the fragment shader (dFdx / dFdy); degrades performance
 };
 
 // Vertex layout: clipPos first, then one Vec4f per varying and nothing else.
@@ -47,11 +49,31 @@ public:
         return Vec4f(__fmaf_rn(c.x, bary.z, __fmaf_rn(a.x, bary.x, __fmul_rn(b.x, bary.y))), __fmaf_rn(c.y, bary.z, __fmaf_rn(a.y, bary.x, __fmul_rn(b.y, bary.y))),
                      __fmaf_rn(c.z, bary.z, __fmaf_rn(a.z, bary.x, __fmul_rn(b.z, bary.y))), __fmaf_rn(c.w, bary.z, __fmaf_rn(a.w, bary.x, __fmul_rn(b.w, bary.y))));
     }
+    // Numerical derivatives (only valid when RenderModeFlag_EnableQuads is set; reference: cuda/PixelPipe.hpp:59-69).
+    // In quads mode the shader runs converged on the four lanes that own the pixels of a 2x2 quad -- pixel
+    // (x, y) of the tile row block sits on lane x + 8*(y & 3) -- so the neighbours are lanes ^1 and ^8.
+    __device__ __forceinline__ F32 dFdx(F32 v) const {
+        const int l = (int)(threadIdx.x & 31);
+        const F32 hi = __shfl_sync(m_quadMask, v, l | 1), lo = __shfl_sync(m_quadMask, v, l & ~1);
+        return __fsub_rn(hi, lo);
+    }
+    __device__ __forceinline__ F32 dFdy(F32 v) const {
+        const int l = (int)(threadIdx.x & 31);
+        const F32 hi = __shfl_sync(m_quadMask, v, l | 8), lo = __shfl_sync(m_quadMask, v, l & ~8);
+        return __fsub_rn(hi, lo);
+    }
+    __device__ __forceinline__ Vec2f dFdx(const Vec2f& v) const { return Vec2f(dFdx(v.x), dFdx(v.y)); }
+    __device__ __forceinline__ Vec2f dFdy(const Vec2f& v) const { return Vec2f(dFdy(v.x), dFdy(v.y)); }
+    __device__ __forceinline__ Vec3f dFdx(const Vec3f& v) const { return Vec3f(dFdx(v.x), dFdx(v.y), dFdx(v.z)); }
+    __device__ __forceinline__ Vec3f dFdy(const Vec3f& v) const { return Vec3f(dFdy(v.x), dFdy(v.y), dFdy(v.z)); }
+    __device__ __forceinline__ Vec4f dFdx(const Vec4f& v) const { return Vec4f(dFdx(v.x), dFdx(v.y), dFdx(v.z), dFdx(v.w)); }
+    __device__ __forceinline__ Vec4f dFdy(const Vec4f& v) const { return Vec4f(dFdy(v.x), dFdy(v.y), dFdy(v.z), dFdy(v.w)); }
     __device__ __forceinline__ void run(void) {}
 #endif
 
 public:
     // Inputs.
+    U32 m_quadMask;      // lanes of this fragment's 2x2 quad (quads mode), else this lane only
     S32 m_triIdx;        // input triangle index
     Vec3i m_vertIdx;     // its three vertex indices
     Vec2i m_pixelPos;    // integer pixel position

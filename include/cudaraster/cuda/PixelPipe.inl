@@ -10,6 +10,7 @@
 // instantiated for the pipe's vertex / shader classes; binRaster and coarseRaster do not depend
 // on the pipe and forward to the kernels inside libcrb200.so.
 #pragma once
+#include <cstring>
 #include "PixelPipe.hpp"
 #include "TriangleSetup.cuh"
 #include "FineRaster.cuh"
@@ -38,3 +39,46 @@ extern "C" int crb_launch_coarse_raster(const crb_frame* frame, void* stream);
         /* profilingMode */ CR_PROFILING_MODE,                                                                                              \
         /* blendShaderName */ #BLEND_SHADER,                                                                                                \
     };
+
+// Vertex-shader stage (reference: the user kernel of test/shader/PassThrough.cu:16-35 and its launch,
+// test/SceneCR.cpp:263-282).  SHADER is a functor type with
+//     __device__ void operator()(const INPUT_VERTEX& in, SHADED_VERTEX& out, const CONSTANTS& c, int vertexIdx) const;
+// The macro emits the kernel (one thread per vertex, 128-thread CTAs like the reference's 32x4 blocks) and
+// `NAME_launch` (crb_vertex_shader_fn, include/crb200.h), found by name like the pipe's stage launchers.
+namespace FW {
+template <class InputVertex, class ShadedVertex, class Constants, class Shader>
+static __global__ void __launch_bounds__(128) vertexShaderKernel(const InputVertex* __restrict__ in, ShadedVertex* __restrict__ out, int numVertices, const __grid_constant__ Constants c) {
+    gridDepLaunchDependents();
+    gridDepWait();   // frames in flight may still read the output buffer
+    const int v = blockIdx.x * 128 + threadIdx.x;
+    if (v >= numVertices) return;
+    ShadedVertex o;
+    Shader()(in[v], o, c, v);
+    out[v] = o;
+}
+
+template <class InputVertex, class ShadedVertex, class Constants, class Shader>
+inline int launchVertexShader(const void* in, void* out, int numVertices, const void* constants, size_t constantsBytes, void* stream) {
+    static_assert(sizeof(Constants) <= CRB_MAX_VS_CONSTANTS, "vertex shader constants must fit a kernel argument");
+    if (numVertices <= 0) return CRB_OK;
+    if (!in || !out || !constants || constantsBytes != sizeof(Constants)) return CRB_ERR_INVALID;
+    Constants c;
+    memcpy(&c, constants, sizeof(Constants));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((numVertices + 127) / 128));
+    cfg.blockDim = dim3(128);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, vertexShaderKernel<InputVertex, ShadedVertex, Constants, Shader>, (const InputVertex*)in, (ShadedVertex*)out, numVertices, c) == cudaSuccess ? CRB_OK
+                                                                                                                                                                                 : CRB_ERR_CUDA;
+}
+}  // namespace FW
+
+#define CR_DEFINE_VERTEX_SHADER(NAME, INPUT_VERTEX, SHADED_VERTEX, CONSTANTS, SHADER)                                                                    \
+    extern "C" int NAME##_launch(const void* in, void* out, int numVertices, const void* constants, size_t constantsBytes, void* stream) {               \
+        return FW::launchVertexShader<INPUT_VERTEX, SHADED_VERTEX, CONSTANTS, SHADER>(in, out, numVertices, constants, constantsBytes, stream);          \
+    }

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 FLAG_DEPTH, FLAG_LERP, FLAG_QUADS = 1, 2, 4
-SHADER = {"passthrough": 0, "gouraud": 1, "texPhong": 2, "gouraudDiscard": 3}
+SHADER = {"passthrough": 0, "gouraud": 1, "texPhong": 2, "gouraudDiscard": 3, "gouraudQuads": 4}
 BLEND = {"BlendReplace": 0, "BlendSrcOver": 1, "BlendAdditive": 2, "BlendDepthOnly": 3}
 
 
@@ -66,6 +66,8 @@ def lib():
         L.gold_render.argtypes = [ctypes.POINTER(Config), vp, vp, ctypes.c_int, vp, vp, ctypes.POINTER(Counts)]
         L.gold_time_render.restype = ctypes.c_double
         L.gold_time_render.argtypes = [ctypes.POINTER(Config), vp, vp, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.gold_resolve.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int]
+        L.gold_vertex_shader.argtypes = [vp, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int]
         assert L.gold_sizeof_config() == ctypes.sizeof(Config), "Config layout mismatch"
         assert L.gold_sizeof_counts() == ctypes.sizeof(Counts), "Counts layout mismatch"
     return _LIB
@@ -167,6 +169,23 @@ def time_render(cfg, verts, idx, reps=3):
     color = np.zeros((rh, rw * n_s), np.uint32)
     depth = np.zeros((rh, rw * n_s), np.uint32)
     return L.gold_time_render(ctypes.byref(cfg), verts.ctypes.data, idx.ctypes.data, idx.shape[0], color.ctypes.data, depth.ctypes.data, reps)
+
+
+def resolve(surface, width, height, num_samples, flip_y=False):
+    """Box-filter resolve of a [roundedH, roundedW*N] U32 surface into a [height, width] image."""
+    src = np.ascontiguousarray(surface, np.uint32)
+    dst = np.zeros((height, width), np.uint32)
+    lib().gold_resolve(src.ctypes.data, width, height, num_samples, dst.ctypes.data, width, 1 if flip_y else 0)
+    return dst
+
+
+def vertex_shader(matrix_colmajor, in_verts, out_stride_floats):
+    """clipPos = M * (modelPos, 1); input floats 3.. are carried through behind clipPos."""
+    m = np.ascontiguousarray(matrix_colmajor, np.float32).reshape(16)
+    vin = np.ascontiguousarray(in_verts, np.float32)
+    out = np.zeros((vin.shape[0], out_stride_floats), np.float32)
+    lib().gold_vertex_shader(m.ctypes.data, vin.ctypes.data, vin.shape[1], out.ctypes.data, out_stride_floats, vin.shape[0])
+    return out
 
 
 def hardware_threads():

@@ -52,7 +52,7 @@ static const U32 kDepthMax = 0xFFFFFFFFu - (2200u << 3);
 static const S32 kBaryMax = (1 << (30 - kSubpixelLog2)) - 1;
 
 enum { kFlagDepth = 1, kFlagLerp = 2, kFlagQuads = 4 };
-enum { kShaderConstant = 0, kShaderGouraud = 1, kShaderPhongProc = 2, kShaderGouraudDiscard = 3 };
+enum { kShaderConstant = 0, kShaderGouraud = 1, kShaderPhongProc = 2, kShaderGouraudDiscard = 3, kShaderGouraudQuads = 4 };
 enum { kBlendReplace = 0, kBlendSrcOver = 1, kBlendAdditive = 2, kBlendDepthOnly = 3 };
 
 struct TriHeader {  // 16 B
@@ -653,6 +653,47 @@ static inline bool runShader(const Config& c, const void* verts, const TriData& 
     return true;
 }
 
+// RenderModeFlag_EnableQuads (cuda/PixelPipe.hpp:34, :59-69; cuda/FineRaster.inl:396-430, :705-724,
+// :1055-1090): the shader runs on all four pixels of every 2x2 quad that holds a fragment, and
+// dFdx(v) = v(x|1) - v(x&~1), dFdy(v) = v(y|1) - v(y&~1) inside the quad.  Each quad pixel is shaded at
+// ITS OWN shading point (codes[k], k = (x&1) + 2*(y&1)): the pixel centre when single-sampled, the
+// centroid of its own sample mask under MSAA (centre when that mask is empty).
+// Test shader "gouraudQuads": colour = (8|dFdx c.r| + 8|dFdy c.r|, 8|dFdx c.g| + 8|dFdy c.g|, c.b, c.a).
+static inline bool runShaderQuads(const Config& c, const void* verts, const TriData& d, int px, int py, const U32* codes, U32& color) {
+    const int S = c.samplesLog2;
+    F32 v[4][4];
+    for (int k = 0; k < 4; k++) {
+        const int qx = (px & ~1) + (k & 1), qy = (py & ~1) + (k >> 1);
+        Bary b = {0.0f, 0.0f, 1.0f};
+        if (c.flags & kFlagLerp) {
+            if (S == 0) b = computeBary(d, qx * 2 + 1, qy * 2 + 1);
+            else b = computeBary(d, (qx << (S + 1)) + (S32)(codes[k] & 0xF), (qy << (S + 1)) + (S32)(codes[k] >> 4));
+        }
+        lerpVarying(v[k], verts, c.vertexStride, d, 0, b);
+    }
+    const int own = (px & 1) + 2 * (py & 1), row = own & 2, col = own & 1;
+    F32 dx[2], dy[2];
+    for (int i = 0; i < 2; i++) {
+        dx[i] = v[row + 1][i] - v[row][i];
+        dy[i] = v[2 + col][i] - v[col][i];
+    }
+    color = toABGR(fmaf(std::fabs(dy[0]), 8.0f, std::fabs(dx[0]) * 8.0f), fmaf(std::fabs(dy[1]), 8.0f, std::fabs(dx[1]) * 8.0f), v[own][2], v[own][3]);
+    return true;
+}
+
+// The multi-sample kernel's per-pixel conservative depth kill (cuda/FineRaster.inl:1034-1068), needed only
+// because in quads mode a killed HELPER pixel is shaded at its centre instead of its centroid.
+// pixZMax = the kernel's tileDepth[pixel]: CR_DEPTH_MAX until the pixel's first ROP of this draw, then the
+// maximum over its samples (FineRaster.inl:934-935, :1101-1108).
+static inline bool msaaPixelZKill(const Config& c, const TriHeader& h, const TriData& d, int px, int py, U32 pixZMax) {
+    if (!(c.flags & kFlagDepth)) return false;
+    const int S = c.samplesLog2;
+    const U32 zbase = ((d.zx * (U32)px + d.zy * (U32)py) << S) + d.zb;
+    const U32 zmin = ((d.zx + d.zy) << std::max(S - 1, 0)) + zbase - d.zslope;
+    if (zmin >= pixZMax && zmin < zmin + d.zslope * 2u) return true;
+    return (h.misc & 0xFFFFF000u) >= pixZMax;
+}
+
 static inline U32 centroidCode(int S, U32 sampleMask) {  // FineRaster.inl:151-164
     int y = msaaCentroid(S, sampleMask);
     if (y < 0) return 0x11u << S;
@@ -661,7 +702,7 @@ static inline U32 centroidCode(int S, U32 sampleMask) {  // FineRaster.inl:151-1
 
 // ---- fine raster: the serial rule -----------------------------------------------
 // Surfaces: U32 [roundedH][roundedW * N]; sample i of pixel (x,y) at column (x>>3)*8*N + i*8 + (x&7).
-struct Surface { U32* color; U32* depth; S32 roundedW, roundedH, pitch; };
+struct Surface { U32* color; U32* depth; S32 roundedW, roundedH, pitch; U32* pixZMax; };   // pixZMax: [roundedH][roundedW], MSAA + quads only
 
 static inline size_t texelIndex(const Surface& s, int N, int x, int y, int sample) {
     return (size_t)y * s.pitch + (size_t)(x >> 3) * 8 * N + (size_t)sample * 8 + (x & 7);
@@ -684,10 +725,29 @@ static inline void rasterTriangle(const Config& c, const void* verts, const TriH
     for (int ty = ty0; ty <= ty1; ty++)
         for (int tx = tx0; tx <= tx1; tx++) {
             bool anyCov = false, anyWritten = false;
-            for (int iy = 0; iy < 8; iy++)
-                for (int ix = 0; ix < 8; ix++) {
-                    int px = tx * 8 + ix, py = ty * 8 + iy;
-                    U32 mask = coverPixelSamples(c, e, px, py);
+            // MSAA + quads: the reference's per-pixel conservative kill decides whether the shader/ROP pair
+            // runs at all, and the ROP refreshes the pixel's bound even when no sample survives
+            const bool quadsMsaa = (c.flags & kFlagQuads) != 0 && S > 0;
+            for (int q = 0; q < 16; q++) {   // the 2x2 quads of the tile; pixels are independent of each other
+                const int qx0 = tx * 8 + (q & 3) * 2, qy0 = ty * 8 + (q >> 2) * 2;
+                U32 masks[4], codes[4];
+                bool kill[4] = {false, false, false, false};
+                bool any = false;
+                for (int k = 0; k < 4; k++) {
+                    masks[k] = coverPixelSamples(c, e, qx0 + (k & 1), qy0 + (k >> 1));
+                    any |= masks[k] != 0;
+                }
+                if (!any) continue;
+                // quads mode: the four pixels of a quad are shaded TOGETHER, each at its own shading point, from
+                // the state the quad had before this triangle (the four lanes run in lock step in the reference)
+                for (int k = 0; k < 4; k++) {
+                    if (quadsMsaa && masks[k] != 0)
+                        kill[k] = msaaPixelZKill(c, h, d, qx0 + (k & 1), qy0 + (k >> 1), s.pixZMax[(size_t)(qy0 + (k >> 1)) * s.roundedW + qx0 + (k & 1)]);
+                    codes[k] = centroidCode(S, kill[k] ? 0u : masks[k]);
+                }
+                for (int k = 0; k < 4; k++) {
+                    const int px = qx0 + (k & 1), py = qy0 + (k >> 1);
+                    const U32 mask = masks[k];
                     if (!mask) continue;
                     anyCov = true;
                     if (cnt) cnt->fragments++;
@@ -705,11 +765,17 @@ static inline void rasterTriangle(const Config& c, const void* verts, const TriH
                     }
                     // (the reference shades whenever sampleMask != 0; shading has no side effects,
                     //  so skipping it when no sample survives is unobservable)
-                    if (!pass) continue;
+                    if (!pass && !quadsMsaa) continue;
+                    if (kill[k]) continue;
                     U32 color;
-                    if (!runShader(c, verts, d, triIdx, px, py, centroidCode(S, mask), color)) continue;
-                    anyWritten = true;
-                    if (cnt) cnt->fragmentsWritten++;
+                    if (c.flags & kFlagQuads) {
+                        if (c.shader == kShaderGouraudQuads) runShaderQuads(c, verts, d, px, py, codes, color);
+                        else if (!runShader(c, verts, d, triIdx, px, py, codes[k], color)) continue;
+                    } else if (!runShader(c, verts, d, triIdx, px, py, centroidCode(S, mask), color)) continue;
+                    if (pass) {
+                        anyWritten = true;
+                        if (cnt) cnt->fragmentsWritten++;
+                    }
                     for (int i = 0; i < N; i++) {
                         if (!(pass >> i & 1)) continue;
                         size_t t = texelIndex(s, N, px, py, i);
@@ -717,9 +783,43 @@ static inline void rasterTriangle(const Config& c, const void* verts, const TriH
                         U32 out;
                         if (runBlend(c.blend, color, s.color[t], out)) s.color[t] = out;
                     }
+                    if (quadsMsaa && (c.flags & kFlagDepth)) {   // the ROP ran on this pixel: its conservative bound becomes exact
+                        U32 m = 0;
+                        for (int i = 0; i < N; i++) m = std::max(m, s.depth[texelIndex(s, N, px, py, i)]);
+                        U32& z = s.pixZMax[(size_t)py * s.roundedW + px];
+                        if (m < z) z = m;
+                    }
                 }
+            }
             if (cnt) cnt->eCov += anyCov, cnt->eShade += anyWritten;
         }
+}
+
+// ---- around the hot path ---------------------------------------------------------
+// MSAA resolve (CudaSurface::resolveToScreen, CudaSurface.hpp:73 -- the Linux port dropped its body, so this
+// row is "parity unpinned": box filter, per 8-bit channel (sum of the N samples + N/2) >> log2 N).
+static inline void resolveSurface(const U32* src, int width, int height, int N, U32* dst, int dstPitch, bool flipY) {
+    const int roundedW = (width + 7) & ~7;
+    int L = 0;
+    while ((1 << L) < N) L++;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            U32 sum[4] = {0, 0, 0, 0};
+            for (int i = 0; i < N; i++) {
+                const U32 t = src[(size_t)y * roundedW * N + (size_t)(x >> 3) * 8 * N + (size_t)i * 8 + (x & 7)];
+                for (int ch = 0; ch < 4; ch++) sum[ch] += (t >> (8 * ch)) & 0xFF;
+            }
+            U32 out = 0;
+            for (int ch = 0; ch < 4; ch++) out |= (((sum[ch] + (U32)(N >> 1)) >> L) & 0xFF) << (8 * ch);
+            dst[(size_t)(flipY ? height - 1 - y : y) * dstPitch + x] = out;
+        }
+}
+
+// Vertex-shader stage: clipPos = posToClip * (modelPos, 1) (test/shader/PassThrough.cu:31-34) with the product
+// evaluated as the fma chain nvcc contracts framework/base/Math.hpp's generic Matrix::operator* into
+// (r[i] += m(i,j) * v[j], j ascending).  m is column-major: m[col*4 + row].
+static inline void transformPoint(const F32* m, const F32* p, F32* out) {
+    for (int r = 0; r < 4; r++) out[r] = fmaf(m[12 + r], 1.0f, fmaf(m[8 + r], p[2], fmaf(m[4 + r], p[1], m[r] * p[0])));
 }
 
 // Sub-triangle index list in submission order (what the bin/tile queues carry: tri*8 + sub|7).
@@ -731,6 +831,12 @@ static inline S32 renderFrame(const Config& c, const void* verts, const S32* ind
     s.color = color; s.depth = depth;
     s.roundedW = (c.width + 7) & ~7; s.roundedH = (c.height + 7) & ~7;
     s.pitch = s.roundedW * N;
+    std::vector<U32> pixZMax;
+    s.pixZMax = nullptr;
+    if ((c.flags & kFlagQuads) && c.samplesLog2 > 0) {
+        pixZMax.assign((size_t)s.roundedW * s.roundedH, kDepthMax);
+        s.pixZMax = pixZMax.data();
+    }
 
     std::vector<U8> subtris((size_t)std::max(numTris, 1));
     std::vector<TriHeader> hdr;

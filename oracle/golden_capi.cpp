@@ -7,7 +7,7 @@ using namespace gold;
 
 extern "C" {
 
-int gold_abi_version(void) { return 5; }
+int gold_abi_version(void) { return 6; }
 int gold_sizeof_config(void) { return (int)sizeof(Config); }
 int gold_sizeof_counts(void) { return (int)sizeof(Counts); }
 
@@ -91,6 +91,19 @@ double gold_time_render(const Config* c, const void* verts, const int* indices, 
     }
     std::sort(t.begin(), t.end());
     return t[t.size() / 2];
+}
+
+void gold_resolve(const unsigned* src, int width, int height, int numSamples, unsigned* dst, int dstPitch, int flipY) {
+    resolveSurface(src, width, height, numSamples, dst, dstPitch, flipY != 0);
+}
+
+// vertex shader of the demo: in = numVertices x inStrideFloats floats (modelPos first), out = numVertices x outStrideFloats floats
+// (clipPos first); floats 3.. of the input are copied behind clipPos (the "colour carried through" variant)
+void gold_vertex_shader(const float* matrix, const float* in, int inStrideFloats, float* out, int outStrideFloats, int numVertices) {
+    for (int v = 0; v < numVertices; v++) {
+        transformPoint(matrix, in + (size_t)v * inStrideFloats, out + (size_t)v * outStrideFloats);
+        for (int k = 4; k < outStrideFloats; k++) out[(size_t)v * outStrideFloats + k] = (k - 1 < inStrideFloats) ? in[(size_t)v * inStrideFloats + k - 1] : 0.0f;
+    }
 }
 
 int gold_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }

@@ -22,6 +22,8 @@ def test_cpp_cube_with_user_pipe_module(tmp_path):
     r = subprocess.run([exe, mod, out, str(w), str(h)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "triangleSetup" in r.stdout and "fine =" in r.stdout
+    ppm = open(out + ".ppm", "rb").read()       # CudaSurface::resolveToFile (stand-in for resolveToScreen)
+    assert ppm.startswith(b"P6\n%d %d\n255\n" % (w, h)) and len(ppm) == len(b"P6\n%d %d\n255\n" % (w, h)) + w * h * 3
     raw = np.fromfile(out, np.uint32)
     tw, th = int(raw[0]), int(raw[1])
     assert (tw, th) == (w, h)

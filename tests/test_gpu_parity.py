@@ -256,3 +256,84 @@ def test_back_to_back_frames_of_different_shape(raster, crb):
                 i = i[:0]
             cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, s_log2)
             _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, s_log2), lsb=1)
+
+
+@pytest.mark.parametrize("shader,flags,samples_log2,blend", [
+    ("gouraudQuads", 7, 0, "BlendReplace"),    # visibility first, then every quad shades its distinct winners
+    ("gouraudQuads", 7, 0, "BlendSrcOver"),    # in-order shading on converged quads, helper lanes included
+    ("gouraudQuads", 6, 0, "BlendSrcOver"),    # no depth test
+    ("gouraudQuads", 7, 2, "BlendReplace"),    # MSAA: helper pixels shaded at the centroid of their own mask
+    ("gouraudQuads", 7, 1, "BlendSrcOver"),
+    ("gouraudDiscard", 7, 0, "BlendReplace")])  # a discarding shader: discarded lanes keep helping
+def test_quads_mode(raster, crb, shader, flags, samples_log2, blend):
+    """RenderModeFlag_EnableQuads (reference: cuda/PixelPipe.hpp:34, :59-69, FineRaster.inl:396-430, :705-724,
+    :1055-1090): dFdx / dFdy inside 2x2 quads, shader run on helper pixels, ROP only where covered."""
+    w, h = 256, 192
+    for seed, size in ((515, 0.5), (516, 0.08)):
+        v, i = crb.scenes.random_soup(4000, seed=seed, stride_floats=8, size=size)
+        v[:, 7] = np.random.default_rng(3).uniform(0.2, 1.0, v.shape[0]).astype(np.float32)  # alpha
+        cc, cd = util.draw_cuda(raster, crb, v, i, w, h, shader, flags, samples_log2, blend)
+        g = util.draw_gold(v, i, w, h, shader, flags, samples_log2, blend)
+        _check_surfaces(cc, cd, g, lsb=1)
+    if shader == "gouraudQuads":
+        assert len(np.unique(cc & 0xFFFF)) > 50, "derivative channels look constant"
+
+
+@pytest.mark.parametrize("samples_log2", [0, 1, 2, 3])
+def test_msaa_resolve_matches_oracle(raster, crb, gold, samples_log2, tmp_path):
+    """crb_resolve_surface (CudaSurface::resolveToScreen, CudaSurface.hpp:73): box filter over the tile-replicated
+    sample layout, bit-exact against the oracle, odd sizes included; PPM writer round trip."""
+    n = 1 << samples_log2
+    for w, h in ((322, 201), (64, 8)):
+        v, i = crb.scenes.random_soup(3000, seed=21 + samples_log2, stride_floats=8, size=0.4)
+        color = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, n)
+        depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32, n)
+        import torch
+        vb, ib = torch.from_numpy(v).cuda(), torch.from_numpy(i).cuda()
+        raster.setSurfaces(color, depth)
+        raster.setPixelPipe(None, crb.pipe_name("gouraud", samples_log2, 3))
+        raster.setVertexBuffer(vb, 0)
+        raster.setIndexBuffer(ib, 0, i.shape[0])
+        raster.setSubViewport(0, 0, 0, 0)
+        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+        raster.drawTriangles()
+        for flip in (False, True):
+            got = color.resolve(flip_y=flip).cpu().numpy().view(np.uint32)
+            want = gold.resolve(color.numpy(), w, h, n, flip_y=flip)
+            assert np.array_equal(got, want)
+    path = str(tmp_path / "frame.ppm")
+    color.writePPM(path)
+    raw = open(path, "rb").read()
+    head = b"P6\n%d %d\n255\n" % (w, h)
+    assert raw.startswith(head) and len(raw) == len(head) + w * h * 3
+    img = np.frombuffer(raw[len(head):], np.uint8).reshape(h, w, 3)
+    want = gold.resolve(color.numpy(), w, h, n, flip_y=True)
+    assert np.array_equal(img[..., 0], want & 0xFF) and np.array_equal(img[..., 2], (want >> 16) & 0xFF)
+
+
+def test_vertex_shader_stage_then_draw(raster, crb, gold):
+    """The demo's frame (test/SceneCR.cpp:263-297): vertex shader kernel -> drawTriangles on the same stream.
+    Shaded vertices bit-exact against the oracle's restatement, then the frame against the oracle."""
+    import torch
+    rng = np.random.default_rng(5)
+    nv, nt, w, h = 5000, 9000, 400, 300
+    vin = np.zeros((nv, 7), np.float32)
+    vin[:, 0:3] = rng.uniform(-1.5, 1.5, (nv, 3))
+    vin[:, 3:7] = rng.uniform(0, 1, (nv, 4))
+    idx = rng.integers(0, nv, (nt, 3)).astype(np.int32)
+    idx[:, 1] = (idx[:, 0] + rng.integers(1, 40, nt)) % nv
+    idx[:, 2] = (idx[:, 0] + rng.integers(1, 40, nt)) % nv
+    m = crb.scenes.cube_mvp(w, h)            # column-major 4x4, perspective * lookAt of the demo camera
+    d_in = torch.from_numpy(vin).cuda()
+    d_out = torch.zeros((nv, 8), dtype=torch.float32, device="cuda")
+    raster.launchVertexShader(None, "vertexShader_color", d_in, d_out, nv, np.ascontiguousarray(m, np.float32).tobytes())
+    want = gold.vertex_shader(m, vin, 8)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    cc, cd = util.draw_cuda(raster, crb, want, idx, w, h, "gouraud", 3)
+    g = util.draw_gold(want, idx, w, h, "gouraud", 3)
+    _check_surfaces(cc, cd, g, lsb=1)
+    # pass-through variant: positions only (test/shader/PassThrough.cu:16-35)
+    d_in2 = torch.from_numpy(np.ascontiguousarray(vin[:, 0:3])).cuda()
+    d_out2 = torch.zeros((nv, 4), dtype=torch.float32, device="cuda")
+    raster.launchVertexShader(None, "vertexShader_passthrough", d_in2, d_out2, nv, np.ascontiguousarray(m, np.float32).tobytes())
+    assert np.array_equal(d_out2.cpu().numpy().view(np.uint32), gold.vertex_shader(m, vin[:, 0:3], 4).view(np.uint32))
