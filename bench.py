@@ -249,6 +249,7 @@ def main():
         gatherer.finish()
     sync_all()
     launches_per_frame = raster.getLaunchCount()
+    direct = raster.lastFrameDirect()   # automatic binning mode: small-triangle frames of an order-independent pipe skip the bin / coarse sort
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -331,6 +332,8 @@ def main():
             "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "frames_per_s": world * 1e3 / ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
             "config": {"workload": desc, "triangles": int(n_tris), "resolution": [w, h], "samples": n_samples, "pipe": crb.pipe_name(shader, s_log2, flags, "BlendReplace"),
+                       "binning": ("direct tile path: setup counts tiles -> queue allocation (timed as binRaster) -> unordered atomic scatter (timed as coarseRaster) -> fine raster keeps the (depth, index) minimum"
+                                   if direct else "general path: stable two-level sort (bin raster, coarse raster), queues in submission order"),
                        "sharding": "1 GPU" if world == 1 else "view-parallel: 1 view per rank per step; every step's colour frames are gathered to rank 0 over NCCL inside the timed region (side stream, overlapped with the next frame's rendering)",
                        "l2": "inputs rotate over %d device copies (%.0f MB) and each frame rewrites ~100 MB of intermediates, > 126 MB L2" %
                              (NUM_INPUT_COPIES, NUM_INPUT_COPIES * (verts.nbytes + idx.nbytes) / 1e6)},

@@ -25,7 +25,7 @@ class _PipeSpec(ctypes.Structure):
 class Atomics(ctypes.Structure):
     _fields_ = [("numSubtris", ctypes.c_int32), ("numBinEntries", ctypes.c_int32), ("numCoarseItems", ctypes.c_int32),
                 ("numTileEntries", ctypes.c_int32), ("numActiveTiles", ctypes.c_int32), ("overflow", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 2)]
+                ("numLargeTris", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class WorkBuffers(ctypes.Structure):
@@ -87,6 +87,8 @@ def load_library():
         "crb_get_launch_count": (i32, [vp]),
         "crb_get_work_buffers": (i32, [vp, ctypes.POINTER(WorkBuffers)]),
         "crb_download": (i32, [vp, vp, vp, ctypes.c_size_t]),
+        "crb_set_binning_mode": (i32, [vp, i32]),
+        "crb_get_last_frame_direct": (i32, [vp]),
         "crb_resolve_surface": (i32, [vp, i32, i32, i32, vp, i32, i32, vp]),
         "crb_write_ppm": (i32, [ctypes.c_char_p, vp, i32, i32, i32]),
         "crb_launch_vertex_shader": (i32, [vp, ctypes.c_char_p, vp, vp, i32, vp, ctypes.c_size_t, vp]),
@@ -103,7 +105,7 @@ EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_er
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
                     "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
-                    "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
+                    "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
 def pipe_name(base, samples_log2, flags, blend="BlendReplace"):
@@ -248,6 +250,13 @@ class CudaRaster:
     def setIndexBuffer(self, buf, ofs, num_tris):
         self._keep["ib"] = buf
         self._check(self.lib.crb_set_index_buffer(self.ctx, buf.data_ptr() + ofs, int(num_tris)))
+
+    def setBinningMode(self, mode):
+        """0 = general path only, 1 = automatic (default), 2 = try the direct tile path on every eligible frame."""
+        self._check(self.lib.crb_set_binning_mode(self.ctx, int(mode)))
+
+    def lastFrameDirect(self):
+        return bool(self.lib.crb_get_last_frame_direct(self.ctx))
 
     def setSubViewport(self, full_w, full_h, x0, y0):
         self._check(self.lib.crb_set_subviewport(self.ctx, full_w, full_h, x0, y0))

@@ -20,6 +20,8 @@
 
 extern "C" int crb_bin_launches(const crb_frame* f);
 extern "C" int crb_coarse_launches(const crb_frame* f);
+extern "C" int crb_launch_direct_alloc(const crb_frame* f, void* stream);
+extern "C" int crb_launch_direct_scatter(const crb_frame* f, void* stream);
 
 namespace {
 
@@ -74,6 +76,17 @@ struct crb_ctx {
     DevBuf binCountMat, binStart, binTotal, binQueue;
     DevBuf items, binItemBase, binItemCount, tileCountMat;
     DevBuf tileQueue, tileStart, tileCount, activeTiles, activeRecs;
+    DevBuf tileCounter;                  // direct tile path: per-tile counters, zero between frames
+    DevBuf tileCursor;                   // direct tile path: per-tile queue cursors (alloc -> scatter)
+    DevBuf triTileCode;                  // direct tile path: one word per input triangle (setup -> scatter)
+    // Binning strategy (crb_set_binning_mode): the direct path runs when the pipe is order independent and the last
+    // completed frame of the same SHAPE (triangle count, surface, window, pipe) reported no large triangle.
+    int binningMode = 1;                 // 0 never, 1 automatic, 2 try on every eligible frame
+    bool shapeValid = false;
+    unsigned long long shapeHash = 0;    // shape of the frame shapeNumLarge was measured on
+    int shapeNumLarge = 0;
+    unsigned long long pendingShape[64] = {};
+    bool lastFrameDirect = false;
     DevBuf atomics;
     crb_atomics* hostAtomics = nullptr;  // pinned; slot 0 = synchronous draws, slots 1.. = ring of asynchronous frames
     int pending = 0;                     // asynchronous frames not yet checked by crb_finish
@@ -134,6 +147,28 @@ int cudaFail(crb_ctx* c, const char* what, cudaError_t e) { return setError(c, C
 constexpr int kAsyncRing = 64;
 
 int popc8(int v) { return __builtin_popcount((unsigned)v & 0xFF); }
+
+// What the direct-path decision is keyed on: a frame of the same shape as one that had no large triangle.
+unsigned long long frameShape(const crb_ctx* c) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
+    mix((unsigned)c->numTris); mix((unsigned)c->width); mix((unsigned)c->height); mix((unsigned)c->samplesLog2);
+    mix((unsigned)c->fullWidth); mix((unsigned)c->fullHeight); mix((unsigned)c->subX0); mix((unsigned)c->subY0);
+    for (char ch : c->pipeName) mix((unsigned char)ch);
+    return h;
+}
+
+bool wantDirect(const crb_ctx* c) {
+    if (c->binningMode == 0 || !c->hasPipe || !c->pipe.orderIndependent) return false;
+    if (c->binningMode == 2) return true;
+    return c->shapeValid && c->shapeHash == frameShape(c) && c->shapeNumLarge == 0;
+}
+
+// Book-keeping after the counters of a completed frame came back.
+void noteFrameCounters(crb_ctx* c, unsigned long long shape, const crb_atomics& a) {
+    if (a.overflow != 0) return;
+    c->shapeValid = true; c->shapeHash = shape; c->shapeNumLarge = a.numLargeTris;
+}
 
 // Fills the frame block and (re)allocates the work buffers for the current capacities.
 int prepareFrame(crb_ctx* c) {
@@ -213,6 +248,7 @@ int prepareFrame(crb_ctx* c) {
     f.maxBinEntries = c->maxBinEntries;
     f.maxTileEntries = c->maxTileEntries;
     f.maxItems = c->maxItems;
+    f.directMode = wantDirect(c) ? 1 : 0;
     f.numSMs = c->numSMs;
     f.chainLaunches = c->chainLaunches ? 1 : 0;
     f.debugFlags = c->debugFlags;
@@ -236,6 +272,11 @@ int prepareFrame(crb_ctx* c) {
     CRB_CUDA(c, c->tileCount.reserve(CR_MAXTILES_SQR * 4));
     CRB_CUDA(c, c->activeTiles.reserve(CR_MAXTILES_SQR * 4));
     CRB_CUDA(c, c->activeRecs.reserve(CR_MAXTILES_SQR * 16));
+    const void* oldTileCounter = c->tileCounter.ptr;
+    CRB_CUDA(c, c->tileCounter.reserve(CR_MAXTILES_SQR * 4));
+    if (oldTileCounter != c->tileCounter.ptr) c->needReset = true;
+    CRB_CUDA(c, c->tileCursor.reserve(CR_MAXTILES_SQR * 4));
+    if (f.directMode) CRB_CUDA(c, c->triTileCode.reserve(((size_t)std::max(c->numTris, 1) + 4) * 4));
 
     f.triSubtris = (uint8_t*)c->triSubtris.ptr;
     f.triHeader = (uint4*)c->triHeader.ptr;
@@ -253,6 +294,9 @@ int prepareFrame(crb_ctx* c) {
     f.tileCount = (int32_t*)c->tileCount.ptr;
     f.activeTiles = (int32_t*)c->activeTiles.ptr;
     f.activeRecs = (int4*)c->activeRecs.ptr;
+    f.tileCounter = (int32_t*)c->tileCounter.ptr;
+    f.tileCursor = (int32_t*)c->tileCursor.ptr;
+    f.triTileCode = (uint32_t*)c->triTileCode.ptr;
     f.atomics = (crb_atomics*)c->atomics.ptr + c->atomicsParity;
     f.nextAtomics = (crb_atomics*)c->atomics.ptr + (c->atomicsParity ^ 1);
     if (oldBinMat != c->binCountMat.ptr || oldTileMat != c->tileCountMat.ptr || c->lastNumBins != f.numBins || c->lastMatPitch != f.matPitch ||
@@ -270,20 +314,22 @@ int launchStages(crb_ctx* c, cudaStream_t s, cudaEvent_t* ev) {
         CRB_CUDA(c, cudaMemsetAsync(c->atomics.ptr, 0, 2 * sizeof(crb_atomics), s));
         CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, c->binCountMat.cap, s));
         CRB_CUDA(c, cudaMemsetAsync(c->tileCountMat.ptr, 0, c->tileCountMat.cap, s));
+        CRB_CUDA(c, cudaMemsetAsync(c->tileCounter.ptr, 0, c->tileCounter.cap, s));
         c->needReset = false;
     }
     // several setup CTAs per chunk ADD their bin counts into one column: that (large-scene) layout needs a zeroed matrix.
     // (Letting the bin scatter zero the cells it reads was measured 3x slower than this memset: 466 vs 169 us on C4.)
-    if (f->numTris > 0 && f->ctasPerChunk > 1) CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, (size_t)f->matPitch * f->numBins * 4, s));
+    if (f->numTris > 0 && f->ctasPerChunk > 1 && !f->directMode) CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, (size_t)f->matPitch * f->numBins * 4, s));
     c->needReset = true;   // until every launch of this frame went through
     if (ev) CRB_CUDA(c, cudaEventRecord(ev[0], s));
     int rc = c->pipe.triangleSetup(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: triangleSetup launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
     if (ev) CRB_CUDA(c, cudaEventRecord(ev[1], s));
-    rc = c->pipe.binRaster(f, s);
+    // direct tile path: queue allocation stands where the bin stage stands, the unordered scatter where the coarse stage does
+    rc = f->directMode ? crb_launch_direct_alloc(f, s) : c->pipe.binRaster(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: binRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
     if (ev) CRB_CUDA(c, cudaEventRecord(ev[2], s));
-    rc = c->pipe.coarseRaster(f, s);
+    rc = f->directMode ? crb_launch_direct_scatter(f, s) : c->pipe.coarseRaster(f, s);
     if (rc != CRB_OK) return setError(c, rc, "CudaRaster: coarseRaster launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
     if (ev) CRB_CUDA(c, cudaEventRecord(ev[3], s));
     rc = c->pipe.fineRaster(f, s);
@@ -293,6 +339,7 @@ int launchStages(crb_ctx* c, cudaStream_t s, cudaEvent_t* ev) {
     c->launchCount += (f->numTris > 0 ? 1 : 0) + crb_bin_launches(f) + crb_coarse_launches(f) + 1;
     c->needReset = false;
     c->atomicsParity ^= 1;   // the fine raster kernel zeroed the other block for the next frame
+    c->lastFrameDirect = f->directMode != 0;
     return CRB_OK;
 }
 
@@ -339,6 +386,8 @@ int crb_create(int device, crb_ctx** out) {
     if (c->atomics.reserve(2 * sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
     const char* noPdl = getenv("CRB_NO_PDL");
     c->chainLaunches = !(noPdl && noPdl[0] == '1');
+    const char* direct = getenv("CRB_DIRECT");   // 0 / 1 / 2, see crb_set_binning_mode
+    if (direct && direct[0] >= '0' && direct[0] <= '2') c->binningMode = direct[0] - '0';
     const char* dbg = getenv("CRB_DEBUG_FLAGS");
     c->debugFlags = dbg ? atoi(dbg) : 0;
     if (cudaMallocHost((void**)&c->hostAtomics, sizeof(crb_atomics) * (1 + kAsyncRing)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
@@ -352,7 +401,7 @@ int crb_destroy(crb_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
-                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx};
+                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode};
     for (DevBuf* b : bufs) b->release();
     if (c->hp.init) {
         cudaStreamDestroy(c->hp.up);
@@ -446,6 +495,13 @@ int crb_set_pixel_pipe_by_name(crb_ctx* c, void* module, const char* name) {
     d.binRaster = (crb_stage_fn)dlsym(handle, (n + "_binRaster").c_str());
     d.coarseRaster = (crb_stage_fn)dlsym(handle, (n + "_coarseRaster").c_str());
     d.fineRaster = (crb_stage_fn)dlsym(handle, (n + "_fineRaster").c_str());
+    typedef int (*ProbeFn)(void);
+    ProbeFn probe = (ProbeFn)dlsym(handle, (n + "_orderIndependent").c_str());   // optional (pipes built before ABI 2 lack it)
+    d.orderIndependent = 0;
+    if (probe) {
+        cudaSetDevice(c->device);
+        d.orderIndependent = probe();
+    }
     if (!d.spec || !d.triangleSetup || !d.binRaster || !d.coarseRaster || !d.fineRaster) {
         c->hasPipe = false;
         return setError(c, CRB_ERR_INVALID, "CudaRaster: Invalid pixel pipe!");
@@ -469,6 +525,15 @@ int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
     c->indicesSet = d_indices != nullptr || numTris == 0;
     return CRB_OK;
 }
+
+int crb_set_binning_mode(crb_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return CRB_ERR_INVALID;
+    c->binningMode = mode;
+    c->shapeValid = false;
+    return CRB_OK;
+}
+
+int crb_get_last_frame_direct(crb_ctx* c) { return c && c->lastFrameDirect ? 1 : 0; }
 
 int crb_set_subviewport(crb_ctx* c, int fullWidth, int fullHeight, int x0, int y0) {
     if (!c) return CRB_ERR_INVALID;
@@ -515,6 +580,7 @@ int crb_draw_triangles(crb_ctx* c, void* stream) {
         crb_atomics a = *c->hostAtomics;
         a.numSubtris += numTris;
         c->lastAtomics = a;
+        noteFrameCounters(c, frameShape(c), a);
         if (a.overflow == 0) break;
         c->needReset = true;   // the kernels of an overflowed frame return early and leave the count matrices dirty
         if (attempt > 8) return setError(c, CRB_ERR_LIMIT, "CudaRaster: work buffers keep overflowing (flags %d)", a.overflow);
@@ -544,6 +610,7 @@ int crb_finish(crb_ctx* c, void* stream) {
         crb_atomics a = c->hostAtomics[1 + i];
         a.numSubtris += c->numTris;
         c->lastAtomics = a;
+        noteFrameCounters(c, c->pendingShape[i], a);
         if (a.overflow == 0) continue;
         overflowed++;
         if (a.overflow & 1) c->maxSubtris = std::max(c->maxSubtris, a.numSubtris + 4096);
@@ -582,6 +649,7 @@ int crb_draw_triangles_async(crb_ctx* c, void* stream) {
     rc = launchStages(c, s, c->stageTiming ? c->ringEv[c->pending] : nullptr);
     if (rc != CRB_OK) return rc;
     CRB_CUDA(c, cudaMemcpyAsync(&c->hostAtomics[1 + c->pending], c->frame.atomics, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
+    c->pendingShape[c->pending] = frameShape(c);
     c->pending++;
     c->deferredClear = false;
     c->drawn = true;

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 1
+#define CRB_ABI_VERSION 2
 
 typedef enum crb_status {
     CRB_OK = 0,
@@ -61,8 +61,9 @@ typedef struct crb_atomics {
     int32_t numCoarseItems;    /* work items the coarse stage processed                        */
     int32_t numTileEntries;    /* triangle-tile pairs written to the tile queue                */
     int32_t numActiveTiles;    /* tiles the fine stage touches                                 */
-    int32_t overflow;          /* bit0 subtris, bit1 bin queue, bit2 tile queue, bit3 items    */
-    int32_t reserved[2];
+    int32_t overflow;          /* bit0 subtris, bit1 bin queue, bit2 tile queue, bit3 items */
+    int32_t numLargeTris;      /* setup CTAs (256 triangles) that met a sub-triangle spanning > CRB_DIRECT_MAX_TILES tiles on an axis */
+    int32_t reserved;
 } crb_atomics;
 
 /* Everything a stage launcher needs; filled by crb_draw_triangles().  Opaque to C callers,
@@ -82,6 +83,9 @@ typedef struct crb_pipe_desc {
     crb_stage_fn binRaster;
     crb_stage_fn coarseRaster;
     crb_stage_fn fineRaster;
+    int32_t orderIndependent;   /* 1 = depth test on, blend ignores dst, shader never discards: the surviving fragment of a sample is
+                                 * the (depth, submission index) minimum whatever the processing order (<pipe>_orderIndependent,
+                                 * emitted by CR_DEFINE_PIXEL_PIPE).  Lets crb_draw_triangles use the direct tile path. */
 } crb_pipe_desc;
 
 /* ---- lifetime: CudaRaster::CudaRaster/init/~CudaRaster, CudaRaster.cpp:53-128 ---------------- */
@@ -124,6 +128,19 @@ int crb_set_index_buffer(crb_ctx* ctx, const void* d_indices, int numTris);
  * Vertices are snapped once in full-frame subpixels so seams are watertight for any split.
  * Passing fullWidth = 0 restores the plain single viewport. */
 int crb_set_subviewport(crb_ctx* ctx, int fullWidth, int fullHeight, int x0, int y0);
+
+/* Binning strategy (new).  The general path is the stable two-level sort (bin raster + coarse raster) that keeps
+ * every tile queue in submission order, like the reference.  The DIRECT path skips both levels: triangle setup counts
+ * the tiles of every triangle, one kernel allocates the tile queues and one scatters the entries with atomics, in
+ * arbitrary order -- valid only for order-independent pipes (crb_pipe_desc.orderIndependent); it is built for frames
+ * of small triangles (a triangle spanning more than CRB_DIRECT_MAX_TILES tiles on an axis is handled by a whole CTA
+ * at a time, correct but slower than the bins of the general path).  mode 0 = never, 1 = automatic (default: direct
+ * when the last completed frame of the same shape -- triangle count, surface, window, pipe -- had no such triangle),
+ * 2 = direct on every frame whose pipe allows it.  Surfaces are bit-identical on both paths. */
+#define CRB_DIRECT_MAX_TILES 4
+int crb_set_binning_mode(crb_ctx* ctx, int mode);
+/* 1 when the last frame ran on the direct path. */
+int crb_get_last_frame_direct(crb_ctx* ctx);
 
 /* ---- the hot path ----------------------------------------------------------------------------
  * CudaRaster::drawTriangles (CudaRaster.cpp:237-342): sizes the work buffers, launches the four

@@ -376,7 +376,10 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
             // pixel centres of the tile inside the triangle's bounding box
             const int colLo = max((loX - bx + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0), colHi = min((hiX - bx) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
             const int rowLo = max((loY - by + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0), rowHi = min((hiY - by) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
-            const bool live = cur.entry >= 0 && (!kDepth || (cur.h.w & 0xFFFFF000u) < tileZMax) && colLo <= colHi && rowLo <= rowHi;
+            // early Z against the tile's farthest depth; on the direct path (unordered queue) a triangle AT that depth
+            // may still beat a later-submitted winner of the same depth, so only strictly farther ones are dropped
+            const U32 zminHdr = cur.h.w & 0xFFFFF000u;
+            const bool live = cur.entry >= 0 && (!kDepth || zminHdr < tileZMax || (f.directMode != 0 && zminHdr == tileZMax)) && colLo <= colHi && rowLo <= rowHi;
             const bool small = (colHi - colLo < 4) & (rowHi - rowLo < 4) & (hiX - loX < (64 << CR_SUBPIXEL_LOG2)) & (hiY - loY < (64 << CR_SUBPIXEL_LOG2));
             if ((f.debugFlags & 1) == 0 && __all_sync(0xFFFFFFFFu, !live || small)) {
                 if (live) coverSmall4x4(x0, y0, x1, y1, x2, y2, bx, by, colLo, rowLo, colHi - colLo + 1, rowHi - rowLo + 1, maskLo, maskHi);
@@ -417,6 +420,10 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
                 if (kDepth) {
                     z = sb.zb[j] + sb.zx[j] * (U32)lx + sb.zy[j] * (U32)(ly + 4 * p);
                     zkill = z >= depth[p];
+                    // Direct path: the queue is unordered, the survivor of a pixel is the (depth, submission index)
+                    // minimum -- what the strict LESS test leaves when fragments arrive in submission order.  A tie
+                    // with the depth the tile started with (winner < 0) still fails.
+                    if (deferred && f.directMode != 0 && z == depth[p] && winner[p] >= 0 && sb.entry[j] < winner[p]) zkill = false;
                     if (!(kQuads && !deferred) && zkill) continue;
                 }
                 if (deferred) {

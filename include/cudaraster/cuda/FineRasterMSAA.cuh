@@ -144,7 +144,8 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
             sb.a0[lane] = a[0]; sb.b0[lane] = b[0]; sb.c0[lane] = c[0];
             sb.a1[lane] = a[1]; sb.b1[lane] = b[1]; sb.c1[lane] = c[1];
             sb.a2[lane] = a[2]; sb.b2[lane] = b[2]; sb.c2[lane] = c[2];
-            if (!kDepth || (cur.h.w & 0xFFFFF000u) < tileZMax) {
+            const U32 zminHdr = cur.h.w & 0xFFFFF000u;
+            if (!kDepth || zminHdr < tileZMax || (f.directMode != 0 && zminHdr == tileZMax)) {   // direct path: see FineRaster.cuh
                 const S32 y0 = (S32)cur.h.x >> 16, y1 = (S32)cur.h.y >> 16, y2 = (S32)cur.h.z >> 16;
                 const int rowLo = max((min(min(y0, y1), y2) - by - kMaxOfs + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0);
                 const int rowHi = min((max(max(y0, y1), y2) - by + kMaxOfs) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
@@ -196,6 +197,11 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
                 for (int i = 0; i < N; i++) {
                     z[i] = zPix + zxv * (U32)msaaSampleX(SamplesLog2, i) + zyv * (U32)i;
                     if (((cov >> i) & 1) && (!kDepth || z[i] < tDepth[i * CR_TILE_SQR + qBase])) pass |= 1u << i;
+                    // direct path (unordered queue): among equal depths the earliest-submitted fragment survives
+                    if (kDepth && deferred && f.directMode != 0 && ((cov >> i) & 1) && z[i] == tDepth[i * CR_TILE_SQR + qBase]) {
+                        const U32 held = tAux[i * CR_TILE_SQR + qBase];
+                        if (held != 0 && (U32)sb.entry[j] + 1u < held) pass |= 1u << i;
+                    }
                 }
                 if (!kQuads && pass == 0) continue;
                 const S32 entry = sb.entry[j];

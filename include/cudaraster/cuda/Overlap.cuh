@@ -75,6 +75,28 @@ __device__ __forceinline__ void forEachCell(const TriFootprint& t, S32 winLoX, S
         }
 }
 
+// The same enumeration shared out over `stride` cooperating threads (thread `first` of them): used for the few
+// triangles that span many cells, where one thread walking the whole rectangle would be a long tail.  Visits
+// exactly the cells forEachCell visits (a rectangle larger than 2x2 cells is always refined).
+template <int SamplesLog2, int CellLog2, class Fn>
+__device__ __forceinline__ void forEachCellStrided(const TriFootprint& t, S32 winLoX, S32 winLoY, S32 winHiX, S32 winHiY, int first, int stride, Fn fn) {
+    if (t.empty) return;
+    S32 cLoX = t.pxLoX >> CellLog2, cHiX = t.pxHiX >> CellLog2, cLoY = t.pxLoY >> CellLog2, cHiY = t.pxHiY >> CellLog2;
+    const bool refine = (cHiX - cLoX > 1) | (cHiY - cLoY > 1);
+    cLoX = max(cLoX, winLoX); cHiX = min(cHiX, winHiX); cLoY = max(cLoY, winLoY); cHiY = min(cHiY, winHiY);
+    const S32 nx = cHiX - cLoX + 1, ny = cHiY - cLoY + 1;
+    if (nx <= 0 || ny <= 0) return;
+    for (S32 k = first; k < nx * ny; k += stride) {
+        const S32 cy = cLoY + k / nx, cx = cLoX + (k - (k / nx) * nx);
+        if (refine) {
+            S32 pxA = max(cx << CellLog2, t.pxLoX), pxB = min((cx << CellLog2) + (1 << CellLog2) - 1, t.pxHiX);
+            S32 pyA = max(cy << CellLog2, t.pxLoY), pyB = min((cy << CellLog2) + (1 << CellLog2) - 1, t.pxHiY);
+            if (cellRejected<SamplesLog2>(t, pxA, pyA, pxB, pyB)) continue;
+        }
+        fn(cx, cy);
+    }
+}
+
 // Cell rectangle of a footprint inside an inclusive cell window: first cell, extent (0 = nothing)
 // and whether cells must be refined with edge tests (decided on the UNclipped footprint, exactly
 // like forEachCell, so that every pass that enumerates the cells of a triangle agrees).

@@ -23,6 +23,27 @@
 extern "C" int crb_launch_bin_raster(const crb_frame* frame, void* stream);
 extern "C" int crb_launch_coarse_raster(const crb_frame* frame, void* stream);
 
+// Is the pipe ORDER INDEPENDENT (crb_pipe_desc.orderIndependent)?  needsDst() is device code (the reference's
+// contract: "must be a constant", cuda/PixelPipe.hpp:112), so the answer is computed by a one-thread kernel, once.
+namespace FW {
+template <class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
+static __global__ void pipeProbeKernel(int* out) {
+    BlendShaderClass b;
+    const bool quadsMsaa = (RenderModeFlags & RenderModeFlag_EnableQuads) != 0 && SamplesLog2 > 0;   // shades in order (FineRasterMSAA.cuh)
+    *out = ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0 && !b.needsDst() && FragmentShaderClass::CanDiscard == 0 && !quadsMsaa) ? 1 : 0;
+}
+template <class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
+inline int probeOrderIndependent() {
+    int* d = nullptr;
+    int v = 0;
+    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return 0;
+    pipeProbeKernel<FragmentShaderClass, BlendShaderClass, SamplesLog2, RenderModeFlags><<<1, 1>>>(d);
+    if (cudaMemcpy(&v, d, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) v = 0;
+    cudaFree(d);
+    return v;
+}
+}  // namespace FW
+
 #define CR_DEFINE_PIXEL_PIPE(PIPE_NAME, VERTEX_STRUCT, FRAGMENT_SHADER, BLEND_SHADER, SAMPLES_LOG2, RENDER_MODE_FLAGS)                      \
     extern "C" int PIPE_NAME##_triangleSetup(const crb_frame* frame, void* stream) {                                                        \
         return FW::launchTriangleSetup<VERTEX_STRUCT, SAMPLES_LOG2, RENDER_MODE_FLAGS>(frame, stream);                                      \
@@ -31,6 +52,11 @@ extern "C" int crb_launch_coarse_raster(const crb_frame* frame, void* stream);
     extern "C" int PIPE_NAME##_coarseRaster(const crb_frame* frame, void* stream) { return crb_launch_coarse_raster(frame, stream); }       \
     extern "C" int PIPE_NAME##_fineRaster(const crb_frame* frame, void* stream) {                                                           \
         return FW::FineRasterLauncher<VERTEX_STRUCT, FRAGMENT_SHADER, BLEND_SHADER, SAMPLES_LOG2, RENDER_MODE_FLAGS>::launch(frame, stream); \
+    }                                                                                                                                       \
+    extern "C" int PIPE_NAME##_orderIndependent(void) {                                                                                     \
+        static int cached = -1;                                                                                                             \
+        if (cached < 0) cached = FW::probeOrderIndependent<FRAGMENT_SHADER, BLEND_SHADER, SAMPLES_LOG2, RENDER_MODE_FLAGS>();               \
+        return cached;                                                                                                                      \
     }                                                                                                                                       \
     extern "C" const crb_pipe_spec PIPE_NAME##_spec = {                                                                                     \
         /* samplesLog2 */ SAMPLES_LOG2,                                                                                                     \

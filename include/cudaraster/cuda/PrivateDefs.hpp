@@ -30,6 +30,8 @@ typedef crb_atomics CRAtomics;
 
 }  // namespace FW
 
+#define CRB_TILECODE_GENERAL 0x40000000u
+
 // One coarse work item: `count` consecutive entries of one bin's queue.
 struct crb_item {
     int32_t bin;
@@ -96,6 +98,14 @@ struct crb_frame {
     int32_t* tileCount;           // [CR_MAXTILES_SQR]
     int32_t* activeTiles;         // [CR_MAXTILES_SQR]
     int4* activeRecs;             // [CR_MAXTILES_SQR] {tile index, queue start, queue count, 0}: one load per fine warp
+
+    // ---- direct tile path (crb_set_binning_mode); tileStart / tileCount / activeRecs / tileQueue as above
+    int32_t directMode;           // 1 = this frame runs setup -> directAlloc -> directScatter -> fine, queues unordered
+    int32_t* tileCounter;         // [CR_MAXTILES_SQR] entries per tile, counted by setup, zeroed again by directAllocKernel
+    int32_t* tileCursor;          // [CR_MAXTILES_SQR] end of the tile's queue extent, counted down by the scatter pass
+    uint32_t* triTileCode;        // [numTris] what the scatter pass needs to know about a triangle in ONE word: 0 = nothing to place,
+                                  // CRB_TILECODE_GENERAL = go through triSubtris / the headers (clipped, refined or large), else
+                                  // tile x0 | y0 << 8 | (nx-1) << 16 | (ny-1) << 17 | 1 << 31 of a footprint of at most 2x2 tiles
 
     crb_atomics* atomics;         // counters of THIS frame (zero when the frame starts)
     crb_atomics* nextAtomics;     // counters of the next frame: zeroed by this frame's fine raster kernel

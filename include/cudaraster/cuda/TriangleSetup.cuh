@@ -137,9 +137,53 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
     return h;
 }
 
-template <int SamplesLog2>
-__device__ __forceinline__ void histogramBins(const crb_frame& f, uint4 h, int* s_binCount) {
+// What binning needs from a finished sub-triangle (header h, stored in record `slot`).  General path: the bins it
+// touches go into the CTA's bin histogram.  Direct tile path (crb_frame::directMode): every tile it touches is
+// counted straight into the per-tile counters with fire-and-forget global reductions; sub-triangles that span
+// more than CRB_DIRECT_MAX_TILES tiles on an axis are put on a per-CTA list and counted by the whole CTA together
+// at the end of the kernel (a thread walking thousands of tiles alone would be a long tail).  Either way the CTA
+// reports whether it met such a large sub-triangle: the automatic binning mode only goes direct while there are none.
+struct SetupShared {
+    int binCount[CR_MAXBINS_SQR];
+    int sawLarge;
+    int numLarge;
+    int largeSlot[CRB_SETUP_THREADS];
+};
+
+// Returns the triangle's tile code (crb_frame::triTileCode) on the direct path, 0 on the general path.
+// DeferSmall: the caller counts a footprint of at most 2x2 tiles itself from the returned code.  (Unused: counting
+// warp-aggregated with __match_any_sync at the end of the kernel measured 37.6 vs 38.5 us on C2 but 225 vs 215 us on C4.)
+template <int SamplesLog2, bool DeferSmall>
+__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, SetupShared& sh) {
+    int* s_binCount = sh.binCount;
     TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
+    const CellRange t = cellRange<CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1);
+    const bool large = (t.nx > CRB_DIRECT_MAX_TILES) | (t.ny > CRB_DIRECT_MAX_TILES);
+    if (large) sh.sawLarge = 1;
+    if (f.directMode) {
+        if (large) {
+            const int k = atomicAdd(&sh.numLarge, 1);
+            if (k < CRB_SETUP_THREADS) { sh.largeSlot[k] = slot; return CRB_TILECODE_GENERAL; }
+            // list full (only clipped triangles can push more than one entry per thread): count it alone
+        }
+        if (!t.refine) {   // at most 2x2 tiles, never refined: the rectangle IS the tile set
+            if (t.nx > 0) {
+                if (!DeferSmall) {
+                    int* p = &f.tileCounter[t.x0 + t.y0 * f.widthTiles];
+                    atomicAdd(p, 1);
+                    if (t.nx > 1) atomicAdd(p + 1, 1);
+                    if (t.ny > 1) {
+                        atomicAdd(p + f.widthTiles, 1);
+                        if (t.nx > 1) atomicAdd(p + f.widthTiles + 1, 1);
+                    }
+                }
+                return 0x80000000u | (U32)t.x0 | ((U32)t.y0 << 8) | ((U32)(t.nx - 1) << 16) | ((U32)(t.ny - 1) << 17);
+            }
+            return 0;
+        }
+        forEachCell<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, [&](S32 tx, S32 ty) { atomicAdd(&f.tileCounter[tx + ty * f.widthTiles], 1); });
+        return CRB_TILECODE_GENERAL;
+    }
     // footprints of at most 2x2 bins are never refined (Overlap.cuh): the rectangle IS the cell set
     const CellRange r = cellRange<CR_BIN_LOG2 + CR_TILE_LOG2>(fp, 0, 0, f.widthBins - 1, f.heightBins - 1);
     if (!r.refine) {
@@ -152,15 +196,16 @@ __device__ __forceinline__ void histogramBins(const crb_frame& f, uint4 h, int* 
                 if (r.nx > 1) atomicAdd(p + f.widthBins + 1, 1);
             }
         }
-        return;
+        return 0;
     }
     forEachCell<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(fp, 0, 0, f.widthBins - 1, f.heightBins - 1,
                                                           [&](S32 bx, S32 by) { atomicAdd(&s_binCount[bx + by * f.widthBins], 1); });
+    return 0;
 }
 
 // Cold path: clip against the view window, fan the polygon, re-snap / re-cull every sub-triangle.
 template <int SamplesLog2, U32 RenderModeFlags>
-__device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, int3 vidx, float4 v0, float4 v1, float4 v2, int* s_binCount) {
+__device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, int3 vidx, float4 v0, float4 v1, float4 v2, SetupShared& sh) {
     const F32 lo[3] = {f.clipLoX, f.clipLoY, -1.0f}, hi[3] = {f.clipHiX, f.clipHiY, 1.0f};
     const float4 d1 = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), __fsub_rn(v1.w, v0.w));
     const float4 d2 = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), __fsub_rn(v2.w, v0.w));
@@ -209,7 +254,7 @@ __device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, in
         snapTriangle(f, c0, cPrev, cCur, s);
         if (prepareTriangle<SamplesLog2>(f, s, e1, e2, area) == 0) {
             uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[slot], &f.triData[(size_t)slot * 4], vidx, c0, cPrev, cCur, bary[0], bary[i - 1], bary[i], s, e1, e2, area);
-            histogramBins<SamplesLog2>(f, h, s_binCount);
+            histogramBins<SamplesLog2, false>(f, h, slot, sh);
             slot++;
         }
         cPrev = cCur;
@@ -219,9 +264,11 @@ __device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, in
 
 template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
 static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
-    __shared__ int s_binCount[CR_MAXBINS_SQR];
+    __shared__ SetupShared sh;
+    int* const s_binCount = sh.binCount;
     gridDepLaunchDependents();
     for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
+    if (threadIdx.x == 0) sh.sawLarge = sh.numLarge = 0;
     __syncthreads();
     gridDepWait();   // the previous frame's kernels still read the work buffers written below
 
@@ -230,6 +277,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     const S32 aabbLimit = (1 << (CR_MAXVIEWPORT_LOG2 + CR_SUBPIXEL_LOG2)) - 1;
 
     const int tri = blockIdx.x * CRB_SETUP_THREADS + threadIdx.x;   // one thread per input triangle
+    U32 tileCode = 0;
     if (tri < f.numTris) {
         const int3 vidx = make_int3(__ldg(&f.indexBuffer[tri * 3 + 0]), __ldg(&f.indexBuffer[tri * 3 + 1]), __ldg(&f.indexBuffer[tri * 3 + 2]));
         const float4 v0 = __ldg(&verts[(size_t)vidx.x * stride4]);
@@ -269,17 +317,30 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
                     if (res == 0) {
                         uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
                                                                               make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area);
-                        histogramBins<SamplesLog2>(f, h, s_binCount);
+                        tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh);
                     }
                     done = true;
                 }
             }
-            if (!done) setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, s_binCount);
+            if (!done && setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, sh) > 0) tileCode = CRB_TILECODE_GENERAL;
         }
+        if (f.directMode) f.triTileCode[tri] = tileCode;
     }
 
     // publish this CTA's bin histogram: one column of binCountMat[bin][chunk]
     __syncthreads();
+    if (threadIdx.x == 0 && sh.sawLarge != 0) atomicAdd(&f.atomics->numLargeTris, 1);   // CTAs with a large sub-triangle (zero / non-zero is what matters)
+    if (f.directMode) {
+        // the large sub-triangles of this CTA, all threads together (their headers were written by this CTA before the barrier)
+        const int numLarge = min(sh.numLarge, CRB_SETUP_THREADS);
+        for (int k = 0; k < numLarge; k++) {
+            const uint4 h = f.triHeader[sh.largeSlot[k]];
+            const TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
+            forEachCellStrided<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, CRB_SETUP_THREADS,
+                                                          [&](S32 tx, S32 ty) { atomicAdd(&f.tileCounter[tx + ty * f.widthTiles], 1); });
+        }
+        return;
+    }
     int* col = f.binCountMat + blockIdx.x / f.ctasPerChunk;
     if (f.ctasPerChunk == 1) {
         for (int b = threadIdx.x; b < f.numBins; b += CRB_SETUP_THREADS) col[(size_t)b * f.matPitch] = s_binCount[b];

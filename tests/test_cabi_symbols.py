@@ -21,7 +21,7 @@ def test_header_functions_are_exported(crb):
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), "libcrb200.so does not export %s" % n
-    assert lib.crb_abi_version() == 1
+    assert lib.crb_abi_version() == 2
 
 
 def test_builtin_pipes_resolve_by_name(crb):
@@ -29,7 +29,7 @@ def test_builtin_pipes_resolve_by_name(crb):
     for base, s, f, blend in [("passthrough", 0, 1, "BlendReplace"), ("gouraud", 0, 3, "BlendReplace"), ("gouraud", 2, 3, "BlendSrcOver"),
                               ("texPhong", 2, 3, "BlendReplace"), ("gouraud", 3, 3, "BlendReplace")]:
         name = crb.pipe_name(base, s, f, blend)
-        for suffix in ("_triangleSetup", "_binRaster", "_coarseRaster", "_fineRaster", "_spec"):
+        for suffix in ("_triangleSetup", "_binRaster", "_coarseRaster", "_fineRaster", "_spec", "_orderIndependent"):
             assert hasattr(lib, name + suffix), name + suffix
     for suffix in ("_triangleSetup", "_binRaster", "_coarseRaster", "_fineRaster", "_spec"):
         assert hasattr(lib, "PixelPipe_passthrough" + suffix)

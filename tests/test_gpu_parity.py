@@ -49,7 +49,9 @@ def test_queues_are_ordered_supersets(raster, crb, gold):
     import ctypes
     w, h = 640, 360
     v, i = crb.scenes.random_soup(6000, seed=77, stride_floats=4, size=0.6)
+    raster.setBinningMode(0)   # the ordered two-level sort is what this test inspects
     util.draw_cuda(raster, crb, v, i, w, h, "passthrough", 1)
+    raster.setBinningMode(1)
     wb = raster.getWorkBuffers(i.shape[0])
     tq, ts, tc = wb["tileQueue"], wb["tileStart"], wb["tileCount"]
     bq, bs, bt = wb["binQueue"], wb["binStart"], wb["binTotal"]
@@ -173,7 +175,8 @@ def test_c2_full_size_properties(raster, crb):
     assert np.array_equal(cc, cc2) and np.array_equal(cd, cd2)           # deterministic / idempotent
     assert (cd < 0xFFFFBB3F).all()                                        # the mesh covers the whole frame
     c = raster.getCounters()
-    assert c["overflow"] == 0 and c["numActiveTiles"] == 240 * 135 and c["numTileEntries"] >= c["numBinEntries"] > 900000
+    assert raster.lastFrameDirect()                                       # automatic mode: second frame of a small-triangle shape
+    assert c["overflow"] == 0 and c["numActiveTiles"] == 240 * 135 and c["numTileEntries"] > 900000 and c["numLargeTris"] == 0
     g = util.draw_gold(v, i, w, h, "gouraud", 3)
     _check_surfaces(cc, cd, g, lsb=1)
 
@@ -337,3 +340,115 @@ def test_vertex_shader_stage_then_draw(raster, crb, gold):
     d_out2 = torch.zeros((nv, 4), dtype=torch.float32, device="cuda")
     raster.launchVertexShader(None, "vertexShader_passthrough", d_in2, d_out2, nv, np.ascontiguousarray(m, np.float32).tobytes())
     assert np.array_equal(d_out2.cpu().numpy().view(np.uint32), gold.vertex_shader(m, vin[:, 0:3], 4).view(np.uint32))
+
+
+# ---- direct tile path (crb_set_binning_mode): unordered tile queues + order-independent resolve -------------------
+def _small_scenes(crb):
+    rng = np.random.default_rng(9)
+    v, i = crb.scenes.grid_gouraud(160, 100)
+    yield "grid", v, i
+    # the same mesh submitted twice with different colours: every fragment of the second copy ties in depth with
+    # the first and must lose (strict LESS in submission order == (depth, index) minimum)
+    v2 = np.concatenate([v, v]); v2[v.shape[0]:, 4:8] = rng.uniform(0, 1, (v.shape[0], 4)).astype(np.float32)
+    i2 = np.concatenate([i, i + v.shape[0]])
+    yield "duplicate", v2, i2
+    # the second copy FIRST in memory order but the draw order interleaved: ties resolved by index, not by position
+    perm = rng.permutation(i2.shape[0])
+    yield "shuffled-duplicate", v2, np.ascontiguousarray(i2[perm])
+    vs, js = crb.scenes.random_soup(30000, seed=41, stride_floats=8, size=0.03, clip_fraction=0.02, behind_fraction=0.0)
+    yield "soup", vs, js
+
+
+@pytest.mark.parametrize("shader,flags,samples_log2,blend", [
+    ("gouraud", 3, 0, "BlendReplace"), ("gouraud", 1, 0, "BlendReplace"), ("passthrough", 1, 0, "BlendDepthOnly"), ("gouraud", 3, 2, "BlendReplace"),
+    ("gouraud", 3, 3, "BlendReplace"), ("gouraudQuads", 7, 0, "BlendReplace")])
+def test_direct_tile_path_matches_oracle(raster, crb, shader, flags, samples_log2, blend):
+    w, h = 512, 384
+    try:
+        for name, v, i in _small_scenes(crb):
+            if shader == "passthrough":
+                v = np.ascontiguousarray(v[:, :4])
+            g = util.draw_gold(v, i, w, h, shader, flags, samples_log2, blend)
+            for mode in (2, 0):
+                raster.setBinningMode(mode)
+                cc, cd = util.draw_cuda(raster, crb, v, i, w, h, shader, flags, samples_log2, blend)
+                assert raster.lastFrameDirect() == (mode == 2), "%s: wrong path (mode %d)" % (name, mode)
+                c = raster.getCounters()
+                assert c["overflow"] == 0 and (c["numBinEntries"] == 0) == (mode == 2)
+                _check_surfaces(cc, cd, g, lsb=0 if shader == "passthrough" else 1)
+    finally:
+        raster.setBinningMode(1)
+
+
+def test_direct_tile_path_large_triangles_and_auto(raster, crb):
+    """Large triangles on the direct path are scattered by whole CTAs (slow but exact); automatic mode goes direct on
+    the second frame of a small-triangle shape and stays general while the shape has large triangles; pipes that
+    read dst never go direct."""
+    w, h = 512, 384
+    v, i = crb.scenes.grid_gouraud(160, 100)
+    big = np.array([[-0.9, -0.8, 0.5, 1, 1, 0, 0, 1], [0.9, -0.7, 0.5, 1, 0, 1, 0, 1], [0.1, 0.9, 0.5, 1, 0, 0, 1, 1],
+                    [-3.0, -3.0, 0.7, 1, 1, 1, 0, 1], [3.0, -3.0, 0.7, 1, 0, 1, 1, 1], [0.0, 3.0, 0.7, 1, 1, 0, 1, 1]], np.float32)
+    nv = v.shape[0]
+    vb = np.concatenate([v, big]); ib = np.concatenate([i[:1000], np.array([[nv, nv + 1, nv + 2]], np.int32), i[1000:], np.array([[nv + 3, nv + 4, nv + 5]], np.int32)])
+    vs, js = crb.scenes.random_soup(5000, seed=1234, stride_floats=8)   # big, clipped and w<=0 triangles
+    try:
+        raster.setBinningMode(2)
+        for vv, ii in ((vb, ib), (vs, js)):
+            cc, cd = util.draw_cuda(raster, crb, vv, ii, w, h, "gouraud", 3)
+            assert raster.lastFrameDirect() and raster.getCounters()["numLargeTris"] > 0
+            _check_surfaces(cc, cd, util.draw_gold(vv, ii, w, h, "gouraud", 3), lsb=1)
+            cc, cd = util.draw_cuda(raster, crb, vv, ii, w, h, "gouraud", 3, 2)
+            assert raster.lastFrameDirect()
+            _check_surfaces(cc, cd, util.draw_gold(vv, ii, w, h, "gouraud", 3, 2), lsb=1)
+        cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, blend="BlendSrcOver")   # reads dst: order matters
+        assert not raster.lastFrameDirect()
+        _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, blend="BlendSrcOver"), lsb=1)
+        raster.setBinningMode(1)
+        g = util.draw_gold(v, i, w, h, "gouraud", 3)
+        seen = []
+        for k in range(3):
+            cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+            seen.append(raster.lastFrameDirect())
+            _check_surfaces(cc, cd, g, lsb=1)
+        assert seen == [False, True, True]
+        for k in range(3):   # large triangles inside: the shape stays on the general path
+            cc, cd = util.draw_cuda(raster, crb, vb, ib, w, h, "gouraud", 3)
+            assert not raster.lastFrameDirect()
+        _check_surfaces(cc, cd, util.draw_gold(vb, ib, w, h, "gouraud", 3), lsb=1)
+    finally:
+        raster.setBinningMode(1)
+
+
+def test_direct_tile_path_async_frames_and_no_clear(raster, crb):
+    """Asynchronous frames on the direct path (counters self-clean between frames), then a frame without a deferred
+    clear: fragments must beat the depth already in the surface, ties with it fail."""
+    import torch
+    w, h = 512, 384
+    v, i = crb.scenes.grid_gouraud(160, 100)
+    g = util.draw_gold(v, i, w, h, "gouraud", 3)
+    try:
+        raster.setBinningMode(2)
+        cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+        color = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, 1)
+        depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32, 1)
+        vbuf, ibuf = torch.from_numpy(v).cuda(), torch.from_numpy(i).cuda()
+        raster.setSurfaces(color, depth)
+        raster.setVertexBuffer(vbuf, 0)
+        raster.setIndexBuffer(ibuf, 0, i.shape[0])
+        for k in range(6):
+            raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+            raster.drawTriangles(asynchronous=True)
+        raster.finish()
+        assert raster.lastFrameDirect()
+        _check_surfaces(color.numpy(), depth.numpy(), g, lsb=1)
+        # second pass over the finished frame without a clear: every fragment ties with the stored depth and fails
+        raster.drawTriangles()
+        assert raster.lastFrameDirect()
+        _check_surfaces(color.numpy(), depth.numpy(), g, lsb=1)
+        rng = np.random.default_rng(11)
+        init = (rng.integers(0, 2**32, g["color"].shape, dtype=np.uint32), rng.integers(2**31, 2**32, g["depth"].shape, dtype=np.uint32))
+        cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, clear=None, init=init)
+        assert raster.lastFrameDirect()
+        _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, clear=None, init=init), lsb=1)
+    finally:
+        raster.setBinningMode(1)

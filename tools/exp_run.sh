@@ -1,7 +1,9 @@
-for v in base pf1 pf2 base pf1 pf2; do
+# developer tool: runs bench.py on experiment builds (tools/build_variant.sh) and prints one line per run
+out=gpurun_out/exp.log; rm -f $out
+for v in "$@"; do
   lib=build/variants/$v/libcrb200.so; [ $v = base ] && lib=cudaraster-linux_b200/libcrb200.so
-  CRB200_LIBRARY=$lib python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-ref-kernels 2>/dev/null | python -c "
+  CRB200_LIBRARY=$lib python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-ref-kernels ${BENCH_ARGS} 2>/dev/null | python -c "
 import sys,json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v', round(d['value']), {k:round(v*1000,1) for k,v in d['stage_ms'].items()})" >> gpurun_out/exp1.log
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v', round(d['value']), {k:round(v*1000,1) for k,v in d['stage_ms'].items()}, 'e2e', round(d['e2e']['value']))" >> $out
 done
-cat gpurun_out/exp1.log
+cat $out
