@@ -488,8 +488,7 @@ __global__ void __launch_bounds__(kThreads) directAllocKernel(const __grid_const
 
 // Every thread places FOUR consecutive input triangles.  Setup left one word per triangle (crb_frame::triTileCode):
 // the common case -- a single sub-triangle on at most 2x2 tiles -- needs nothing else, and its (at most four) slots
-// are taken in four rounds of up to four independent atomics each, so that a thread always has several atomic round
-// trips in flight.  The cursor a slot comes from already holds the absolute queue position (directAllocKernel), so a
+// are taken with up to sixteen independent atomics issued back to back before any result is used.  The cursor a slot comes from already holds the absolute queue position (directAllocKernel), so a
 // placed entry costs two scattered memory operations: the atomic and the store -- the kernel is bound by the rate at
 // which an SM issues scattered accesses, not by latency.  (Measured and rejected: warp-aggregated atomics with
 // __match_any_sync -- 25 vs 19 us on C2, 109 vs 52 us on C4: the match costs more than the atomics it saves.)
@@ -543,17 +542,22 @@ __global__ void __launch_bounds__(kThreads, CRB_SCATTER_MIN_BLOCKS) directScatte
         if (base + k >= f.numTris) code[k] = 0;
         t0[k] = (S32)(code[k] & 0xFF) + (S32)((code[k] >> 8) & 0xFF) * f.widthTiles;
     }
+    // all (up to 16) atomics of the thread are issued before the first result is used
+    int pos[4][kScatterTris];
 #pragma unroll
     for (int s = 0; s < 4; s++) {   // tile (s & 1, s >> 1) of the footprint
         const U32 need = 0x80000000u | ((s & 1) ? 0x10000u : 0u) | ((s & 2) ? 0x20000u : 0u);
         const S32 ofs = (s & 1) + ((s & 2) ? f.widthTiles : 0);
-        int pos[kScatterTris];
 #pragma unroll
         for (int k = 0; k < kScatterTris; k++)
-            if ((code[k] & need) == need) pos[k] = atomicSub(&f.tileCursor[t0[k] + ofs], 1) - 1;
+            if ((code[k] & need) == need) pos[s][k] = atomicSub(&f.tileCursor[t0[k] + ofs], 1) - 1;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const U32 need = 0x80000000u | ((s & 1) ? 0x10000u : 0u) | ((s & 2) ? 0x20000u : 0u);
 #pragma unroll
         for (int k = 0; k < kScatterTris; k++)
-            if ((code[k] & need) == need) f.tileQueue[pos[k]] = (base + k) * 8 + 7;
+            if ((code[k] & need) == need) f.tileQueue[pos[s][k]] = (base + k) * 8 + 7;
     }
 
 #pragma unroll 1

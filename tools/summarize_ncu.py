@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGE_OF = {"triangleSetupKernel": "triangleSetup", "binScanKernel": "binRaster", "binScatterKernel": "binRaster", "coarseScanKernel": "coarseRaster",
-            "coarseScatterKernel": "coarseRaster", "fineRasterSingleKernel": "fineRaster", "fineRasterMultiKernel": "fineRaster"}
+            "coarseScatterKernel": "coarseRaster", "directAllocKernel": "binRaster", "directScatterKernel": "coarseRaster", "fineRasterSingleKernel": "fineRaster", "fineRasterMultiKernel": "fineRaster"}
 
 
 def main():
