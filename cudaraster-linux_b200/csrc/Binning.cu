@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(kThreads) directAllocKernel(const __grid_const
     const bool inside = t < f.numTiles;
     const int cnt = inside ? f.tileCounter[t] : 0;
     if (cnt != 0) f.tileCounter[t] = 0;   // clean for the next frame's setup
-    const bool active = inside && (cnt > 0 || f.deferredClear != 0);
+    // micro mode: every tile is active (a tile without queue entries may hold fragments in the visibility buffer) and
+    // the fine raster addresses tiles directly, numActiveTiles == numTiles
+    const bool active = inside && (cnt > 0 || f.deferredClear != 0 || f.microMode != 0);
     int blockSum, numActive;
     const int ofs = blockExclusiveScan256g(cnt, 0, s_warp, &blockSum);
     const int activeOfs = blockExclusiveScan256g(active ? 1 : 0, 0, s_warp, &numActive);
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, CRB_SCATTER_MIN_BLOCKS) directScatte
     if (threadIdx.x == 0) s_numLarge = 0;
     gridDepLaunchDependents();
     gridDepWait();
+    if (f.atomics->numTileEntries == 0) return;   // nothing was queued (every triangle went the micro way): final since directAllocKernel ended
     const int base = (blockIdx.x * kThreads + threadIdx.x) * kScatterTris;
     uint4 c4 = make_uint4(0, 0, 0, 0);
     if (base < f.numTris) c4 = __ldg(reinterpret_cast<const uint4*>(f.triTileCode + base));   // the buffer is padded to a multiple of 4 words

@@ -77,6 +77,8 @@ struct crb_ctx {
     DevBuf items, binItemBase, binItemCount, tileCountMat;
     DevBuf tileQueue, tileStart, tileCount, activeTiles, activeRecs;
     DevBuf tileCounter;                  // direct tile path: per-tile counters, zero between frames
+    DevBuf visBuffer;                    // micro-triangle visibility buffer (8 B / pixel), all ones between frames
+    size_t visBytes = 0;                 // extent the current surface uses
     DevBuf tileCursor;                   // direct tile path: per-tile queue cursors (alloc -> scatter)
     DevBuf triTileCode;                  // direct tile path: one word per input triangle (setup -> scatter)
     // Binning strategy (crb_set_binning_mode): the direct path runs when the pipe is order independent and the last
@@ -87,6 +89,7 @@ struct crb_ctx {
     int shapeNumLarge = 0;
     unsigned long long pendingShape[64] = {};
     bool lastFrameDirect = false;
+    bool microEnabled = true;            // CRB_MICRO=0 keeps small triangles on the tile queues (A/B measurements)
     DevBuf atomics;
     crb_atomics* hostAtomics = nullptr;  // pinned; slot 0 = synchronous draws, slots 1.. = ring of asynchronous frames
     int pending = 0;                     // asynchronous frames not yet checked by crb_finish
@@ -249,6 +252,7 @@ int prepareFrame(crb_ctx* c) {
     f.maxTileEntries = c->maxTileEntries;
     f.maxItems = c->maxItems;
     f.directMode = wantDirect(c) ? 1 : 0;
+    f.microMode = (f.directMode && c->samplesLog2 == 0 && c->microEnabled) ? 1 : 0;
     f.numSMs = c->numSMs;
     f.chainLaunches = c->chainLaunches ? 1 : 0;
     f.debugFlags = c->debugFlags;
@@ -276,6 +280,13 @@ int prepareFrame(crb_ctx* c) {
     CRB_CUDA(c, c->tileCounter.reserve(CR_MAXTILES_SQR * 4));
     if (oldTileCounter != c->tileCounter.ptr) c->needReset = true;
     CRB_CUDA(c, c->tileCursor.reserve(CR_MAXTILES_SQR * 4));
+    if (f.microMode) {
+        const void* oldVis = c->visBuffer.ptr;
+        const size_t need = (size_t)f.widthPixels * f.heightPixels * 8;
+        CRB_CUDA(c, c->visBuffer.reserve(need));
+        if (oldVis != c->visBuffer.ptr) c->needReset = true;
+        c->visBytes = std::max(c->visBytes, need);
+    }
     if (f.directMode) CRB_CUDA(c, c->triTileCode.reserve(((size_t)std::max(c->numTris, 1) + 4) * 4));
 
     f.triSubtris = (uint8_t*)c->triSubtris.ptr;
@@ -296,6 +307,7 @@ int prepareFrame(crb_ctx* c) {
     f.activeRecs = (int4*)c->activeRecs.ptr;
     f.tileCounter = (int32_t*)c->tileCounter.ptr;
     f.tileCursor = (int32_t*)c->tileCursor.ptr;
+    f.visBuffer = (unsigned long long*)c->visBuffer.ptr;
     f.triTileCode = (uint32_t*)c->triTileCode.ptr;
     f.atomics = (crb_atomics*)c->atomics.ptr + c->atomicsParity;
     f.nextAtomics = (crb_atomics*)c->atomics.ptr + (c->atomicsParity ^ 1);
@@ -315,6 +327,7 @@ int launchStages(crb_ctx* c, cudaStream_t s, cudaEvent_t* ev) {
         CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, c->binCountMat.cap, s));
         CRB_CUDA(c, cudaMemsetAsync(c->tileCountMat.ptr, 0, c->tileCountMat.cap, s));
         CRB_CUDA(c, cudaMemsetAsync(c->tileCounter.ptr, 0, c->tileCounter.cap, s));
+        if (c->visBuffer.ptr) CRB_CUDA(c, cudaMemsetAsync(c->visBuffer.ptr, 0xFF, c->visBuffer.cap, s));
         c->needReset = false;
     }
     // several setup CTAs per chunk ADD their bin counts into one column: that (large-scene) layout needs a zeroed matrix.
@@ -388,6 +401,8 @@ int crb_create(int device, crb_ctx** out) {
     c->chainLaunches = !(noPdl && noPdl[0] == '1');
     const char* direct = getenv("CRB_DIRECT");   // 0 / 1 / 2, see crb_set_binning_mode
     if (direct && direct[0] >= '0' && direct[0] <= '2') c->binningMode = direct[0] - '0';
+    const char* micro = getenv("CRB_MICRO");
+    if (micro && micro[0] == '0') c->microEnabled = false;
     const char* dbg = getenv("CRB_DEBUG_FLAGS");
     c->debugFlags = dbg ? atoi(dbg) : 0;
     if (cudaMallocHost((void**)&c->hostAtomics, sizeof(crb_atomics) * (1 + kAsyncRing)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
@@ -401,7 +416,7 @@ int crb_destroy(crb_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
-                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode};
+                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode, &c->visBuffer};
     for (DevBuf* b : bufs) b->release();
     if (c->hp.init) {
         cudaStreamDestroy(c->hp.up);

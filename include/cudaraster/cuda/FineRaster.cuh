@@ -316,8 +316,22 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     gridDepWait();
     finishFrameState(f);
     // {tile, queue start, queue count} in ONE load, issued together with the counters (the slot is
-    // always inside the buffer; it only holds a real record when activeIdx < numActiveTiles)
-    const int4 rec = __ldg(&f.activeRecs[activeIdx]);
+    // always inside the buffer; it only holds a real record when activeIdx < numActiveTiles).
+    // Micro mode: every tile is active, so the warp's tile is known up front and the loads of its queue extent
+    // and of its visibility-buffer entries (below) go out together -- one dependent round trip less per tile.
+    int4 rec;
+    unsigned long long* vis = nullptr;
+    unsigned long long v0 = ~0ull, v1 = ~0ull;
+    if (f.microMode != 0) {
+        const int t = min(activeIdx, f.numTiles - 1);
+        rec = make_int4(t, __ldg(&f.tileStart[t]), __ldg(&f.tileCount[t]), 0);
+        const int ty = t / f.widthTiles, tx = t - ty * f.widthTiles;
+        vis = f.visBuffer + (size_t)((ty << CR_TILE_LOG2) + (lane >> 3)) * f.widthPixels + (tx << CR_TILE_LOG2) + (lane & 7);
+        v0 = vis[0];
+        v1 = vis[(size_t)4 * f.widthPixels];
+    } else {
+        rec = __ldg(&f.activeRecs[activeIdx]);
+    }
     if (f.atomics->overflow != 0) return;
     if (activeIdx >= f.atomics->numActiveTiles) return;
 
@@ -352,6 +366,16 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     } else {
         color[0] = colorPtr[0]; color[1] = colorPtr[rowStep];
         depth[0] = kDepth ? depthPtr[0] : 0u; depth[1] = kDepth ? depthPtr[rowStep] : 0u;
+    }
+
+    if (deferred && kDepth && f.microMode != 0) {
+        // Micro-triangle visibility (TriangleSetup.cuh microRaster): the (depth, entry + 1) minimum over the triangles that
+        // setup rasterized itself (loaded at the top of the kernel).  It joins the tile state under the same rule as a
+        // queued fragment, and the buffer gets its neutral value back for the next frame.
+        if (v0 != ~0ull) vis[0] = ~0ull;
+        if (v1 != ~0ull) vis[(size_t)4 * f.widthPixels] = ~0ull;
+        if (v0 != ~0ull && (U32)(v0 >> 32) < depth[0]) { depth[0] = (U32)(v0 >> 32); winner[0] = (S32)(U32)v0 - 1; }
+        if (v1 != ~0ull && (U32)(v1 >> 32) < depth[1]) { depth[1] = (U32)(v1 >> 32); winner[1] = (S32)(U32)v1 - 1; }
     }
 
     // sample-space origin: centre of pixel (0,0) of the tile, viewport-centred subpixels

@@ -103,6 +103,12 @@ struct crb_frame {
     int32_t directMode;           // 1 = this frame runs setup -> directAlloc -> directScatter -> fine, queues unordered
     int32_t* tileCounter;         // [CR_MAXTILES_SQR] entries per tile, counted by setup, zeroed again by directAllocKernel
     int32_t* tileCursor;          // [CR_MAXTILES_SQR] end of the tile's queue extent, counted down by the scatter pass
+    // Micro-triangle visibility (single-sample direct frames): setup rasterizes triangles whose pixel footprint is at
+    // most 4x4 straight into this per-pixel buffer with 64-bit atomicMin on (depth << 32 | entry + 1) -- the same
+    // (depth, index) minimum the fine raster keeps -- and never queues them; the fine raster merges the buffer into
+    // its tile state and writes the neutral value (all ones) back, so the buffer is clean for the next frame.
+    int32_t microMode;            // 1 = on (implies directMode)
+    unsigned long long* visBuffer; // [heightPixels][widthPixels]
     uint32_t* triTileCode;        // [numTris] what the scatter pass needs to know about a triangle in ONE word: 0 = nothing to place,
                                   // CRB_TILECODE_GENERAL = go through triSubtris / the headers (clipped, refined or large), else
                                   // tile x0 | y0 << 8 | (nx-1) << 16 | (ny-1) << 17 | 1 << 31 of a footprint of at most 2x2 tiles

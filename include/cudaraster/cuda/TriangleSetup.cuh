@@ -73,7 +73,7 @@ __device__ __forceinline__ int prepareTriangle(const crb_frame& f, const Snapped
 // Writes one sub-triangle record and returns its packed header (for the bin histogram).
 template <int SamplesLog2, U32 RenderModeFlags>
 __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, uint4* td, int3 vidx, float4 v0, float4 v1, float4 v2,
-                                               float2 b0, float2 b1, float2 b2, const SnappedTri& s, int2 d1, int2 d2, S32 area) {
+                                               float2 b0, float2 b1, float2 b2, const SnappedTri& s, int2 d1, int2 d2, S32 area, uint3* zpOut = nullptr) {
     F32 areaRcp = 0.0f;
     int2 wv0 = make_int2(0, 0);
     if ((RenderModeFlags & (CRB_FLAG_DEPTH | CRB_FLAG_LERP)) != 0) {
@@ -107,6 +107,7 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
         }
         zp.z += zp.x * ((U32)f.subX0 << SamplesLog2) + zp.y * ((U32)f.subY0 << SamplesLog2);
         td[0] = make_uint4(zp.x, zp.y, zp.z, zslope);
+        if (zpOut) *zpOut = zp;
     }
 
     if ((RenderModeFlags & CRB_FLAG_LERP) != 0) {
@@ -137,6 +138,42 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
     return h;
 }
 
+// Micro-triangle path (crb_frame::microMode): a sub-triangle whose pixel-centre footprint is at most 4x4 pixels is
+// rasterized right here -- exact coverage of its <= 16 candidate pixels (the fine raster's own small-triangle
+// evaluation, FineRaster.cuh coverSmall4x4), plane depth per covered pixel, 64-bit atomicMin of
+// (depth << 32 | entry + 1) into the visibility buffer -- and is never queued.  Kept out of line so that its
+// registers do not weigh on the setup kernel.  (pxLo*, n*) = its pixel rectangle in surface pixels.
+static __device__ __noinline__ void microRaster(const crb_frame& f, uint4 h, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX, S32 pxLoY, int nx, int ny) {
+    const S32 x0 = (S32)(S16)(h.x & 0xFFFF), y0 = (S32)h.x >> 16;
+    const S32 x1 = (S32)(S16)(h.y & 0xFFFF), y1 = (S32)h.y >> 16;
+    const S32 x2 = (S32)(S16)(h.z & 0xFFFF), y2 = (S32)h.z >> 16;
+    // centre of pixel (pxLoX, pxLoY) in viewport-centred subpixels
+    const S32 px = (pxLoX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originX, py = (pxLoY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
+    const S32 dx0 = x1 - x0, dy0 = y1 - y0, dx1 = x2 - x1, dy1 = y2 - y1, dx2 = x0 - x2, dy2 = y0 - y2;
+    S32 e0 = (x0 - px) * dy0 - (y0 - py) * dx0 - ((dy0 > 0 || (dy0 == 0 && dx0 <= 0)) ? 1 : 0);
+    S32 e1 = (x1 - px) * dy1 - (y1 - py) * dx1 - ((dy1 > 0 || (dy1 == 0 && dx1 <= 0)) ? 1 : 0);
+    S32 e2 = (x0 - px) * dy2 - (y0 - py) * dx2 - ((dy2 > 0 || (dy2 == 0 && dx2 <= 0)) ? 1 : 0);
+    const S32 a0 = -(dy0 << CR_SUBPIXEL_LOG2), a1 = -(dy1 << CR_SUBPIXEL_LOG2), a2 = -(dy2 << CR_SUBPIXEL_LOG2);
+    const S32 b0 = dx0 << CR_SUBPIXEL_LOG2, b1 = dx1 << CR_SUBPIXEL_LOG2, b2 = dx2 << CR_SUBPIXEL_LOG2;
+    const unsigned long long id = (unsigned long long)(U32)(entry + 1);
+    unsigned long long* row = f.visBuffer + (size_t)pxLoY * f.widthPixels + pxLoX;
+    U32 zrow = zb + zx * (U32)pxLoX + zy * (U32)pxLoY;
+#pragma unroll 1
+    for (int r = 0; r < ny; r++) {
+        S32 t0 = e0, t1 = e1, t2 = e2;
+        U32 z = zrow;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (c < nx && (t0 | t1 | t2) >= 0) atomicMin(row + c, ((unsigned long long)z << 32) | id);
+            t0 += a0; t1 += a1; t2 += a2;
+            z += zx;
+        }
+        e0 += b0; e1 += b1; e2 += b2;
+        zrow += zy;
+        row += f.widthPixels;
+    }
+}
+
 // What binning needs from a finished sub-triangle (header h, stored in record `slot`).  General path: the bins it
 // touches go into the CTA's bin histogram.  Direct tile path (crb_frame::directMode): every tile it touches is
 // counted straight into the per-tile counters with fire-and-forget global reductions; sub-triangles that span
@@ -154,9 +191,19 @@ struct SetupShared {
 // DeferSmall: the caller counts a footprint of at most 2x2 tiles itself from the returned code.  (Unused: counting
 // warp-aggregated with __match_any_sync at the end of the kernel measured 37.6 vs 38.5 us on C2 but 225 vs 215 us on C4.)
 template <int SamplesLog2, bool DeferSmall>
-__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, SetupShared& sh) {
+__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, SetupShared& sh, S32 microEntry = -1, uint3 zp = make_uint3(0, 0, 0)) {
     int* s_binCount = sh.binCount;
     TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
+    if (SamplesLog2 == 0 && microEntry >= 0 && f.microMode) {
+        // a footprint of at most 4x4 pixel centres (and an extent that keeps the S32 edge functions exact) is rasterized now
+        const int nx = fp.pxHiX - fp.pxLoX + 1, ny = fp.pxHiY - fp.pxLoY + 1;
+        if (fp.empty) return 0;
+        const S32 ex = max(max(fp.x0, fp.x1), fp.x2) - min(min(fp.x0, fp.x1), fp.x2), ey = max(max(fp.y0, fp.y1), fp.y2) - min(min(fp.y0, fp.y1), fp.y2);
+        if (nx <= 4 && ny <= 4 && ex < (64 << CR_SUBPIXEL_LOG2) && ey < (64 << CR_SUBPIXEL_LOG2)) {
+            microRaster(f, h, zp.x, zp.y, zp.z, microEntry, fp.pxLoX, fp.pxLoY, nx, ny);
+            return 0;
+        }
+    }
     const CellRange t = cellRange<CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1);
     const bool large = (t.nx > CRB_DIRECT_MAX_TILES) | (t.ny > CRB_DIRECT_MAX_TILES);
     if (large) sh.sawLarge = 1;
@@ -315,9 +362,10 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
                     const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
                     f.triSubtris[tri] = (res == 0) ? 1 : 0;
                     if (res == 0) {
+                        uint3 zp = make_uint3(0, 0, 0);
                         uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
-                                                                              make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area);
-                        tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh);
+                                                                              make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area, &zp);
+                        tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh, (RenderModeFlags & CRB_FLAG_DEPTH) != 0 ? tri * 8 + 7 : -1, zp);
                     }
                     done = true;
                 }

@@ -176,7 +176,7 @@ def test_c2_full_size_properties(raster, crb):
     assert (cd < 0xFFFFBB3F).all()                                        # the mesh covers the whole frame
     c = raster.getCounters()
     assert raster.lastFrameDirect()                                       # automatic mode: second frame of a small-triangle shape
-    assert c["overflow"] == 0 and c["numActiveTiles"] == 240 * 135 and c["numTileEntries"] > 900000 and c["numLargeTris"] == 0
+    assert c["overflow"] == 0 and c["numLargeTris"] == 0 and c["numBinEntries"] == 0
     g = util.draw_gold(v, i, w, h, "gouraud", 3)
     _check_surfaces(cc, cd, g, lsb=1)
 
