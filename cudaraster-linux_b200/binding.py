@@ -252,7 +252,8 @@ class CudaRaster:
         self._check(self.lib.crb_set_index_buffer(self.ctx, buf.data_ptr() + ofs, int(num_tris)))
 
     def setBinningMode(self, mode):
-        """0 = general path only, 1 = automatic (default), 2 = try the direct tile path on every eligible frame."""
+        """0 = general path only, 1 = automatic (default), 2 = direct tile path on every eligible frame, 3 = like 2 without the
+        micro-triangle visibility buffer."""
         self._check(self.lib.crb_set_binning_mode(self.ctx, int(mode)))
 
     def lastFrameDirect(self):

@@ -89,6 +89,7 @@ struct crb_ctx {
     int shapeNumLarge = 0;
     unsigned long long pendingShape[64] = {};
     bool lastFrameDirect = false;
+    bool microOff = false;               // crb_set_binning_mode(3)
     bool microEnabled = true;            // CRB_MICRO=0 keeps small triangles on the tile queues (A/B measurements)
     DevBuf atomics;
     crb_atomics* hostAtomics = nullptr;  // pinned; slot 0 = synchronous draws, slots 1.. = ring of asynchronous frames
@@ -252,7 +253,7 @@ int prepareFrame(crb_ctx* c) {
     f.maxTileEntries = c->maxTileEntries;
     f.maxItems = c->maxItems;
     f.directMode = wantDirect(c) ? 1 : 0;
-    f.microMode = (f.directMode && c->samplesLog2 == 0 && c->microEnabled) ? 1 : 0;
+    f.microMode = (f.directMode && c->samplesLog2 == 0 && c->microEnabled && !c->microOff) ? 1 : 0;
     f.numSMs = c->numSMs;
     f.chainLaunches = c->chainLaunches ? 1 : 0;
     f.debugFlags = c->debugFlags;
@@ -542,8 +543,9 @@ int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
 }
 
 int crb_set_binning_mode(crb_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 2) return CRB_ERR_INVALID;
-    c->binningMode = mode;
+    if (!c || mode < 0 || mode > 3) return CRB_ERR_INVALID;
+    c->binningMode = mode == 3 ? 2 : mode;
+    c->microOff = mode == 3;
     c->shapeValid = false;
     return CRB_OK;
 }

@@ -136,7 +136,12 @@ int crb_set_subviewport(crb_ctx* ctx, int fullWidth, int fullHeight, int x0, int
  * of small triangles (a triangle spanning more than CRB_DIRECT_MAX_TILES tiles on an axis is handled by a whole CTA
  * at a time, correct but slower than the bins of the general path).  mode 0 = never, 1 = automatic (default: direct
  * when the last completed frame of the same shape -- triangle count, surface, window, pipe -- had no such triangle),
- * 2 = direct on every frame whose pipe allows it.  Surfaces are bit-identical on both paths. */
+ * 2 = direct on every frame whose pipe allows it, 3 = like 2 but without the micro-triangle visibility buffer (below;
+ * a testing aid).  Surfaces are bit-identical on all paths.
+ * Micro-triangles: on single-sample direct frames, triangle setup rasterizes every triangle whose pixel-centre
+ * footprint is at most 4x4 pixels itself -- exact coverage, plane depth, one 64-bit atomicMin of (depth << 32 | index)
+ * per covered pixel into a per-pixel visibility buffer -- and never queues it; the fine raster merges the buffer
+ * into its tile state under the same (depth, index) rule and restores it. */
 #define CRB_DIRECT_MAX_TILES 4
 int crb_set_binning_mode(crb_ctx* ctx, int mode);
 /* 1 when the last frame ran on the direct path. */

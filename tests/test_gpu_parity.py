@@ -369,12 +369,20 @@ def test_direct_tile_path_matches_oracle(raster, crb, shader, flags, samples_log
             if shader == "passthrough":
                 v = np.ascontiguousarray(v[:, :4])
             g = util.draw_gold(v, i, w, h, shader, flags, samples_log2, blend)
-            for mode in (2, 0):
+            queued = None
+            for mode in (3, 2, 0):   # direct with tile queues only, direct + micro-triangle buffer, general
                 raster.setBinningMode(mode)
                 cc, cd = util.draw_cuda(raster, crb, v, i, w, h, shader, flags, samples_log2, blend)
-                assert raster.lastFrameDirect() == (mode == 2), "%s: wrong path (mode %d)" % (name, mode)
+                assert raster.lastFrameDirect() == (mode != 0), "%s: wrong path (mode %d)" % (name, mode)
                 c = raster.getCounters()
-                assert c["overflow"] == 0 and (c["numBinEntries"] == 0) == (mode == 2)
+                assert c["overflow"] == 0 and (c["numBinEntries"] == 0) == (mode != 0)
+                if mode == 3:
+                    queued = c["numTileEntries"]
+                    assert queued > 10000                                  # everything went through the tile queues
+                elif mode == 2 and samples_log2 == 0:
+                    assert c["numTileEntries"] < queued, name            # part of the triangles went the micro way instead
+                elif mode == 2:
+                    assert c["numTileEntries"] == queued                   # MSAA: no micro path
                 _check_surfaces(cc, cd, g, lsb=0 if shader == "passthrough" else 1)
     finally:
         raster.setBinningMode(1)
@@ -392,11 +400,13 @@ def test_direct_tile_path_large_triangles_and_auto(raster, crb):
     vb = np.concatenate([v, big]); ib = np.concatenate([i[:1000], np.array([[nv, nv + 1, nv + 2]], np.int32), i[1000:], np.array([[nv + 3, nv + 4, nv + 5]], np.int32)])
     vs, js = crb.scenes.random_soup(5000, seed=1234, stride_floats=8)   # big, clipped and w<=0 triangles
     try:
-        raster.setBinningMode(2)
-        for vv, ii in ((vb, ib), (vs, js)):
+        for mode, vv, ii in ((2, vb, ib), (2, vs, js), (3, vb, ib), (3, vs, js)):
+            raster.setBinningMode(mode)
             cc, cd = util.draw_cuda(raster, crb, vv, ii, w, h, "gouraud", 3)
             assert raster.lastFrameDirect() and raster.getCounters()["numLargeTris"] > 0
             _check_surfaces(cc, cd, util.draw_gold(vv, ii, w, h, "gouraud", 3), lsb=1)
+        raster.setBinningMode(2)
+        for vv, ii in ((vb, ib), (vs, js)):
             cc, cd = util.draw_cuda(raster, crb, vv, ii, w, h, "gouraud", 3, 2)
             assert raster.lastFrameDirect()
             _check_surfaces(cc, cd, util.draw_gold(vv, ii, w, h, "gouraud", 3, 2), lsb=1)
@@ -416,6 +426,31 @@ def test_direct_tile_path_large_triangles_and_auto(raster, crb):
             assert not raster.lastFrameDirect()
         _check_surfaces(cc, cd, util.draw_gold(vb, ib, w, h, "gouraud", 3), lsb=1)
     finally:
+        raster.setBinningMode(1)
+
+
+def test_direct_tile_path_sort_first_windows(raster, crb):
+    """Sort-first windows on the direct path (micro-triangles included): every window equals its part of the full
+    frame rendered on the general path, for a mesh of small triangles with a few large ones crossing the seams."""
+    fw, fh = 512, 384
+    v, i = crb.scenes.grid_gouraud(200, 150)
+    big = np.array([[-0.7, -0.9, 0.6, 1, 1, 0, 0, 1], [0.8, -0.2, 0.6, 1, 0, 1, 0, 1], [-0.1, 0.8, 0.6, 1, 0, 0, 1, 1]], np.float32)
+    nv = v.shape[0]
+    v = np.concatenate([v, big]); i = np.concatenate([i, np.array([[nv, nv + 1, nv + 2]], np.int32)])
+    try:
+        raster.setBinningMode(0)
+        full_c, full_d = util.draw_cuda(raster, crb, v, i, fw, fh, "gouraud", 3)
+        _check_surfaces(full_c, full_d, util.draw_gold(v, i, fw, fh, "gouraud", 3), lsb=1)
+        for mode in (2, 3):
+            raster.setBinningMode(mode)
+            for (x0, y0, w, h) in [(0, 0, 256, 192), (256, 0, 256, 192), (0, 192, 256, 192), (256, 192, 256, 192), (128, 96, 200, 120)]:
+                cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0))
+                assert raster.lastFrameDirect()
+                rh, rw = cd.shape
+                assert np.array_equal(cd[:h, :w], full_d[y0:y0 + h, x0:x0 + w]) and np.array_equal(cc[:h, :w], full_c[y0:y0 + h, x0:x0 + w])
+                _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0)), lsb=1)
+    finally:
+        raster.setSubViewport(0, 0, 0, 0)
         raster.setBinningMode(1)
 
 
