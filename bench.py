@@ -125,7 +125,7 @@ def cpu_oracle_frame(verts, idx, w, h, shader, s_log2, flags, threads, want_coun
     return time.perf_counter() - t0, r
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     """The CPU restatement of the path on the host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
@@ -149,7 +149,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -180,8 +180,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL's version banner,
+    # nvcc of the reference-kernel harness) are pointed at stderr; emit() writes the line to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -373,7 +382,7 @@ def main():
                     pass
         if not args.no_ref_kernels and world == 1:
             line["ref_kernels"] = time_ref_kernels(args.workload)
-        print(json.dumps(line))
+        emit(line)
     raster.close()
     if world > 1:
         dist.barrier()

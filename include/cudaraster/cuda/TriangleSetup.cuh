@@ -73,7 +73,10 @@ __device__ __forceinline__ int prepareTriangle(const crb_frame& f, const Snapped
 // Writes one sub-triangle record and returns its packed header (for the bin histogram).
 template <int SamplesLog2, U32 RenderModeFlags>
 __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, uint4* td, int3 vidx, float4 v0, float4 v1, float4 v2,
-                                               float2 b0, float2 b1, float2 b2, const SnappedTri& s, int2 d1, int2 d2, S32 area, uint3* zpOut = nullptr) {
+                                               float2 b0, float2 b1, float2 b2, const SnappedTri& s, int2 d1, int2 d2, S32 area, uint3* zpOut = nullptr,
+                                               bool microOnly = false) {
+    // microOnly: the triangle is rasterized by setup itself (micro mode) and never queued, so nothing will read its header
+    // or its depth-plane row: only the shading rows (w/u/v planes, vertex ids) are produced.
     F32 areaRcp = 0.0f;
     int2 wv0 = make_int2(0, 0);
     if ((RenderModeFlags & (CRB_FLAG_DEPTH | CRB_FLAG_LERP)) != 0) {
@@ -95,7 +98,7 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
         zvert.z = __fmaf_rn(__fmul_rn(v2.z, zcoef), s.rcpW.z, zbias);
         int2 zv0 = make_int2(wv0.x - (1 << (CR_SUBPIXEL_LOG2 - SamplesLog2 - 1)), wv0.y - (1 << (CR_SUBPIXEL_LOG2 - SamplesLog2 - 1)));
         uint3 zp = setupPleq(zvert, zv0, d1, d2, areaRcp, SamplesLog2);
-        zmin = f32ToU32SatRni(__fsub_rn(fminf(fminf(zvert.x, zvert.y), zvert.z), (F32)CR_LERP_ERROR(SamplesLog2)));
+        if (!microOnly) zmin = f32ToU32SatRni(__fsub_rn(fminf(fminf(zvert.x, zvert.y), zvert.z), (F32)CR_LERP_ERROR(SamplesLog2)));
         U32 zslope = 0;
         if (SamplesLog2 != 0) {
             S32 ax = (S32)zp.x; ax = ax >= 0 ? ax : -ax;
@@ -106,7 +109,7 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
             if ((zslope >> k) != tmp) zslope = FW_U32_MAX;
         }
         zp.z += zp.x * ((U32)f.subX0 << SamplesLog2) + zp.y * ((U32)f.subY0 << SamplesLog2);
-        td[0] = make_uint4(zp.x, zp.y, zp.z, zslope);
+        if (!microOnly) td[0] = make_uint4(zp.x, zp.y, zp.z, zslope);
         if (zpOut) *zpOut = zp;
     }
 
@@ -129,6 +132,7 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
         td[3] = make_uint4(0u, (U32)vidx.x, (U32)vidx.y, (U32)vidx.z);
     }
 
+    if (microOnly) return make_uint4(0, 0, 0, 0);
     const U32 f01 = cover8x8_selectFlips(d1.x, d1.y);
     const U32 f12 = cover8x8_selectFlips(d2.x - d1.x, d2.y - d1.y);
     const U32 f20 = cover8x8_selectFlips(-d2.x, -d2.y);
@@ -142,11 +146,10 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
 // rasterized right here -- exact coverage of its <= 16 candidate pixels (the fine raster's own small-triangle
 // evaluation, FineRaster.cuh coverSmall4x4), plane depth per covered pixel, 64-bit atomicMin of
 // (depth << 32 | entry + 1) into the visibility buffer -- and is never queued.  Kept out of line so that its
-// registers do not weigh on the setup kernel.  (pxLo*, n*) = its pixel rectangle in surface pixels.
-static __device__ __noinline__ void microRaster(const crb_frame& f, uint4 h, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX, S32 pxLoY, int nx, int ny) {
-    const S32 x0 = (S32)(S16)(h.x & 0xFFFF), y0 = (S32)h.x >> 16;
-    const S32 x1 = (S32)(S16)(h.y & 0xFFFF), y1 = (S32)h.y >> 16;
-    const S32 x2 = (S32)(S16)(h.z & 0xFFFF), y2 = (S32)h.z >> 16;
+// registers do not weigh on the setup kernel.  (x*, y*) = snapped vertices, viewport-centred subpixels (what the
+// header would hold); (pxLo*, n*) = its pixel rectangle in surface pixels.
+static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 y0, S32 x1, S32 y1, S32 x2, S32 y2, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX,
+                                                S32 pxLoY, int nx, int ny) {
     // centre of pixel (pxLoX, pxLoY) in viewport-centred subpixels
     const S32 px = (pxLoX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originX, py = (pxLoY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
     const S32 dx0 = x1 - x0, dy0 = y1 - y0, dx1 = x2 - x1, dy1 = y2 - y1, dx2 = x0 - x2, dy2 = y0 - y2;
@@ -191,19 +194,9 @@ struct SetupShared {
 // DeferSmall: the caller counts a footprint of at most 2x2 tiles itself from the returned code.  (Unused: counting
 // warp-aggregated with __match_any_sync at the end of the kernel measured 37.6 vs 38.5 us on C2 but 225 vs 215 us on C4.)
 template <int SamplesLog2, bool DeferSmall>
-__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, SetupShared& sh, S32 microEntry = -1, uint3 zp = make_uint3(0, 0, 0)) {
+__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, SetupShared& sh) {
     int* s_binCount = sh.binCount;
     TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
-    if (SamplesLog2 == 0 && microEntry >= 0 && f.microMode) {
-        // a footprint of at most 4x4 pixel centres (and an extent that keeps the S32 edge functions exact) is rasterized now
-        const int nx = fp.pxHiX - fp.pxLoX + 1, ny = fp.pxHiY - fp.pxLoY + 1;
-        if (fp.empty) return 0;
-        const S32 ex = max(max(fp.x0, fp.x1), fp.x2) - min(min(fp.x0, fp.x1), fp.x2), ey = max(max(fp.y0, fp.y1), fp.y2) - min(min(fp.y0, fp.y1), fp.y2);
-        if (nx <= 4 && ny <= 4 && ex < (64 << CR_SUBPIXEL_LOG2) && ey < (64 << CR_SUBPIXEL_LOG2)) {
-            microRaster(f, h, zp.x, zp.y, zp.z, microEntry, fp.pxLoX, fp.pxLoY, nx, ny);
-            return 0;
-        }
-    }
     const CellRange t = cellRange<CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1);
     const bool large = (t.nx > CRB_DIRECT_MAX_TILES) | (t.ny > CRB_DIRECT_MAX_TILES);
     if (large) sh.sawLarge = 1;
@@ -362,10 +355,26 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
                     const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
                     f.triSubtris[tri] = (res == 0) ? 1 : 0;
                     if (res == 0) {
-                        uint3 zp = make_uint3(0, 0, 0);
-                        uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
-                                                                              make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area, &zp);
-                        tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh, (RenderModeFlags & CRB_FLAG_DEPTH) != 0 ? tri * 8 + 7 : -1, zp);
+                        // Micro mode: a footprint of at most 4x4 pixel centres (and an extent that keeps the S32 edge functions of
+                        // microRaster exact) is rasterized right here and never queued; one without any pixel centre inside the
+                        // surface is dropped.  Same pixel range as triFootprint (Overlap.cuh).
+                        bool micro = false, nothing = false;
+                        S32 pxLoX = 0, pxLoY = 0, pxHiX = 0, pxHiY = 0;
+                        if (SamplesLog2 == 0 && (RenderModeFlags & CRB_FLAG_DEPTH) != 0 && f.microMode) {
+                            pxLoX = max((s.lo.x + f.originX + 7) >> CR_SUBPIXEL_LOG2, 0);
+                            pxLoY = max((s.lo.y + f.originY + 7) >> CR_SUBPIXEL_LOG2, 0);
+                            pxHiX = min((s.hi.x + f.originX - 8) >> CR_SUBPIXEL_LOG2, f.widthPixels - 1);
+                            pxHiY = min((s.hi.y + f.originY - 8) >> CR_SUBPIXEL_LOG2, f.heightPixels - 1);
+                            nothing = (pxLoX > pxHiX) | (pxLoY > pxHiY);
+                            micro = !nothing & (pxHiX - pxLoX < 4) & (pxHiY - pxLoY < 4) & (s.hi.x - s.lo.x < (64 << CR_SUBPIXEL_LOG2)) & (s.hi.y - s.lo.y < (64 << CR_SUBPIXEL_LOG2));
+                        }
+                        if (!nothing) {
+                            uint3 zp = make_uint3(0, 0, 0);
+                            uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
+                                                                                  make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area, &zp, micro);
+                            if (micro) microRaster(f, s.p0.x, s.p0.y, s.p1.x, s.p1.y, s.p2.x, s.p2.y, zp.x, zp.y, zp.z, tri * 8 + 7, pxLoX, pxLoY, pxHiX - pxLoX + 1, pxHiY - pxLoY + 1);
+                            else tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh);
+                        }
                     }
                     done = true;
                 }
