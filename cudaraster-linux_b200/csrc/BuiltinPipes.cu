@@ -125,6 +125,14 @@ CRB_GOURAUD_DISCARD(0, 7, BlendReplace)
 CRB_TEXPHONG(0, 3, BlendReplace)
 CRB_TEXPHONG(2, 3, BlendReplace)
 
+// ---- ProfilingMode_Counters variants (reference: -DCR_PROFILING_MODE=ProfilingMode_Counters, test/SceneCR.cpp:170-177) ----
+#undef CR_PROFILING_MODE
+#define CR_PROFILING_MODE ProfilingMode_Counters
+CRB_PIPE(gouraudCounters, ShadedVertex_gouraud, FragmentShader_gouraud, BlendReplace, 0, 3)
+CRB_PIPE(gouraudCounters, ShadedVertex_gouraud, FragmentShader_gouraud, BlendReplace, 2, 3)
+#undef CR_PROFILING_MODE
+#define CR_PROFILING_MODE ProfilingMode_Default
+
 // ---- vertex shaders ----------------------------------------------------------------
 // The demo's pass-through vertex shader (test/shader/PassThrough.cu:16-35): clipPos = posToClip * (modelPos, 1).
 // The matrix-vector product is spelled as the fma chain nvcc contracts the reference's generic

@@ -77,6 +77,8 @@ struct crb_ctx {
     DevBuf items, binItemBase, binItemCount, tileCountMat;
     DevBuf tileQueue, tileStart, tileCount, activeTiles, activeRecs;
     DevBuf tileCounter;                  // direct tile path: per-tile counters, zero between frames
+    DevBuf profCounters;                 // ProfilingMode_Counters: CRB_PROF_NUM numerator / denominator pairs
+    unsigned long long hostProf[2 * CRB_PROF_NUM] = {};
     DevBuf visBuffer;                    // micro-triangle visibility buffer (8 B / pixel), all ones between frames
     size_t visBytes = 0;                 // extent the current surface uses
     DevBuf tileCursor;                   // direct tile path: per-tile queue cursors (alloc -> scatter)
@@ -164,6 +166,7 @@ unsigned long long frameShape(const crb_ctx* c) {
 
 bool wantDirect(const crb_ctx* c) {
     if (c->binningMode == 0 || !c->hasPipe || !c->pipe.orderIndependent) return false;
+    if (c->spec.profilingMode != ProfilingMode_Default) return false;   // the counters describe the ordered two-level path
     if (c->binningMode == 2) return true;
     return c->shapeValid && c->shapeHash == frameShape(c) && c->shapeNumLarge == 0;
 }
@@ -281,6 +284,8 @@ int prepareFrame(crb_ctx* c) {
     CRB_CUDA(c, c->tileCounter.reserve(CR_MAXTILES_SQR * 4));
     if (oldTileCounter != c->tileCounter.ptr) c->needReset = true;
     CRB_CUDA(c, c->tileCursor.reserve(CR_MAXTILES_SQR * 4));
+    CRB_CUDA(c, c->profCounters.reserve(2 * CRB_PROF_NUM * sizeof(unsigned long long)));
+    f.profCounters = (unsigned long long*)c->profCounters.ptr;
     if (f.microMode) {
         const void* oldVis = c->visBuffer.ptr;
         const size_t need = (size_t)f.widthPixels * f.heightPixels * 8;
@@ -334,6 +339,7 @@ int launchStages(crb_ctx* c, cudaStream_t s, cudaEvent_t* ev) {
     // several setup CTAs per chunk ADD their bin counts into one column: that (large-scene) layout needs a zeroed matrix.
     // (Letting the bin scatter zero the cells it reads was measured 3x slower than this memset: 466 vs 169 us on C4.)
     if (f->numTris > 0 && f->ctasPerChunk > 1 && !f->directMode) CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, (size_t)f->matPitch * f->numBins * 4, s));
+    if (c->spec.profilingMode == ProfilingMode_Counters) CRB_CUDA(c, cudaMemsetAsync(c->profCounters.ptr, 0, 2 * CRB_PROF_NUM * sizeof(unsigned long long), s));
     c->needReset = true;   // until every launch of this frame went through
     if (ev) CRB_CUDA(c, cudaEventRecord(ev[0], s));
     int rc = c->pipe.triangleSetup(f, s);
@@ -417,7 +423,7 @@ int crb_destroy(crb_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
-                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode, &c->visBuffer};
+                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode, &c->visBuffer, &c->profCounters};
     for (DevBuf* b : bufs) b->release();
     if (c->hp.init) {
         cudaStreamDestroy(c->hp.up);
@@ -803,6 +809,38 @@ int crb_get_profiling_info(crb_ctx* c, char* buf, size_t bufSize) {
     const float total = st[0] + st[1] + st[2] + st[3];
     const float pct = total > 0.0f ? 100.0f / total : 0.0f;
     char line[256];
+    if (c->spec.profilingMode == ProfilingMode_Counters && c->hasPipe && c->drawn) {
+        // ProfilingMode_Counters report (CudaRaster.cpp:424-450): the reference's format strings for the counters that exist
+        // in this pipeline; bin / coarse lines come from the frame counters (their reference counters describe its own
+        // round / segment / merge loops).
+        CRB_CUDA(c, cudaDeviceSynchronize());
+        CRB_CUDA(c, cudaMemcpy(c->hostProf, c->profCounters.ptr, sizeof(c->hostProf), cudaMemcpyDeviceToHost));
+        auto ratio = [&](int k) { return (double)c->hostProf[2 * k] / std::max((double)c->hostProf[2 * k + 1], 1.0); };
+        s += "ProfilingMode_Counters\n----------------------\n\n";
+        s += "TriangleSetup:\n";
+        snprintf(line, sizeof(line), "- Viewport cull        %.1f%%\n", ratio(CRB_PROF_SetupViewportCull)); s += line;
+        snprintf(line, sizeof(line), "- Backface cull        %.1f%%\n", ratio(CRB_PROF_SetupBackfaceCull)); s += line;
+        snprintf(line, sizeof(line), "- Between pixels cull  %.1f%%\n", ratio(CRB_PROF_SetupBetweenPixelsCull)); s += line;
+        snprintf(line, sizeof(line), "- Clipped              %.1f%%\n", ratio(CRB_PROF_SetupClipped)); s += line;
+        snprintf(line, sizeof(line), "- Avg. samples / tri   %.2f\n\n", ratio(CRB_PROF_SetupSamplesPerTri)); s += line;
+        s += "BinRaster:\n";
+        snprintf(line, sizeof(line), "- Bin queue entries    %d\n", a.numBinEntries); s += line;
+        snprintf(line, sizeof(line), "- Entries / sub-tri    %.2f\n\n", (double)a.numBinEntries / std::max(a.numSubtris, 1)); s += line;
+        s += "CoarseRaster:\n";
+        snprintf(line, sizeof(line), "- Work items           %d\n", a.numCoarseItems); s += line;
+        snprintf(line, sizeof(line), "- Emits / Triangle     %.2f\n\n", (double)a.numTileEntries / std::max(a.numBinEntries, 1)); s += line;
+        s += "FineRaster:\n- Triangles culled\n";
+        snprintf(line, sizeof(line), "  - Early Z kill       %.1f%%\n", ratio(CRB_PROF_FineEarlyZCull)); s += line;
+        snprintf(line, sizeof(line), "  - Empty coverage     %.1f%%\n", ratio(CRB_PROF_FineEmptyCull)); s += line;
+        snprintf(line, sizeof(line), "- Z kills              %.1f%%\n", ratio(CRB_PROF_FineZKill)); s += line;
+        snprintf(line, sizeof(line), "- MSAA kills           %.1f%%\n", ratio(CRB_PROF_FineMSAAKill)); s += line;
+        snprintf(line, sizeof(line), "- Avg. tri/tile        %.0f\n", ratio(CRB_PROF_FineTriPerTile)); s += line;
+        snprintf(line, sizeof(line), "- Avg. frag/tri        %.1f\n", ratio(CRB_PROF_FineFragPerTri)); s += line;
+        snprintf(line, sizeof(line), "- Avg. frag/tile       %.0f\n", ratio(CRB_PROF_FineFragPerTile)); s += line;
+        s += "\n";
+        snprintf(buf, bufSize, "%s", s.c_str());
+        return CRB_OK;
+    }
     s += "ProfilingMode_Default\n---------------------\n\n";
     const char* names[4] = {"triangleSetup", "binRaster", "coarseRaster", "fineRaster"};
     for (int i = 0; i < 4; i++) {

@@ -191,7 +191,8 @@ int crb_set_stage_timing(crb_ctx* ctx, int enable);
 int crb_get_stage_timing(crb_ctx* ctx, double outMeanMs[4], int* outFrames);
 /* g_crAtomics read-back (CudaRaster.cpp:326). */
 int crb_get_counters(crb_ctx* ctx, crb_atomics* out);
-/* CudaRaster::getProfilingInfo, ProfilingMode_Default report (CudaRaster.cpp:367-422). */
+/* CudaRaster::getProfilingInfo (CudaRaster.cpp:367-497): the ProfilingMode_Default report, or -- for a pipe compiled with
+ * -DCR_PROFILING_MODE=ProfilingMode_Counters -- the counters report (the reference's counters that exist in this pipeline). */
 int crb_get_profiling_info(crb_ctx* ctx, char* buf, size_t bufSize);
 /* Number of kernels the last crb_draw_triangles enqueued (all retries included). */
 int crb_get_launch_count(crb_ctx* ctx);

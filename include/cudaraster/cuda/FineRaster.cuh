@@ -304,7 +304,7 @@ struct FineBatch {
 // are still applied by one thread in submission order.
 //------------------------------------------------------------------------------------------------
 
-template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
+template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER_SM / CRB_FINE_WARPS) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
     __shared__ FineBatch s_batch[CRB_FINE_WARPS];
 
@@ -381,6 +381,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     // sample-space origin: centre of pixel (0,0) of the tile, viewport-centred subpixels
     const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
     const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
+    U32 profFrags = 0, profZTests = 0, profZKills = 0;   // ProfilingMode_Counters only
 
     for (int base = 0; base < queueCount; base += 32) {
         // ---- issue the loads of the batches ahead
@@ -411,6 +412,17 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
                 S32 a[3], b[3], c[3];
                 setupTileEdges(cur.h, bx, by, a, b, c);
                 coverTileRows(a, b, c, rowLo, rowHi, maskLo, maskHi);
+            }
+            if (ProfMode == ProfilingMode_Counters) {   // reference: FineRaster.inl:235, :621-622
+                const bool fetched = cur.entry >= 0;
+                const bool earlyZ = fetched && kDepth && !(zminHdr < tileZMax || (f.directMode != 0 && zminHdr == tileZMax));
+                const bool considered = fetched && !earlyZ;
+                profCountWarp<ProfMode>(f, CRB_PROF_FineEarlyZCull, earlyZ, fetched);
+                profCountWarp<ProfMode>(f, CRB_PROF_FineEmptyCull, considered && (maskLo | maskHi) == 0, considered);
+                const U32 frags = __reduce_add_sync(0xFFFFFFFFu, (U32)(__popc(maskLo) + __popc(maskHi)));
+                const U32 tris = __popc(__ballot_sync(0xFFFFFFFFu, considered));
+                if (lane == 0) profCount<ProfMode>(f, CRB_PROF_FineFragPerTri, frags, tris);
+                profFrags += frags;
             }
         }
         if (kDepth) {
@@ -444,6 +456,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
                 if (kDepth) {
                     z = sb.zb[j] + sb.zx[j] * (U32)lx + sb.zy[j] * (U32)(ly + 4 * p);
                     zkill = z >= depth[p];
+                    if (ProfMode == ProfilingMode_Counters && covered) { profZTests++; profZKills += zkill ? 1 : 0; }
                     // Direct path: the queue is unordered, the survivor of a pixel is the (depth, submission index)
                     // minimum -- what the strict LESS test leaves when fragments arrive in submission order.  A tie
                     // with the depth the tile started with (winner < 0) still fails.
@@ -509,6 +522,17 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         runBlendShader(bs1, e1 >> 3, pixelX, pixelY0 + 4, 0, fs1.m_color, 0u);
         if (winner[0] >= 0 && bs0.m_writeColor) color[0] = bs0.m_color;
         if (winner[1] >= 0 && bs1.m_writeColor) color[1] = bs1.m_color;
+    }
+
+    if (ProfMode == ProfilingMode_Counters) {   // reference: FineRaster.inl:221, :684, :702, :733-734
+        __syncwarp();
+        const U32 zt = __reduce_add_sync(0xFFFFFFFFu, profZTests), zk = __reduce_add_sync(0xFFFFFFFFu, profZKills);
+        if (lane == 0) {
+            profCount<ProfMode>(f, CRB_PROF_FineZKill, 100ull * zk, zt);
+            profCount<ProfMode>(f, CRB_PROF_FineTriPerTile, (U32)queueCount, 1);
+            profCount<ProfMode>(f, CRB_PROF_FineFragPerTile, profFrags, 1);
+            profCount<ProfMode>(f, CRB_PROF_SetupSamplesPerTri, profFrags, 0);
+        }
     }
 
     colorPtr[0] = color[0];

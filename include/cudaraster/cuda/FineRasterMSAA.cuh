@@ -56,7 +56,7 @@ struct FineBatchMSAA {
 // mask is a superset of the pixels with a covered sample -- two warp transposes hand every lane
 // the triangles touching its two pixels, and the ownership loop tests the N samples of those
 // fragments exactly, in queue order.
-template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
+template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fineRasterMultiKernel(const __grid_constant__ crb_frame f) {
     constexpr int N = 1 << SamplesLog2;
     constexpr int kWarps = FineWarps<SamplesLog2>::Value;
@@ -123,6 +123,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
     // quads mode: the reference kernel's tileDepth[pixel] -- CR_DEPTH_MAX until the pixel's first ROP of this
     // draw, then the maximum over its samples (FineRaster.inl:934-935, :1101-1108)
     U32 pixZMax[2] = {CR_DEPTH_MAX, CR_DEPTH_MAX};
+    U32 profFrags = 0, profSamples = 0, profZTests = 0, profZKills = 0, profMsaaKills = 0;   // ProfilingMode_Counters only
 
     for (int base = 0; base < queueCount; base += 32) {
         FineFetch nxt;
@@ -157,6 +158,17 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
                 coverTileRows(a, b, cr, rowLo, rowHi, maskLo, maskHi);
             }
         }
+        if (ProfMode == ProfilingMode_Counters) {   // reference: FineRaster.inl:235, :969-970 (pixel mask = conservative coverage)
+            const bool fetched = cur.entry >= 0;
+            const bool earlyZ = fetched && kDepth && !((cur.h.w & 0xFFFFF000u) < tileZMax || (f.directMode != 0 && (cur.h.w & 0xFFFFF000u) == tileZMax));
+            const bool considered = fetched && !earlyZ;
+            profCountWarp<ProfMode>(f, CRB_PROF_FineEarlyZCull, earlyZ, fetched);
+            profCountWarp<ProfMode>(f, CRB_PROF_FineEmptyCull, considered && (maskLo | maskHi) == 0, considered);
+            const U32 frags = __reduce_add_sync(0xFFFFFFFFu, (U32)(__popc(maskLo) + __popc(maskHi)));
+            const U32 tris = __popc(__ballot_sync(0xFFFFFFFFu, considered));
+            if (lane == 0) profCount<ProfMode>(f, CRB_PROF_FineFragPerTri, frags, tris);
+            profFrags += frags;
+        }
         if (kDepth) {
             sb.zx[lane] = cur.z.x; sb.zy[lane] = cur.z.y;
             sb.zb[lane] = cur.z.z + cur.z.x * (U32)(tileX << (CR_TILE_LOG2 + SamplesLog2)) + cur.z.y * (U32)(tileY << (CR_TILE_LOG2 + SamplesLog2));
@@ -188,6 +200,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
                 const S32 ea[3] = {sb.a0[j], sb.a1[j], sb.a2[j]}, eb[3] = {sb.b0[j], sb.b1[j], sb.b2[j]};
                 const S32 ec[3] = {sb.c0[j] + ea[0] * sx0 + eb[0] * sy, sb.c1[j] + ea[1] * sx0 + eb[1] * sy, sb.c2[j] + ea[2] * sx0 + eb[2] * sy};
                 const U32 cov = pixelSampleMask<SamplesLog2>(ea, eb, ec);
+                if (ProfMode == ProfilingMode_Counters && ((cover[p] >> j) & 1)) { profMsaaKills += cov == 0 ? 1 : 0; profSamples += __popc(cov); }
                 if (!kQuads && cov == 0) continue;
                 const U32 zxv = sb.zx[j], zyv = sb.zy[j];
                 const U32 zPix = sb.zb[j] + zxv * (U32)(lx * N) + zyv * (U32)((ly + 4 * p) * N);
@@ -203,6 +216,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
                         if (held != 0 && (U32)sb.entry[j] + 1u < held) pass |= 1u << i;
                     }
                 }
+                if (ProfMode == ProfilingMode_Counters && cov != 0) { profZTests++; profZKills += pass == 0 ? 1 : 0; }
                 if (!kQuads && pass == 0) continue;
                 const S32 entry = sb.entry[j];
                 if (kQuads) {
@@ -256,6 +270,19 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
         cur = nxt;
     }
 
+    if (ProfMode == ProfilingMode_Counters) {   // reference: FineRaster.inl:1032, :1069-1070, :1120-1121
+        __syncwarp();
+        const U32 zt = __reduce_add_sync(0xFFFFFFFFu, profZTests), zk = __reduce_add_sync(0xFFFFFFFFu, profZKills);
+        const U32 mk = __reduce_add_sync(0xFFFFFFFFu, profMsaaKills), ns = __reduce_add_sync(0xFFFFFFFFu, profSamples);
+        if (lane == 0) {
+            profCount<ProfMode>(f, CRB_PROF_FineZKill, 100ull * zk, zt);
+            profCount<ProfMode>(f, CRB_PROF_FineMSAAKill, 100ull * mk, profFrags);
+            profCount<ProfMode>(f, CRB_PROF_FineTriPerTile, (U32)queueCount, 1);
+            profCount<ProfMode>(f, CRB_PROF_FineFragPerTile, profFrags, 1);
+            profCount<ProfMode>(f, CRB_PROF_SetupSamplesPerTri, ns, 0);
+        }
+    }
+
     // ---- resolve + write back
 #pragma unroll 1
     for (int p = 0; p < 2; p++) {
@@ -303,21 +330,21 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
 
 // Picks the kernel variant for a pipe; one warp per tile, surplus warps exit at once (the number
 // of active tiles is only known on the device).
-template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
+template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 struct FineRasterLauncher {
     static int launch(const crb_frame* f, void* stream) {
         constexpr int kWarps = FineWarps<SamplesLog2>::Value;
         const int blocks = (f->numTiles + kWarps - 1) / kWarps;
-        return launchChained(fineRasterMultiKernel<VertexClass, FragmentShaderClass, BlendShaderClass, SamplesLog2, RenderModeFlags>, blocks, kWarps * 32, (cudaStream_t)stream, *f) == cudaSuccess
+        return launchChained(fineRasterMultiKernel<VertexClass, FragmentShaderClass, BlendShaderClass, SamplesLog2, RenderModeFlags, ProfMode>, blocks, kWarps * 32, (cudaStream_t)stream, *f) == cudaSuccess
                    ? CRB_OK : CRB_ERR_CUDA;
     }
 };
 
-template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags>
-struct FineRasterLauncher<VertexClass, FragmentShaderClass, BlendShaderClass, 0, RenderModeFlags> {
+template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags, int ProfMode>
+struct FineRasterLauncher<VertexClass, FragmentShaderClass, BlendShaderClass, 0, RenderModeFlags, ProfMode> {
     static int launch(const crb_frame* f, void* stream) {
         const int blocks = (f->numTiles + CRB_FINE_WARPS - 1) / CRB_FINE_WARPS;
-        return launchChained(fineRasterSingleKernel<VertexClass, FragmentShaderClass, BlendShaderClass, RenderModeFlags>, blocks, CRB_FINE_WARPS * 32, (cudaStream_t)stream, *f) == cudaSuccess
+        return launchChained(fineRasterSingleKernel<VertexClass, FragmentShaderClass, BlendShaderClass, RenderModeFlags, ProfMode>, blocks, CRB_FINE_WARPS * 32, (cudaStream_t)stream, *f) == cudaSuccess
                    ? CRB_OK : CRB_ERR_CUDA;
     }
 };

@@ -151,8 +151,6 @@ public:
 #endif
 };
 
-#define ProfilingMode_Default 0
-#define ProfilingMode_Counters 1   // accepted for source compatibility; reports like Default
-#define ProfilingMode_Timers 2
+// ProfilingMode_Default / _Counters / _Timers: PrivateDefs.hpp
 
 }  // namespace FW

@@ -46,12 +46,12 @@ inline int probeOrderIndependent() {
 
 #define CR_DEFINE_PIXEL_PIPE(PIPE_NAME, VERTEX_STRUCT, FRAGMENT_SHADER, BLEND_SHADER, SAMPLES_LOG2, RENDER_MODE_FLAGS)                      \
     extern "C" int PIPE_NAME##_triangleSetup(const crb_frame* frame, void* stream) {                                                        \
-        return FW::launchTriangleSetup<VERTEX_STRUCT, SAMPLES_LOG2, RENDER_MODE_FLAGS>(frame, stream);                                      \
+        return FW::launchTriangleSetup<VERTEX_STRUCT, SAMPLES_LOG2, RENDER_MODE_FLAGS, CR_PROFILING_MODE>(frame, stream);                   \
     }                                                                                                                                       \
     extern "C" int PIPE_NAME##_binRaster(const crb_frame* frame, void* stream) { return crb_launch_bin_raster(frame, stream); }             \
     extern "C" int PIPE_NAME##_coarseRaster(const crb_frame* frame, void* stream) { return crb_launch_coarse_raster(frame, stream); }       \
     extern "C" int PIPE_NAME##_fineRaster(const crb_frame* frame, void* stream) {                                                           \
-        return FW::FineRasterLauncher<VERTEX_STRUCT, FRAGMENT_SHADER, BLEND_SHADER, SAMPLES_LOG2, RENDER_MODE_FLAGS>::launch(frame, stream); \
+        return FW::FineRasterLauncher<VERTEX_STRUCT, FRAGMENT_SHADER, BLEND_SHADER, SAMPLES_LOG2, RENDER_MODE_FLAGS, CR_PROFILING_MODE>::launch(frame, stream); \
     }                                                                                                                                       \
     extern "C" int PIPE_NAME##_orderIndependent(void) {                                                                                     \
         static int cached = -1;                                                                                                             \

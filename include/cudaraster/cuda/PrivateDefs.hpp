@@ -32,6 +32,18 @@ typedef crb_atomics CRAtomics;
 
 #define CRB_TILECODE_GENERAL 0x40000000u
 
+// Profiling modes of a pixel pipe (reference: cuda/PrivateDefs.hpp:161-270, CR_PROFILING_MODE).  Counters: the kernels of a
+// pipe compiled with -DCR_PROFILING_MODE=ProfilingMode_Counters add to crb_frame::profCounters -- the counters of the
+// reference's report that have a meaning in this pipeline, each a numerator / denominator pair (CRProfCounter).
+#define ProfilingMode_Default 0
+#define ProfilingMode_Counters 1
+#define ProfilingMode_Timers 2   // accepted for source compatibility; reports like Default
+enum {
+    CRB_PROF_SetupViewportCull = 0, CRB_PROF_SetupBackfaceCull, CRB_PROF_SetupBetweenPixelsCull, CRB_PROF_SetupClipped, CRB_PROF_SetupSamplesPerTri,
+    CRB_PROF_FineEarlyZCull, CRB_PROF_FineEmptyCull, CRB_PROF_FineZKill, CRB_PROF_FineMSAAKill, CRB_PROF_FineTriPerTile, CRB_PROF_FineFragPerTri,
+    CRB_PROF_FineFragPerTile, CRB_PROF_NUM
+};
+
 // One coarse work item: `count` consecutive entries of one bin's queue.
 struct crb_item {
     int32_t bin;
@@ -112,6 +124,8 @@ struct crb_frame {
     uint32_t* triTileCode;        // [numTris] what the scatter pass needs to know about a triangle in ONE word: 0 = nothing to place,
                                   // CRB_TILECODE_GENERAL = go through triSubtris / the headers (clipped, refined or large), else
                                   // tile x0 | y0 << 8 | (nx-1) << 16 | (ny-1) << 17 | 1 << 31 of a footprint of at most 2x2 tiles
+
+    unsigned long long* profCounters;   // [CRB_PROF_NUM][2], zeroed before every frame of a ProfilingMode_Counters pipe
 
     crb_atomics* atomics;         // counters of THIS frame (zero when the frame starts)
     crb_atomics* nextAtomics;     // counters of the next frame: zeroed by this frame's fine raster kernel

@@ -302,7 +302,7 @@ __device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, in
     return numSub;
 }
 
-template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
+template <class VertexClass, int SamplesLog2, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
     __shared__ SetupShared sh;
     int* const s_binCount = sh.binCount;
@@ -318,7 +318,9 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
 
     const int tri = blockIdx.x * CRB_SETUP_THREADS + threadIdx.x;   // one thread per input triangle
     U32 tileCode = 0;
+    U32 prof = 0;   // ProfilingMode_Counters: bit 0 triangle, 1 viewport cull, 2 backface cull, 3 between-pixels cull, 4 clipped, 5 survived
     if (tri < f.numTris) {
+        prof = 1;
         const int3 vidx = make_int3(__ldg(&f.indexBuffer[tri * 3 + 0]), __ldg(&f.indexBuffer[tri * 3 + 1]), __ldg(&f.indexBuffer[tri * 3 + 2]));
         const float4 v0 = __ldg(&verts[(size_t)vidx.x * stride4]);
         const float4 v1 = __ldg(&verts[(size_t)vidx.y * stride4]);
@@ -342,6 +344,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
         }
         if (outside) {
             f.triSubtris[tri] = 0;
+            prof |= 2;
         } else {
             // inside the depth range: snap; inside the S16 guard band and small enough -> fast path
             bool done = false;
@@ -354,6 +357,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
                     S32 area;
                     const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
                     f.triSubtris[tri] = (res == 0) ? 1 : 0;
+                    prof |= res == 1 ? 4u : res == 2 ? 8u : 32u;
                     if (res == 0) {
                         // Micro mode: a footprint of at most 4x4 pixel centres (and an extent that keeps the S32 edge functions of
                         // microRaster exact) is rasterized right here and never queued; one without any pixel centre inside the
@@ -379,11 +383,20 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
                     done = true;
                 }
             }
-            if (!done && setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, sh) > 0) tileCode = CRB_TILECODE_GENERAL;
+            if (!done) prof |= 16;
+            if (!done && setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, sh) > 0) { tileCode = CRB_TILECODE_GENERAL; prof |= 32; }
         }
         if (f.directMode) f.triTileCode[tri] = tileCode;
     }
 
+    if (ProfMode == ProfilingMode_Counters) {   // reference: TriangleSetup.inl:255-258, :271, :304-305, :329
+        __syncwarp();
+        profCountWarp<ProfMode>(f, CRB_PROF_SetupViewportCull, (prof & 2) != 0, (prof & 1) != 0);
+        profCountWarp<ProfMode>(f, CRB_PROF_SetupBackfaceCull, (prof & 4) != 0, (prof & 1) != 0);
+        profCountWarp<ProfMode>(f, CRB_PROF_SetupBetweenPixelsCull, (prof & 8) != 0, (prof & 1) != 0);
+        profCountWarp<ProfMode>(f, CRB_PROF_SetupClipped, (prof & 16) != 0, (prof & 1) != 0);
+        profCountWarp<ProfMode>(f, CRB_PROF_SetupSamplesPerTri, false, (prof & 32) != 0);   // denominator: triangles that survive setup (the fine raster adds the samples)
+    }
     // publish this CTA's bin histogram: one column of binCountMat[bin][chunk]
     __syncthreads();
     if (threadIdx.x == 0 && sh.sawLarge != 0) atomicAdd(&f.atomics->numLargeTris, 1);   // CTAs with a large sub-triangle (zero / non-zero is what matters)
@@ -407,11 +420,11 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     }
 }
 
-template <class VertexClass, int SamplesLog2, U32 RenderModeFlags>
+template <class VertexClass, int SamplesLog2, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 inline int launchTriangleSetup(const crb_frame* f, void* stream) {
     if (f->numTris <= 0) return CRB_OK;
     const int grid = (f->numTris + CRB_SETUP_THREADS - 1) / CRB_SETUP_THREADS;
-    return launchChained(triangleSetupKernel<VertexClass, SamplesLog2, RenderModeFlags>, grid, CRB_SETUP_THREADS, (cudaStream_t)stream, *f) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+    return launchChained(triangleSetupKernel<VertexClass, SamplesLog2, RenderModeFlags, ProfMode>, grid, CRB_SETUP_THREADS, (cudaStream_t)stream, *f) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
 }
 
 }  // namespace FW

@@ -200,6 +200,24 @@ static inline cudaError_t launchChained(Kernel kernel, int grid, int block, cuda
     return cudaLaunchKernelEx(&cfg, kernel, f);
 }
 
+// ---- ProfilingMode_Counters (reference: CR_COUNT, cuda/Util.hpp) -------------------------------------------------
+// num / den are added to the counter's numerator / denominator; compiles to nothing in the other modes.
+template <int ProfMode>
+__device__ __forceinline__ void profCount(const crb_frame& f, int counter, unsigned long long num, unsigned long long den) {
+    if (ProfMode == ProfilingMode_Counters) {
+        if (num) atomicAdd(&f.profCounters[2 * counter], num);
+        if (den) atomicAdd(&f.profCounters[2 * counter + 1], den);
+    }
+}
+// The same for a predicate evaluated by every lane of a CONVERGED warp: one pair of atomics per warp.
+template <int ProfMode>
+__device__ __forceinline__ void profCountWarp(const crb_frame& f, int counter, bool numPred, bool denPred) {
+    if (ProfMode == ProfilingMode_Counters) {
+        const unsigned n = __popc(__ballot_sync(0xFFFFFFFFu, numPred)), d = __popc(__ballot_sync(0xFFFFFFFFu, denPred));
+        if ((threadIdx.x & 31) == 0) profCount<ProfMode>(f, counter, 100ull * n, d);
+    }
+}
+
 // ---- warp helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ U32 laneId() { return threadIdx.x & 31; }
 __device__ __forceinline__ U32 laneMaskLt() { U32 r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }

@@ -487,3 +487,33 @@ def test_direct_tile_path_async_frames_and_no_clear(raster, crb):
         _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, clear=None, init=init), lsb=1)
     finally:
         raster.setBinningMode(1)
+
+
+@pytest.mark.parametrize("samples_log2", [0, 2])
+def test_profiling_mode_counters(raster, crb, samples_log2):
+    """A pipe compiled with CR_PROFILING_MODE = ProfilingMode_Counters (reference: cuda/PrivateDefs.hpp:161-205,
+    CudaRaster.cpp:424-450): same frame as the plain pipe, and a counters report whose numbers agree with the oracle."""
+    import re
+    w, h = 320, 200
+    v, i = crb.scenes.random_soup(8000, seed=77, stride_floats=8, size=0.3)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraudCounters", 3, samples_log2)
+    info = raster.getProfilingInfo()
+    g = util.draw_gold(v, i, w, h, "gouraud", 3, samples_log2, want_counts=True)
+    _check_surfaces(cc, cd, g, lsb=1)
+    assert "ProfilingMode_Counters" in info and "TriangleSetup:" in info and "FineRaster:" in info
+    val = {m.group(1).strip(): float(m.group(2)) for m in re.finditer(r"- ([A-Za-z./ ]+?)\s+([0-9.]+)%?\n", info)}
+    for k in ("Viewport cull", "Backface cull", "Between pixels cull", "Clipped", "Early Z kill", "Empty coverage", "Z kills"):
+        assert 0.0 <= val[k] <= 100.0, (k, val)
+    gs = util.gold_setup(v, i, w, h, "gouraud", 3, samples_log2)
+    sub = gs["triSubtris"]
+    # culled = viewport + backface + between-pixels culls of unclipped triangles + clipped triangles that vanished
+    assert abs((val["Viewport cull"] + val["Backface cull"] + val["Between pixels cull"]) - 100.0 * ((sub == 0).sum() - 0) / len(sub)) < val["Clipped"] + 0.1
+    assert val["Clipped"] > 5.0 and val["Avg. tri/tile"] > 1 and val["Avg. frag/tri"] > 1
+    c = g["counts"]
+    tiles = ((w + 7) // 8) * ((h + 7) // 8)
+    if samples_log2 == 0:   # fragments the fine raster saw = all covered (triangle, pixel) pairs minus those of early-Z-culled triangles
+        assert 0.3 * c["fragments"] <= val["Avg. frag/tile"] * tiles <= 1.001 * c["fragments"] + tiles
+    # the plain pipe is unaffected
+    cc2, cd2 = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, samples_log2)
+    assert np.array_equal(cc, cc2) and np.array_equal(cd, cd2)
+    assert "ProfilingMode_Default" in raster.getProfilingInfo()
