@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true")
+    ap.add_argument("--composite", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = every rank renders straight into rank 0's memory over NVLink (CUDA IPC, no gather); 'nccl' = NCCL gather of finished frames")
     args = ap.parse_args()
     # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL's version banner,
     # nvcc of the reference-kernel harness) are pointed at stderr; emit() writes the line to the real stdout.
@@ -223,21 +225,32 @@ def main():
     for k in range(NUM_INPUT_COPIES):
         vv = verts if world == 1 else crb.scenes.apply_view(verts, views[(k * world + rank) % len(views)])
         copies.append((torch.from_numpy(vv).to(dev), torch.from_numpy(idx).to(dev)))
-    # N > 1: two colour surfaces; the NCCL gather of frame k (side stream) overlaps with the rendering of frame k+1
-    colors = [color] + ([crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, n_samples, device=dev)] if world > 1 else [])
-    gatherer = multigpu.AsyncFrameGather([c.tensor for c in colors], world, rank, dst=0) if world > 1 else None
+    # N > 1, composite to rank 0.  Default: rank 0 owns two frame slots per rank, exported with CUDA IPC; every
+    # rank renders STRAIGHT into its slot, so the fine raster's colour stores cross NVLink / NVSwitch while the frame is being
+    # rendered and there is no gather step at all.  --composite nccl: two local colour surfaces and an NCCL gather of frame k
+    # (side stream) that overlaps the rendering of frame k+1.
+    peer = world > 1 and args.composite == "peer"
+    sink = multigpu.PeerFrameSink(world, rank, color.tensor.numel() * 4, depth=2, device=dev) if peer else None
+    peer_surfaces = [sink.surface(k, (w, h), n_samples) for k in range(2)] if peer else None
+    colors = [color] + ([crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, n_samples, device=dev)] if world > 1 and not peer else [])
+    gatherer = multigpu.AsyncFrameGather([c.tensor for c in colors], world, rank, dst=0) if world > 1 and not peer else None
     stream = torch.cuda.current_stream(dev)
 
     def step(k, asynchronous=True):
         vb, ib = copies[k % NUM_INPUT_COPIES]
-        if world > 1:
+        if peer:
+            raster.setSurfaces(peer_surfaces[k % 2], depth)
+            raster.setColorLayout(True)      # tile-major slot: two 128-byte lines per tile cross NVLink instead of eight 32-byte rows
+        elif world > 1:
             gatherer.before_render(k)
             raster.setSurfaces(colors[k % 2], depth)
         raster.setVertexBuffer(vb, 0)
         raster.setIndexBuffer(ib, 0, n_tris)
         raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
         raster.drawTriangles(asynchronous=asynchronous)
-        if world > 1:
+        if peer:
+            sink.publish(k)
+        elif world > 1:
             gatherer.submit(k)
 
     def sync_all():
@@ -254,7 +267,7 @@ def main():
             stage_times[s].append(st[key] * 1e3)
     for s in STAGES:   # drop the cold first frames
         stage_times[s] = stage_times[s][2:] or stage_times[s]
-    if world > 1:
+    if gatherer:
         gatherer.finish()
     sync_all()
     launches_per_frame = raster.getLaunchCount()
@@ -269,7 +282,7 @@ def main():
     e0.record(stream)
     for k in range(args.steps):
         step(k)
-    if world > 1:
+    if gatherer:
         gatherer.finish()          # the last gather is inside the timed region
     e1.record(stream)
     raster.finish()
@@ -288,14 +301,37 @@ def main():
     sync_all()
     for k in range(args.steps):
         step(k)
-    if world > 1:
+    if gatherer:
         gatherer.finish()
     raster.finish()
     sync_all()
     live = raster.getStageTiming()
     raster.setStageTiming(False)
 
+    composite_ok = None
+    if peer:
+        # outside the timed regions: every rank re-renders its last frame into a LOCAL surface; rank 0 compares the frames that
+        # arrived in its memory over NVLink with them (checksums), and checks the per-slot frame marks
+        k_last = args.steps - 1
+        raster.setColorLayout(False)
+        raster.setSurfaces(color, depth)
+        vb, ib = copies[k_last % NUM_INPUT_COPIES]
+        raster.setVertexBuffer(vb, 0)
+        raster.setIndexBuffer(ib, 0, n_tris)
+        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+        raster.drawTriangles()
+        local_sum = color.tensor.to(torch.int64).sum().reshape(1)
+        sums = [torch.zeros_like(local_sum) for _ in range(world)] if rank == 0 else None
+        dist.gather(local_sum, sums, dst=0)
+        sync_all()
+        if rank == 0:
+            marks = sink.read_marks(raster)
+            composite_ok = bool((marks[k_last % 2] == k_last + 1).all())
+            for r in range(world):
+                got = sink.read_frame(raster, k_last, r, color.tensor.numel() * 4).view(np.int32).astype(np.int64).sum()
+                composite_ok = composite_ok and int(got) == int(sums[r].item())
     if world > 1:
+        raster.setColorLayout(False)
         raster.setSurfaces(color, depth)
     # ---- end to end through the host-buffer entry (pinned host memory in, colour frame out) ----------------
     h_color = torch.zeros_like(color.tensor, device="cpu").pin_memory()
@@ -343,10 +379,12 @@ def main():
             "config": {"workload": desc, "triangles": int(n_tris), "resolution": [w, h], "samples": n_samples, "pipe": crb.pipe_name(shader, s_log2, flags, "BlendReplace"),
                        "binning": ("direct tile path: setup counts tiles -> queue allocation (timed as binRaster) -> unordered atomic scatter (timed as coarseRaster) -> fine raster keeps the (depth, index) minimum"
                                    if direct else "general path: stable two-level sort (bin raster, coarse raster), queues in submission order"),
-                       "sharding": "1 GPU" if world == 1 else "view-parallel: 1 view per rank per step; every step's colour frames are gathered to rank 0 over NCCL inside the timed region (side stream, overlapped with the next frame's rendering)",
+                       "sharding": "1 GPU" if world == 1 else ("view-parallel: 1 view per rank per step; " + (
+                           "every rank renders straight into its frame slot in rank 0's memory (CUDA IPC peer memory over NVLink / NVSwitch): the composite is the render, no gather; frames verified on rank 0 after the timed region: %s" % composite_ok
+                           if peer else "every step's colour frames are gathered to rank 0 over NCCL inside the timed region (side stream, overlapped with the next frame's rendering)")),
                        "l2": "inputs rotate over %d device copies (%.0f MB) and each frame rewrites ~100 MB of intermediates, > 126 MB L2" %
                              (NUM_INPUT_COPIES, NUM_INPUT_COPIES * (verts.nbytes + idx.nbytes) / 1e6)},
-            "stage_ms": mean, "device_frame_ms": sum(mean.values()), "stage_ms_sync_draw": med, "stage_frames": live["frames"], "gpu_launches": launches_per_frame * args.steps, "clocks": clocks,
+            "stage_ms": mean, "device_frame_ms": sum(mean.values()), "stage_ms_sync_draw": med, "stage_frames": live["frames"], "gpu_launches": (launches_per_frame + (1 if peer else 0)) * args.steps, "clocks": clocks,
             "e2e": {"value": world * n_tris / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "crb_draw_triangles_host_async (pinned host vertices+indices in, colour surface out; upload/render/download of consecutive frames overlap)",
                     "blocking_value": world * n_tris / (e2e_blocking_ms * 1e-3) / 1e6, "blocking_ms_per_step": e2e_blocking_ms,
@@ -383,6 +421,9 @@ def main():
         if not args.no_ref_kernels and world == 1:
             line["ref_kernels"] = time_ref_kernels(args.workload)
         emit(line)
+    if peer:
+        sync_all()
+        sink.close()
     raster.close()
     if world > 1:
         dist.barrier()

@@ -89,6 +89,12 @@ def load_library():
         "crb_download": (i32, [vp, vp, vp, ctypes.c_size_t]),
         "crb_set_binning_mode": (i32, [vp, i32]),
         "crb_get_last_frame_direct": (i32, [vp]),
+        "crb_set_color_layout": (i32, [vp, i32]),
+        "crb_ipc_alloc": (i32, [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]),
+        "crb_ipc_free": (i32, [vp]),
+        "crb_ipc_open": (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
+        "crb_ipc_close": (i32, [vp]),
+        "crb_ipc_signal": (i32, [vp, u32, vp]),
         "crb_resolve_surface": (i32, [vp, i32, i32, i32, vp, i32, i32, vp]),
         "crb_write_ppm": (i32, [ctypes.c_char_p, vp, i32, i32, i32]),
         "crb_launch_vertex_shader": (i32, [vp, ctypes.c_char_p, vp, vp, i32, vp, ctypes.c_size_t, vp]),
@@ -105,12 +111,22 @@ EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_er
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
                     "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
-                    "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
+                    "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
 def pipe_name(base, samples_log2, flags, blend="BlendReplace"):
     """Name of a precompiled pipe variant (csrc/BuiltinPipes.cu)."""
     return "PixelPipe_%s_s%d_f%d_%s" % (base, samples_log2, flags, blend)
+
+
+class _ExternalMemory:
+    """Device memory owned by someone else: just enough of the tensor interface for CudaRaster.setSurfaces."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    def data_ptr(self):
+        return self.ptr
 
 
 class CudaSurface:
@@ -139,6 +155,19 @@ class CudaSurface:
         self.format = fmt
         self.num_samples = num_samples
         self.tensor = torch.zeros((self.texture_size[1], self.texture_size[0]), dtype=torch.int32, device=device)
+
+    @classmethod
+    def from_pointer(cls, ptr, size, fmt, num_samples=1):
+        """A surface over device memory the caller owns (e.g. a slot of a peer GPU's frame buffer mapped with CUDA IPC,
+        multigpu.PeerFrameSink): same layout, nothing is allocated."""
+        self = cls.__new__(cls)
+        w, h = int(size[0]), int(size[1])
+        self.size = (w, h)
+        self.rounded_size = ((w + 7) & ~7, (h + 7) & ~7)
+        self.texture_size = (self.rounded_size[0] * num_samples, self.rounded_size[1])
+        self.format, self.num_samples = fmt, num_samples
+        self.tensor = _ExternalMemory(int(ptr), self.texture_size[0] * self.texture_size[1] * 4)
+        return self
 
     def getSize(self):
         return self.size
@@ -250,6 +279,10 @@ class CudaRaster:
     def setIndexBuffer(self, buf, ofs, num_tris):
         self._keep["ib"] = buf
         self._check(self.lib.crb_set_index_buffer(self.ctx, buf.data_ptr() + ofs, int(num_tris)))
+
+    def setColorLayout(self, tile_major):
+        """False = row-major colour surface (reference layout), True = tile-major (64 contiguous texels per 8x8 tile)."""
+        self._check(self.lib.crb_set_color_layout(self.ctx, 1 if tile_major else 0))
 
     def setBinningMode(self, mode):
         """0 = general path only, 1 = automatic (default), 2 = direct tile path on every eligible frame, 3 = like 2 without the

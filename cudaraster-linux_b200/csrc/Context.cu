@@ -59,6 +59,7 @@ struct crb_ctx {
     int width = 0, height = 0, numSamples = 1, samplesLog2 = 0;
     int fullWidth = 0, fullHeight = 0, subX0 = 0, subY0 = 0;
     bool deferredClear = false;
+    bool colorTiled = false;             // crb_set_color_layout
     uint32_t clearColor = 0, clearDepth = 0;
     const void* vertices = nullptr;
     size_t vertexBytes = 0;
@@ -245,6 +246,8 @@ int prepareFrame(crb_ctx* c) {
     f.colorBuffer = c->color;
     f.depthBuffer = c->depth;
     f.surfacePitch = f.widthPixels << c->samplesLog2;
+    if (c->colorTiled && c->samplesLog2 != 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: the tile-major colour layout is single-sample only!");
+    f.colorTiled = c->colorTiled ? 1 : 0;
 
     f.ctasPerChunk = std::max(1, CRB_MIN_CHUNK_TRIS / CRB_SETUP_THREADS);
     while (((int64_t)c->numTris + CRB_SETUP_THREADS * f.ctasPerChunk - 1) / (CRB_SETUP_THREADS * f.ctasPerChunk) > CRB_MAX_CHUNKS) f.ctasPerChunk *= 2;
@@ -545,6 +548,12 @@ int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
     c->indices = (const int32_t*)d_indices;
     c->numTris = numTris;
     c->indicesSet = d_indices != nullptr || numTris == 0;
+    return CRB_OK;
+}
+
+int crb_set_color_layout(crb_ctx* c, int tileMajor) {
+    if (!c) return CRB_ERR_INVALID;
+    c->colorTiled = tileMajor != 0;
     return CRB_OK;
 }
 

@@ -11,6 +11,7 @@
 // per sample) and one 128-bit store; algorithmic bytes = 4 (N + 1) per pixel.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
 
 #include "../../include/crb200.h"
 
@@ -76,5 +77,41 @@ extern "C" int crb_resolve_surface(const void* d_src, int width, int height, int
         case 8: resolveKernel<8><<<grid, block, 0, s>>>(src, srcPitch4, dst, dstPitch, width, height, flipY); break;
         default: return CRB_ERR_INVALID;
     }
+    return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}
+
+// ---- multi-GPU composite over peer memory: CUDA IPC plumbing (crb200.h) ---------------------------------------------
+namespace {
+__global__ void ipcSignalKernel(volatile uint32_t* word, uint32_t value) {
+    __threadfence_system();
+    *word = value;
+}
+}  // namespace
+
+extern "C" int crb_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[CRB_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == CRB_IPC_HANDLE_BYTES, "handle size");
+    if (!d_ptr || !handle || bytes == 0) return CRB_ERR_INVALID;
+    if (cudaMalloc(d_ptr, bytes) != cudaSuccess) return CRB_ERR_CUDA;
+    if (cudaMemset(*d_ptr, 0, bytes) != cudaSuccess) return CRB_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, *d_ptr) != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return CRB_ERR_CUDA; }
+    memcpy(handle, &h, sizeof(h));
+    return CRB_OK;
+}
+
+extern "C" int crb_ipc_free(void* d_ptr) { return !d_ptr || cudaFree(d_ptr) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA; }
+
+extern "C" int crb_ipc_open(const unsigned char handle[CRB_IPC_HANDLE_BYTES], void** d_ptr) {
+    if (!d_ptr || !handle) return CRB_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    return cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}
+
+extern "C" int crb_ipc_close(void* d_ptr) { return !d_ptr || cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA; }
+
+extern "C" int crb_ipc_signal(void* d_word, uint32_t value, void* stream) {
+    if (!d_word) return CRB_ERR_INVALID;
+    ipcSignalKernel<<<1, 1, 0, (cudaStream_t)stream>>>((volatile uint32_t*)d_word, value);
     return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
 }

@@ -119,6 +119,77 @@ class AsyncFrameGather:
         return self.recv[k % len(self.surfaces)]
 
 
+class PeerFrameSink:
+    """View-parallel / sort-first composite WITHOUT a gather: rank `dst` owns the frame slots of all ranks (`depth`
+    deep) and exports them through CUDA IPC; every rank renders straight into its own slot, so the fine raster's colour
+    stores cross NVLink / NVSwitch while the frame is still being rendered (crb200.h: crb_ipc_*).  A 32-bit mark per
+    (slot, rank) says which frame the slot holds (`publish`, stream ordered, written after the frame).
+
+        sink = PeerFrameSink(world, rank, frame_bytes, depth=2)
+        raster.setSurfaces(sink.surface(k, (w, h)), depth_surface); raster.drawTriangles(asynchronous=True); sink.publish(k)
+    """
+
+    def __init__(self, world, rank, frame_bytes, depth=2, dst=0, device=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from .binding import load_library
+        self.lib, self.world, self.rank, self.depth, self.dst = load_library(), world, rank, depth, dst
+        self.frame_bytes = (frame_bytes + 255) & ~255
+        self.flag_ofs = self.frame_bytes * world * depth
+        total = self.flag_ofs + 4 * world * depth
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+        base = ctypes.c_void_p()
+        if rank == dst:
+            buf = ctypes.create_string_buffer(64)
+            if self.lib.crb_ipc_alloc(total, ctypes.byref(base), buf) != 0:
+                raise RuntimeError("PeerFrameSink: crb_ipc_alloc failed")
+            handle.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(handle, src=dst)
+        if rank != dst:
+            raw = bytes(handle.cpu().numpy().tobytes())
+            if self.lib.crb_ipc_open(raw, ctypes.byref(base)) != 0:
+                raise RuntimeError("PeerFrameSink: crb_ipc_open failed (no peer access between the GPUs?)")
+        self.base = base.value
+        dist.barrier()
+
+    def slot_pointer(self, k, rank=None):
+        r = self.rank if rank is None else rank
+        return self.base + ((k % self.depth) * self.world + r) * self.frame_bytes
+
+    def surface(self, k, size, num_samples=1):
+        """The colour surface rank `self.rank` renders frame k into (memory of rank `dst`)."""
+        from .binding import CudaSurface
+        return CudaSurface.from_pointer(self.slot_pointer(k), size, CudaSurface.FORMAT_RGBA8, num_samples)
+
+    def publish(self, k, stream=None):
+        import ctypes
+        import torch
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        word = self.base + self.flag_ofs + 4 * ((k % self.depth) * self.world + self.rank)
+        if self.lib.crb_ipc_signal(ctypes.c_void_p(word), k + 1, ctypes.c_void_p(s)) != 0:
+            raise RuntimeError("PeerFrameSink: signal failed")
+
+    def read_marks(self, raster):
+        """On `dst`: the frame number + 1 every (slot, rank) holds (blocking; raster = a CudaRaster of this process)."""
+        import numpy as np
+        return raster._dev_to_numpy(self.base + self.flag_ofs, 4 * self.world * self.depth, np.uint32).reshape(self.depth, self.world)
+
+    def read_frame(self, raster, k, rank, nbytes):
+        """On `dst`: a host copy (uint32) of the slot of `rank` for frame k (blocking)."""
+        import numpy as np
+        return raster._dev_to_numpy(self.slot_pointer(k, rank), nbytes, np.uint32)
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.rank == self.dst:
+            self.lib.crb_ipc_free(self.base)
+        else:
+            self.lib.crb_ipc_close(self.base)
+
+
 def composite_sort_first(local_rects, local_tiles, full_w, full_h, num_rects, dst=0, out=None):
     """Composites sort-first rectangles on rank `dst`.
 

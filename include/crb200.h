@@ -239,6 +239,23 @@ typedef int (*crb_vertex_shader_fn)(const void* d_inVertices, void* d_outVertice
 int crb_launch_vertex_shader(void* module, const char* name, const void* d_inVertices, void* d_outVertices, int numVertices, const void* h_constants,
                              size_t constantsBytes, void* stream);
 
+/* ---- multi-GPU composite over NVLink peer memory -----------------------------------
+ * One process per GPU.  The display process allocates the frame slots of ALL ranks in its own memory and exports them
+ * (CUDA IPC); every other process maps them and passes its slot to crb_set_surfaces as the colour surface: the fine
+ * raster's colour stores then travel over NVLink / NVSwitch as the tiles are finished -- the composite is the render
+ * itself, there is no gather step.  crb_ipc_signal leaves a stream-ordered 32-bit mark (e.g. the frame number) in
+ * shared memory for the consumer.  Handles are cudaIpcMemHandle_t (64 bytes). */
+/* Layout of the COLOUR surface (single sample): 0 = the reference's row-major layout (crb_set_surfaces), 1 = tile-major --
+ * tile t = tx + ty * ceil(width / 8) occupies texels [64 t, 64 t + 64), pixel (x, y) of the tile at y * 8 + x; same size.
+ * A warp then writes its tile as two full 128-byte lines; meant for frame slots in a peer GPU's memory. */
+int crb_set_color_layout(crb_ctx* ctx, int tileMajor);
+#define CRB_IPC_HANDLE_BYTES 64
+int crb_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[CRB_IPC_HANDLE_BYTES]);
+int crb_ipc_free(void* d_ptr);
+int crb_ipc_open(const unsigned char handle[CRB_IPC_HANDLE_BYTES], void** d_ptr);
+int crb_ipc_close(void* d_ptr);
+int crb_ipc_signal(void* d_word, uint32_t value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

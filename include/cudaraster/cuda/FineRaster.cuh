@@ -354,7 +354,11 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     const int lx = lane & 7, ly = lane >> 3;
     const int pixelX = (tileX << CR_TILE_LOG2) + lx;
     const int pixelY0 = (tileY << CR_TILE_LOG2) + ly;
-    U32* colorPtr = f.colorBuffer + (size_t)pixelY0 * f.surfacePitch + pixelX;
+    // colour surface: the reference's row-major layout, or TILE-MAJOR (crb_set_color_layout: the 64 texels of a tile are
+    // contiguous, pixel (x, y) of the tile at y*8 + x): a warp then writes its tile as two full 128-byte lines, which is
+    // what a frame slot in a PEER GPU's memory wants -- the stores cross NVLink as two large packets instead of eight 32-byte ones
+    U32* colorPtr = f.colorTiled ? f.colorBuffer + (size_t)tileIdx * CR_TILE_SQR + lane : f.colorBuffer + (size_t)pixelY0 * f.surfacePitch + pixelX;
+    const size_t colorStep = f.colorTiled ? (size_t)32 : (size_t)4 * f.surfacePitch;
     U32* depthPtr = f.depthBuffer + (size_t)pixelY0 * f.surfacePitch + pixelX;
     const size_t rowStep = (size_t)4 * f.surfacePitch;
 
@@ -364,7 +368,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         color[0] = color[1] = f.clearColor;
         depth[0] = depth[1] = f.clearDepth;
     } else {
-        color[0] = colorPtr[0]; color[1] = colorPtr[rowStep];
+        color[0] = colorPtr[0]; color[1] = colorPtr[colorStep];
         depth[0] = kDepth ? depthPtr[0] : 0u; depth[1] = kDepth ? depthPtr[rowStep] : 0u;
     }
 
@@ -536,7 +540,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     }
 
     colorPtr[0] = color[0];
-    colorPtr[rowStep] = color[1];
+    colorPtr[colorStep] = color[1];
     if (kDepth || f.deferredClear) {
         depthPtr[0] = depth[0];
         depthPtr[rowStep] = depth[1];

@@ -80,6 +80,7 @@ struct crb_frame {
     uint32_t* colorBuffer;        // linear surfaces, pitch in texels = widthPixels << samplesLog2
     uint32_t* depthBuffer;
     int32_t surfacePitch;
+    int32_t colorTiled;           // 1 = the colour surface is tile-major (single sample only; crb_set_color_layout)
 
     // ---- setup output
     int32_t maxSubtris;

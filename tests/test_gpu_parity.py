@@ -517,3 +517,77 @@ def test_profiling_mode_counters(raster, crb, samples_log2):
     cc2, cd2 = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, samples_log2)
     assert np.array_equal(cc, cc2) and np.array_equal(cd, cd2)
     assert "ProfilingMode_Default" in raster.getProfilingInfo()
+
+
+def test_limits_and_error_behaviour(crb):
+    """The reference's state checks, in its order and with its messages (CudaRaster.cpp:141-159, :243-260;
+    CudaSurface.cpp:44-62), and its format limits: 2048 x 2048 viewport with 8 samples, degenerate input."""
+    import torch
+    r = crb.CudaRaster(0)
+    try:
+        for size, n, msg in (((0, 10), 1, "Size must be positive"), ((4096, 16), 1, "CR_MAXVIEWPORT_SIZE exceeded"), ((64, 64), 16, "cannot exceed 8"),
+                             ((64, 64), 3, "power of two")):
+            with pytest.raises(crb.CrbError, match=msg):
+                crb.CudaSurface(size, crb.CudaSurface.FORMAT_RGBA8, n)
+        c1 = crb.CudaSurface((64, 64), crb.CudaSurface.FORMAT_RGBA8, 1)
+        d1 = crb.CudaSurface((64, 64), crb.CudaSurface.FORMAT_DEPTH32, 1)
+        d2 = crb.CudaSurface((64, 32), crb.CudaSurface.FORMAT_DEPTH32, 1)
+        d4 = crb.CudaSurface((64, 64), crb.CudaSurface.FORMAT_DEPTH32, 4)
+        for args, msg in (((None, d1), "No color buffer"), ((c1, None), "No depth buffer"), ((d1, d1), "Unsupported color buffer format"),
+                          ((c1, c1), "Unsupported depth buffer format"), ((c1, d2), "Mismatch in size"), ((c1, d4), "Mismatch in multisampling between surfaces")):
+            with pytest.raises(crb.CrbError, match=msg):
+                r.setSurfaces(*args)
+        with pytest.raises(crb.CrbError, match="Surfaces not set"):
+            r.drawTriangles()
+        r.setSurfaces(c1, d1)
+        with pytest.raises(crb.CrbError, match="Pixel pipe not set"):
+            r.drawTriangles()
+        with pytest.raises(crb.CrbError, match="Invalid pixel pipe"):
+            r.setPixelPipe(None, "PixelPipe_doesNotExist")
+        r.setPixelPipe(None, crb.pipe_name("gouraud", 2, 3))
+        with pytest.raises(crb.CrbError, match="Vertex buffer not set"):
+            r.drawTriangles()
+        v, i = crb.scenes.random_soup(50, seed=1, stride_floats=8)
+        vb, ib = torch.from_numpy(v).cuda(), torch.from_numpy(i).cuda()
+        r.setVertexBuffer(vb, 0)
+        with pytest.raises(crb.CrbError, match="Index buffer not set"):
+            r.drawTriangles()
+        r.setIndexBuffer(ib, 0, i.shape[0])
+        with pytest.raises(crb.CrbError, match="Mismatch in multisampling between pixel pipe and surface"):
+            r.drawTriangles()
+        # the largest surface the format allows: 2048 x 2048, 8 samples; a full-screen triangle, degenerate and repeated-index triangles
+        w = h = 2048
+        v = np.array([[-1.5, -1.5, 0.3, 1, 1, 0, 0, 1], [1.5, -1.5, 0.3, 1, 0, 1, 0, 1], [0, 1.5, 0.3, 1, 0, 0, 1, 1], [0.2, 0.2, 0.1, 1, 1, 1, 1, 1], [0.21, 0.2, 0.1, 1, 1, 1, 1, 1],
+                      [0.2, 0.21, 0.1, 1, 1, 1, 1, 1]], np.float32)
+        i = np.array([[0, 1, 2], [3, 3, 4], [3, 4, 5], [5, 4, 3], [0, 0, 0]], np.int32)
+        for s_log2, mode in ((3, 0), (0, 2), (0, 0)):
+            r.setBinningMode(mode)
+            cc, cd = util.draw_cuda(r, crb, v, i, w, h, "gouraud", 3, s_log2)
+            g = util.draw_gold(v, i, w, h, "gouraud", 3, s_log2)
+            _check_surfaces(cc, cd, g, lsb=1)
+            assert (cd != cd[0, 0]).any()
+    finally:
+        r.close()
+
+
+def test_tile_major_colour_layout(raster, crb):
+    """crb_set_color_layout: the same frame with a tile-major colour surface (what a frame slot in a peer GPU's memory
+    uses), on the general, direct and micro paths; depth stays row-major."""
+    w, h = 328, 200
+    v, i = crb.scenes.grid_gouraud(120, 80)
+    try:
+        for mode in (0, 2, 3):
+            raster.setBinningMode(mode)
+            raster.setColorLayout(False)
+            cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+            raster.setColorLayout(True)
+            tc, td = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
+            rh, rw = cc.shape
+            detiled = tc.reshape(rh // 8, rw // 8, 8, 8).transpose(0, 2, 1, 3).reshape(rh, rw)
+            assert np.array_equal(detiled, cc) and np.array_equal(td, cd)
+        raster.setColorLayout(True)
+        with pytest.raises(crb.CrbError, match="single-sample only"):
+            util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, 2)
+    finally:
+        raster.setColorLayout(False)
+        raster.setBinningMode(1)
