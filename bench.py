@@ -179,8 +179,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true")
-    ap.add_argument("--composite", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: 'peer' = every rank renders straight into rank 0's memory over NVLink (CUDA IPC, no gather); 'nccl' = NCCL gather of finished frames")
+    ap.add_argument("--composite", default="auto", choices=["auto", "peer", "push", "nccl"],
+                    help="N > 1: 'peer' = every rank renders straight into rank 0's memory over NVLink (CUDA IPC, no gather); 'push' = render locally, "
+                         "DMA copy of finished frames into rank 0's slots on a side stream; 'nccl' = NCCL gather of finished frames; 'auto' = peer for 2 GPUs, push beyond "
+                         "(measured: with 8 ranks the simultaneous fine-raster stores exceed rank 0's NVLink ingress, the DMA copies spread over the frame)")
     args = ap.parse_args()
     # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL's version banner,
     # nvcc of the reference-kernel harness) are pointed at stderr; emit() writes the line to the real stdout.
@@ -229,11 +231,16 @@ def main():
     # rank renders STRAIGHT into its slot, so the fine raster's colour stores cross NVLink / NVSwitch while the frame is being
     # rendered and there is no gather step at all.  --composite nccl: two local colour surfaces and an NCCL gather of frame k
     # (side stream) that overlaps the rendering of frame k+1.
+    if args.composite == "auto":
+        args.composite = "peer" if world <= 2 else "push"
     peer = world > 1 and args.composite == "peer"
-    sink = multigpu.PeerFrameSink(world, rank, color.tensor.numel() * 4, depth=2, device=dev) if peer else None
+    push = world > 1 and args.composite == "push"
+    sink = multigpu.PeerFrameSink(world, rank, color.tensor.numel() * 4, depth=2, device=dev) if (peer or push) else None
     peer_surfaces = [sink.surface(k, (w, h), n_samples) for k in range(2)] if peer else None
     colors = [color] + ([crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, n_samples, device=dev)] if world > 1 and not peer else [])
-    gatherer = multigpu.AsyncFrameGather([c.tensor for c in colors], world, rank, dst=0) if world > 1 and not peer else None
+    gatherer = multigpu.AsyncFrameGather([c.tensor for c in colors], world, rank, dst=0) if world > 1 and not (peer or push) else None
+    if push:
+        sink.attach_local([c.tensor for c in colors])
     stream = torch.cuda.current_stream(dev)
 
     def step(k, asynchronous=True):
@@ -241,6 +248,9 @@ def main():
         if peer:
             raster.setSurfaces(peer_surfaces[k % 2], depth)
             raster.setColorLayout(True)      # tile-major slot: two 128-byte lines per tile cross NVLink instead of eight 32-byte rows
+        elif push:
+            sink.before_render(k)
+            raster.setSurfaces(colors[k % 2], depth)
         elif world > 1:
             gatherer.before_render(k)
             raster.setSurfaces(colors[k % 2], depth)
@@ -250,6 +260,8 @@ def main():
         raster.drawTriangles(asynchronous=asynchronous)
         if peer:
             sink.publish(k)
+        elif push:
+            sink.push(k)
         elif world > 1:
             gatherer.submit(k)
 
@@ -267,8 +279,8 @@ def main():
             stage_times[s].append(st[key] * 1e3)
     for s in STAGES:   # drop the cold first frames
         stage_times[s] = stage_times[s][2:] or stage_times[s]
-    if gatherer:
-        gatherer.finish()
+    if gatherer or push:
+        (gatherer or sink).finish()
     sync_all()
     launches_per_frame = raster.getLaunchCount()
     direct = raster.lastFrameDirect()   # automatic binning mode: small-triangle frames of an order-independent pipe skip the bin / coarse sort
@@ -282,8 +294,8 @@ def main():
     e0.record(stream)
     for k in range(args.steps):
         step(k)
-    if gatherer:
-        gatherer.finish()          # the last gather is inside the timed region
+    if gatherer or push:
+        (gatherer or sink).finish()          # the last gather / copy is inside the timed region
     e1.record(stream)
     raster.finish()
     sync_all()
@@ -301,15 +313,15 @@ def main():
     sync_all()
     for k in range(args.steps):
         step(k)
-    if gatherer:
-        gatherer.finish()
+    if gatherer or push:
+        (gatherer or sink).finish()
     raster.finish()
     sync_all()
     live = raster.getStageTiming()
     raster.setStageTiming(False)
 
     composite_ok = None
-    if peer:
+    if peer or push:
         # outside the timed regions: every rank re-renders its last frame into a LOCAL surface; rank 0 compares the frames that
         # arrived in its memory over NVLink with them (checksums), and checks the per-slot frame marks
         k_last = args.steps - 1
@@ -381,7 +393,8 @@ def main():
                                    if direct else "general path: stable two-level sort (bin raster, coarse raster), queues in submission order"),
                        "sharding": "1 GPU" if world == 1 else ("view-parallel: 1 view per rank per step; " + (
                            "every rank renders straight into its frame slot in rank 0's memory (CUDA IPC peer memory over NVLink / NVSwitch): the composite is the render, no gather; frames verified on rank 0 after the timed region: %s" % composite_ok
-                           if peer else "every step's colour frames are gathered to rank 0 over NCCL inside the timed region (side stream, overlapped with the next frame's rendering)")),
+                           if peer else "every rank renders locally and a DMA copy on a side stream (overlapped with the next frame) pushes the finished frame into its slot in rank 0's memory (CUDA IPC peer memory over NVLink / NVSwitch); frames verified on rank 0 after the timed region: %s" % composite_ok
+                           if push else "every step's colour frames are gathered to rank 0 over NCCL inside the timed region (side stream, overlapped with the next frame's rendering)")),
                        "l2": "inputs rotate over %d device copies (%.0f MB) and each frame rewrites ~100 MB of intermediates, > 126 MB L2" %
                              (NUM_INPUT_COPIES, NUM_INPUT_COPIES * (verts.nbytes + idx.nbytes) / 1e6)},
             "stage_ms": mean, "device_frame_ms": sum(mean.values()), "stage_ms_sync_draw": med, "stage_frames": live["frames"], "gpu_launches": (launches_per_frame + (1 if peer else 0)) * args.steps, "clocks": clocks,
@@ -421,7 +434,7 @@ def main():
         if not args.no_ref_kernels and world == 1:
             line["ref_kernels"] = time_ref_kernels(args.workload)
         emit(line)
-    if peer:
+    if sink:
         sync_all()
         sink.close()
     raster.close()

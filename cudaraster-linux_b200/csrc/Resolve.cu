@@ -115,3 +115,8 @@ extern "C" int crb_ipc_signal(void* d_word, uint32_t value, void* stream) {
     ipcSignalKernel<<<1, 1, 0, (cudaStream_t)stream>>>((volatile uint32_t*)d_word, value);
     return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
 }
+
+extern "C" int crb_ipc_copy(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+    if (bytes && (!d_dst || !d_src)) return CRB_ERR_INVALID;
+    return cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}

@@ -171,6 +171,46 @@ class PeerFrameSink:
         if self.lib.crb_ipc_signal(ctypes.c_void_p(word), k + 1, ctypes.c_void_p(s)) != 0:
             raise RuntimeError("PeerFrameSink: signal failed")
 
+    # -- staged variant: render into LOCAL surfaces, let the DMA engines push finished frames into the slots ---------------
+    def attach_local(self, surfaces):
+        """surfaces: the local colour tensors frames are rendered into (frame k -> surfaces[k % len]); enables push()."""
+        import torch
+        self.local = list(surfaces)
+        self.side = torch.cuda.Stream(device=self.local[0].device)
+        self.rendered = [torch.cuda.Event() for _ in self.local]
+        self.pushed = [None for _ in self.local]
+
+    def before_render(self, k):
+        """Makes the render stream wait until the copy that last read the local surface of frame k is done."""
+        import torch
+        i = k % len(self.local)
+        if self.pushed[i] is not None:
+            torch.cuda.current_stream(self.local[i].device).wait_event(self.pushed[i])
+        return self.local[i]
+
+    def push(self, k):
+        """Frame k is rendered (on the current stream): copy it into this rank's slot on the side stream (DMA over NVLink,
+        overlapped with the rendering of the next frame) and leave the frame mark."""
+        import ctypes
+        import torch
+        i = k % len(self.local)
+        t = self.local[i]
+        self.rendered[i].record(torch.cuda.current_stream(t.device))
+        self.side.wait_event(self.rendered[i])
+        with torch.cuda.stream(self.side):
+            if self.lib.crb_ipc_copy(ctypes.c_void_p(self.slot_pointer(k)), ctypes.c_void_p(t.data_ptr()), t.numel() * t.element_size(),
+                                     ctypes.c_void_p(self.side.cuda_stream)) != 0:
+                raise RuntimeError("PeerFrameSink: copy failed")
+            self.publish(k, stream=self.side.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.pushed[i] = ev
+
+    def finish(self):
+        import torch
+        if getattr(self, "side", None) is not None:
+            torch.cuda.current_stream(self.local[0].device).wait_stream(self.side)
+
     def read_marks(self, raster):
         """On `dst`: the frame number + 1 every (slot, rank) holds (blocking; raster = a CudaRaster of this process)."""
         import numpy as np

@@ -255,6 +255,9 @@ int crb_ipc_free(void* d_ptr);
 int crb_ipc_open(const unsigned char handle[CRB_IPC_HANDLE_BYTES], void** d_ptr);
 int crb_ipc_close(void* d_ptr);
 int crb_ipc_signal(void* d_word, uint32_t value, void* stream);
+/* Stream-ordered device-to-device copy (either side may be mapped peer memory): the DMA engines move a finished frame
+ * into its slot with full-size NVLink packets. */
+int crb_ipc_copy(void* d_dst, const void* d_src, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }
