@@ -90,6 +90,7 @@ def load_library():
         "crb_set_binning_mode": (i32, [vp, i32]),
         "crb_get_last_frame_direct": (i32, [vp]),
         "crb_set_color_layout": (i32, [vp, i32]),
+        "crb_set_color_pitch": (i32, [vp, i32]),
         "crb_ipc_alloc": (i32, [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]),
         "crb_ipc_free": (i32, [vp]),
         "crb_ipc_open": (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
@@ -112,7 +113,7 @@ EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_er
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
                     "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
-                    "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_ipc_copy", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
+                    "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_set_color_pitch", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_ipc_copy", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
 def pipe_name(base, samples_log2, flags, blend="BlendReplace"):
@@ -284,6 +285,10 @@ class CudaRaster:
     def setColorLayout(self, tile_major):
         """False = row-major colour surface (reference layout), True = tile-major (64 contiguous texels per 8x8 tile)."""
         self._check(self.lib.crb_set_color_layout(self.ctx, 1 if tile_major else 0))
+
+    def setColorPitch(self, pitch_texels):
+        """Row pitch of the colour surface (0 = its own): the surface is a window of a larger image (crb_set_color_pitch)."""
+        self._check(self.lib.crb_set_color_pitch(self.ctx, int(pitch_texels)))
 
     def setBinningMode(self, mode):
         """0 = general path only, 1 = automatic (default), 2 = direct tile path on every eligible frame, 3 = like 2 without the

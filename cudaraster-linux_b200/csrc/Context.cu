@@ -60,6 +60,7 @@ struct crb_ctx {
     int fullWidth = 0, fullHeight = 0, subX0 = 0, subY0 = 0;
     bool deferredClear = false;
     bool colorTiled = false;             // crb_set_color_layout
+    int colorPitch = 0;                  // crb_set_color_pitch (0 = the surface's own pitch)
     uint32_t clearColor = 0, clearDepth = 0;
     const void* vertices = nullptr;
     size_t vertexBytes = 0;
@@ -248,6 +249,9 @@ int prepareFrame(crb_ctx* c) {
     f.surfacePitch = f.widthPixels << c->samplesLog2;
     if (c->colorTiled && c->samplesLog2 != 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: the tile-major colour layout is single-sample only!");
     f.colorTiled = c->colorTiled ? 1 : 0;
+    if (c->colorPitch != 0 && (c->samplesLog2 != 0 || c->colorTiled || c->colorPitch < f.widthPixels))
+        return setError(c, CRB_ERR_INVALID, "CudaRaster: a colour pitch needs a single-sample row-major surface and must cover the rounded width!");
+    f.colorPitch = c->colorPitch != 0 ? c->colorPitch : f.surfacePitch;
 
     f.ctasPerChunk = std::max(1, CRB_MIN_CHUNK_TRIS / CRB_SETUP_THREADS);
     while (((int64_t)c->numTris + CRB_SETUP_THREADS * f.ctasPerChunk - 1) / (CRB_SETUP_THREADS * f.ctasPerChunk) > CRB_MAX_CHUNKS) f.ctasPerChunk *= 2;
@@ -548,6 +552,12 @@ int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
     c->indices = (const int32_t*)d_indices;
     c->numTris = numTris;
     c->indicesSet = d_indices != nullptr || numTris == 0;
+    return CRB_OK;
+}
+
+int crb_set_color_pitch(crb_ctx* c, int pitchTexels) {
+    if (!c || pitchTexels < 0) return CRB_ERR_INVALID;
+    c->colorPitch = pitchTexels;
     return CRB_OK;
 }
 

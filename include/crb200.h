@@ -249,6 +249,11 @@ int crb_launch_vertex_shader(void* module, const char* name, const void* d_inVer
  * tile t = tx + ty * ceil(width / 8) occupies texels [64 t, 64 t + 64), pixel (x, y) of the tile at y * 8 + x; same size.
  * A warp then writes its tile as two full 128-byte lines; meant for frame slots in a peer GPU's memory. */
 int crb_set_color_layout(crb_ctx* ctx, int tileMajor);
+/* Row pitch of the COLOUR surface in texels (single sample, row-major; 0 = the surface's own rounded width): lets the colour
+ * pointer of crb_set_surfaces address a window inside a larger image, e.g. a sort-first rectangle inside the full frame in
+ * the display GPU's memory -- every rank then renders its rectangles in place and the composite needs no paste.  The window
+ * should be a multiple of 8 px wide and high (the kernels write whole tiles).  The host-buffer entries ignore it. */
+int crb_set_color_pitch(crb_ctx* ctx, int pitchTexels);
 #define CRB_IPC_HANDLE_BYTES 64
 int crb_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[CRB_IPC_HANDLE_BYTES]);
 int crb_ipc_free(void* d_ptr);

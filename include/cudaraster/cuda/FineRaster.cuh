@@ -357,8 +357,8 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     // colour surface: the reference's row-major layout, or TILE-MAJOR (crb_set_color_layout: the 64 texels of a tile are
     // contiguous, pixel (x, y) of the tile at y*8 + x): a warp then writes its tile as two full 128-byte lines, which is
     // what a frame slot in a PEER GPU's memory wants -- the stores cross NVLink as two large packets instead of eight 32-byte ones
-    U32* colorPtr = f.colorTiled ? f.colorBuffer + (size_t)tileIdx * CR_TILE_SQR + lane : f.colorBuffer + (size_t)pixelY0 * f.surfacePitch + pixelX;
-    const size_t colorStep = f.colorTiled ? (size_t)32 : (size_t)4 * f.surfacePitch;
+    U32* colorPtr = f.colorTiled ? f.colorBuffer + (size_t)tileIdx * CR_TILE_SQR + lane : f.colorBuffer + (size_t)pixelY0 * f.colorPitch + pixelX;
+    const size_t colorStep = f.colorTiled ? (size_t)32 : (size_t)4 * f.colorPitch;
     U32* depthPtr = f.depthBuffer + (size_t)pixelY0 * f.surfacePitch + pixelX;
     const size_t rowStep = (size_t)4 * f.surfacePitch;
 

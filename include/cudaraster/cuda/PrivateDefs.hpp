@@ -80,6 +80,8 @@ struct crb_frame {
     uint32_t* colorBuffer;        // linear surfaces, pitch in texels = widthPixels << samplesLog2
     uint32_t* depthBuffer;
     int32_t surfacePitch;
+    int32_t colorPitch;           // texels per row of the colour surface: surfacePitch, or the pitch of a larger image the surface is a
+                                  // window of (crb_set_color_pitch: sort-first windows rendered straight into the full frame)
     int32_t colorTiled;           // 1 = the colour surface is tile-major (single sample only; crb_set_color_layout)
 
     // ---- setup output

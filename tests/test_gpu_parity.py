@@ -591,3 +591,32 @@ def test_tile_major_colour_layout(raster, crb):
     finally:
         raster.setColorLayout(False)
         raster.setBinningMode(1)
+
+
+def test_sort_first_windows_rendered_in_place(raster, crb):
+    """crb_set_color_pitch: the four sort-first windows of a frame rendered STRAIGHT into one full-frame image (the
+    composite without a paste; across GPUs the image is a PeerFrameSink slot) equal the frame rendered whole."""
+    import torch
+    fw, fh = 512, 384
+    v, i = crb.scenes.random_soup(6000, seed=31, stride_floats=8, size=0.5)
+    full_c, full_d = util.draw_cuda(raster, crb, v, i, fw, fh, "gouraud", 3)
+    frame = torch.zeros((fh, fw), dtype=torch.int32, device="cuda")
+    vb, ib = torch.from_numpy(v).cuda(), torch.from_numpy(i).cuda()
+    try:
+        for (x0, y0, w, h) in [(0, 0, 256, 192), (256, 0, 256, 192), (0, 192, 256, 192), (256, 192, 256, 192)]:
+            color = crb.CudaSurface.from_pointer(frame.data_ptr() + 4 * (y0 * fw + x0), (w, h), crb.CudaSurface.FORMAT_RGBA8)
+            depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32)
+            raster.setSurfaces(color, depth)
+            raster.setColorPitch(fw)
+            raster.setPixelPipe(None, crb.pipe_name("gouraud", 0, 3))
+            raster.setVertexBuffer(vb, 0)
+            raster.setIndexBuffer(ib, 0, i.shape[0])
+            raster.setSubViewport(fw, fh, x0, y0)
+            raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+            raster.drawTriangles()
+            assert np.array_equal(depth.numpy(), full_d[y0:y0 + h, x0:x0 + w])
+        torch.cuda.synchronize()
+        assert np.array_equal(frame.cpu().numpy().view(np.uint32), full_c)
+    finally:
+        raster.setColorPitch(0)
+        raster.setSubViewport(0, 0, 0, 0)
