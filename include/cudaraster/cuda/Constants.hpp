@@ -49,6 +49,9 @@
 #define CRB_BIN_THREADS 256       // == CR_MAXBINS_SQR: one thread per bin in the scan phases
 #define CRB_COARSE_THREADS 256    // == CR_BIN_SQR: one thread per tile-in-bin in the scan phases
 #define CRB_ITEM_ENTRIES 256      // bin-queue entries per coarse work item (one warp, 8 batches)
+#ifndef CRB_FINE_REVERSE
+#define CRB_FINE_REVERSE 1        // micro-mode fine raster walks the tiles last to first (C2: fine 39.0 -> 37.4 us, next setup 49.5 -> 46.0 us)
+#endif
 #ifndef CRB_FINE_WARPS
 #ifndef CRB_FINE_WARPS_PER_SM
 #define CRB_FINE_WARPS_PER_SM 32  // resident fine warps per SM the register allocation must allow (32 -> 64 registers)

@@ -323,7 +323,13 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     unsigned long long* vis = nullptr;
     unsigned long long v0 = ~0ull, v1 = ~0ull;
     if (f.microMode != 0) {
+#if CRB_FINE_REVERSE
+        // tiles in REVERSE order: for a mesh submitted in screen order the records setup wrote LAST are still in L2, and the
+        // fine raster, which starts right after setup, meets them first (a stack instead of a cyclic sweep through the L2)
+        const int t = max(f.numTiles - 1 - activeIdx, 0);
+#else
         const int t = min(activeIdx, f.numTiles - 1);
+#endif
         rec = make_int4(t, __ldg(&f.tileStart[t]), __ldg(&f.tileCount[t]), 0);
         const int ty = t / f.widthTiles, tx = t - ty * f.widthTiles;
         vis = f.visBuffer + (size_t)((ty << CR_TILE_LOG2) + (lane >> 3)) * f.widthPixels + (tx << CR_TILE_LOG2) + (lane & 7);
