@@ -25,7 +25,7 @@ class _PipeSpec(ctypes.Structure):
 class Atomics(ctypes.Structure):
     _fields_ = [("numSubtris", ctypes.c_int32), ("numBinEntries", ctypes.c_int32), ("numCoarseItems", ctypes.c_int32),
                 ("numTileEntries", ctypes.c_int32), ("numActiveTiles", ctypes.c_int32), ("overflow", ctypes.c_int32),
-                ("numLargeTris", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("numLargeTris", ctypes.c_int32), ("numQueuedCtas", ctypes.c_int32)]
 
 
 class WorkBuffers(ctypes.Structure):
@@ -360,7 +360,7 @@ class CudaRaster:
     def getCounters(self):
         a = Atomics()
         self._check(self.lib.crb_get_counters(self.ctx, ctypes.byref(a)))
-        return {k: getattr(a, k) for k, _ in Atomics._fields_ if k != "reserved"}
+        return {k: getattr(a, k) for k, _ in Atomics._fields_}
 
     def getLaunchCount(self):
         return self.lib.crb_get_launch_count(self.ctx)

@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(kThreads) directAllocKernel(const __grid_const
     gridDepWait();
     // one thread decides for the block: other blocks of THIS grid may raise the flag at any time, and a block
     // whose threads disagree would hang in the barriers below
-    if (threadIdx.x == 0) s_abort = f.atomics->overflow;
+    // micro mode with nothing queued (every triangle went the micro way): no queue extents to make -- the fine raster
+    // addresses the tiles directly and takes every queue as empty (the counter is final: setup has ended)
+    if (threadIdx.x == 0) s_abort = f.atomics->overflow | ((f.microMode != 0 && f.atomics->numQueuedCtas == 0) ? 1 : 0);
     __syncthreads();
     if (s_abort != 0) return;
     const int t = blockIdx.x * kThreads + threadIdx.x;

@@ -63,7 +63,7 @@ typedef struct crb_atomics {
     int32_t numActiveTiles;    /* tiles the fine stage touches                                 */
     int32_t overflow;          /* bit0 subtris, bit1 bin queue, bit2 tile queue, bit3 items */
     int32_t numLargeTris;      /* setup CTAs (256 triangles) that met a sub-triangle spanning > CRB_DIRECT_MAX_TILES tiles on an axis */
-    int32_t reserved;
+    int32_t numQueuedCtas;     /* direct path: setup CTAs that put at least one sub-triangle on a tile queue (0 = everything went the micro way) */
 } crb_atomics;
 
 /* Everything a stage launcher needs; filled by crb_draw_triangles().  Opaque to C callers,

@@ -339,7 +339,10 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         rec = __ldg(&f.activeRecs[activeIdx]);
     }
     if (f.atomics->overflow != 0) return;
-    if (activeIdx >= f.atomics->numActiveTiles) return;
+    if (f.microMode != 0) {
+        if (activeIdx >= f.numTiles) return;
+        if (f.atomics->numQueuedCtas == 0) rec.z = 0;   // nothing was queued in this frame: directAllocKernel did not run, the extents are stale
+    } else if (activeIdx >= f.atomics->numActiveTiles) return;
 
     BlendShaderClass blendProbe;
     const bool deferred = !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);

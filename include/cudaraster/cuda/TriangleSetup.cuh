@@ -185,6 +185,7 @@ static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 
 // reports whether it met such a large sub-triangle: the automatic binning mode only goes direct while there are none.
 struct SetupShared {
     int binCount[CR_MAXBINS_SQR];
+    int queuedAny;   // direct path: this CTA counted a sub-triangle into the tile counters
     int sawLarge;
     int numLarge;
     int largeSlot[CRB_SETUP_THREADS];
@@ -201,6 +202,7 @@ __device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int sl
     const bool large = (t.nx > CRB_DIRECT_MAX_TILES) | (t.ny > CRB_DIRECT_MAX_TILES);
     if (large) sh.sawLarge = 1;
     if (f.directMode) {
+        sh.queuedAny = 1;
         if (large) {
             const int k = atomicAdd(&sh.numLarge, 1);
             if (k < CRB_SETUP_THREADS) { sh.largeSlot[k] = slot; return CRB_TILECODE_GENERAL; }
@@ -308,7 +310,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     int* const s_binCount = sh.binCount;
     gridDepLaunchDependents();
     for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
-    if (threadIdx.x == 0) sh.sawLarge = sh.numLarge = 0;
+    if (threadIdx.x == 0) sh.sawLarge = sh.numLarge = sh.queuedAny = 0;
     __syncthreads();
     gridDepWait();   // the previous frame's kernels still read the work buffers written below
 
@@ -401,6 +403,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     __syncthreads();
     if (threadIdx.x == 0 && sh.sawLarge != 0) atomicAdd(&f.atomics->numLargeTris, 1);   // CTAs with a large sub-triangle (zero / non-zero is what matters)
     if (f.directMode) {
+        if (threadIdx.x == 0 && sh.queuedAny != 0) atomicAdd(&f.atomics->numQueuedCtas, 1);
         // the large sub-triangles of this CTA, all threads together (their headers were written by this CTA before the barrier)
         const int numLarge = min(sh.numLarge, CRB_SETUP_THREADS);
         for (int k = 0; k < numLarge; k++) {
