@@ -640,7 +640,7 @@ int crb_finish(crb_ctx* c, void* stream) {
     if (!c) return CRB_ERR_INVALID;
     CRB_CUDA(c, cudaSetDevice(c->device));
     CRB_CUDA(c, cudaStreamSynchronize((cudaStream_t)stream));
-    int overflowed = 0;
+    int overflowed = 0, firstBad = -1;
     for (int i = 0; i < c->pending; i++) {
         if (c->stageTiming) {
             for (int k = 0; k < 4; k++) {
@@ -655,6 +655,7 @@ int crb_finish(crb_ctx* c, void* stream) {
         noteFrameCounters(c, c->pendingShape[i], a);
         if (a.overflow == 0) continue;
         overflowed++;
+        if (firstBad < 0) firstBad = i;
         if (a.overflow & 1) c->maxSubtris = std::max(c->maxSubtris, a.numSubtris + 4096);
         if (a.overflow & (2 | 8)) c->maxBinEntries = std::max(c->maxBinEntries, a.numBinEntries + a.numBinEntries / 16 + 16384);
         if (a.overflow & 4) c->maxTileEntries = std::max(c->maxTileEntries, a.numTileEntries + a.numTileEntries / 16 + 65536);
@@ -662,7 +663,11 @@ int crb_finish(crb_ctx* c, void* stream) {
     const int n = c->pending;
     c->pending = 0;
     if (overflowed) c->needReset = true;
-    if (overflowed) return setError(c, CRB_ERR_OVERFLOW, "CudaRaster: %d of %d asynchronous frames overflowed a work buffer; capacities grown, redraw", overflowed, n);
+    // An overflowed frame returns early and leaves the self-cleaning scratch state (count matrices, tile counters, visibility
+    // buffer) dirty, so every frame enqueued AFTER it in this batch is suspect as well: all of them must be redrawn.
+    if (overflowed)
+        return setError(c, CRB_ERR_OVERFLOW, "CudaRaster: %d of %d asynchronous frames overflowed a work buffer (first: frame %d of the batch); capacities grown, redraw that frame and all later ones",
+                        overflowed, n, firstBad);
     return CRB_OK;
 }
 

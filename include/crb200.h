@@ -157,8 +157,9 @@ int crb_draw_triangles(crb_ctx* ctx, void* stream);
  * CudaRaster.cpp:326): enqueues one frame with the CURRENT work-buffer capacities and returns without
  * synchronizing, so consecutive frames run back to back on the GPU.  The counters of every frame
  * are copied to pinned host memory; crb_finish() synchronizes `stream` and checks them: CRB_OK, or
- * CRB_ERR_OVERFLOW if some frame overflowed a queue (its output is incomplete; the capacities
- * have been grown, redraw it -- a synchronous crb_draw_triangles() of the same scene first makes
+ * CRB_ERR_OVERFLOW if some frame overflowed a queue (its output is incomplete and so may be that of
+ * every frame enqueued after it in the same batch -- the message names the first one; the capacities
+ * have been grown, redraw them -- a synchronous crb_draw_triangles() of the same scene first makes
  * that impossible).  At most 64 frames may be pending; the 65th call finishes implicitly. */
 int crb_draw_triangles_async(crb_ctx* ctx, void* stream);
 int crb_finish(crb_ctx* ctx, void* stream);

@@ -620,3 +620,40 @@ def test_sort_first_windows_rendered_in_place(raster, crb):
     finally:
         raster.setColorPitch(0)
         raster.setSubViewport(0, 0, 0, 0)
+
+
+def test_async_overflow_is_reported_and_recovered(crb):
+    """A fresh context whose first frames are asynchronous and overflow the tile queue (large triangles, tiny initial
+    capacity): finish() reports it, the synchronous redraw grows the buffers and the frame is right -- on the ordered path
+    and on the direct path (whose per-tile counters and visibility buffer must come back clean)."""
+    import torch
+    w, h = 1024, 768
+    v, i = crb.scenes.random_soup(3000, seed=9, stride_floats=8, size=1.5, clip_fraction=0.0, behind_fraction=0.0)
+    g = util.draw_gold(v, i, w, h, "gouraud", 3)
+    for mode in (0, 2):
+        r = crb.CudaRaster(0)
+        try:
+            r.setBinningMode(mode)
+            color = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8)
+            depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32)
+            vb, ib = torch.from_numpy(v).cuda(), torch.from_numpy(i).cuda()
+            r.setSurfaces(color, depth)
+            r.setPixelPipe(None, crb.pipe_name("gouraud", 0, 3))
+            r.setVertexBuffer(vb, 0)
+            r.setIndexBuffer(ib, 0, i.shape[0])
+            for _ in range(3):
+                r.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+                r.drawTriangles(asynchronous=True)
+            with pytest.raises(crb.CrbError, match="overflowed a work buffer"):
+                r.finish()
+            assert r.getCounters()["overflow"] != 0
+            cc, cd = util.draw_cuda(r, crb, v, i, w, h, "gouraud", 3)
+            assert r.getCounters()["overflow"] == 0 and r.lastFrameDirect() == (mode == 2)
+            _check_surfaces(cc, cd, g, lsb=1)
+            for _ in range(2):      # and asynchronous frames are fine from now on
+                r.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+                r.drawTriangles(asynchronous=True)
+            r.finish()
+            _check_surfaces(r._keep["color"].numpy(), r._keep["depth"].numpy(), g, lsb=1)
+        finally:
+            r.close()
