@@ -131,6 +131,9 @@ CRB_TEXPHONG(2, 3, BlendReplace)
 CRB_PIPE(gouraudCounters, ShadedVertex_gouraud, FragmentShader_gouraud, BlendReplace, 0, 3)
 CRB_PIPE(gouraudCounters, ShadedVertex_gouraud, FragmentShader_gouraud, BlendReplace, 2, 3)
 #undef CR_PROFILING_MODE
+#define CR_PROFILING_MODE ProfilingMode_Timers
+CRB_PIPE(gouraudTimers, ShadedVertex_gouraud, FragmentShader_gouraud, BlendReplace, 0, 3)
+#undef CR_PROFILING_MODE
 #define CR_PROFILING_MODE ProfilingMode_Default
 
 // ---- vertex shaders ----------------------------------------------------------------

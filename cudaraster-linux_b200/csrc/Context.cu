@@ -80,7 +80,7 @@ struct crb_ctx {
     DevBuf tileQueue, tileStart, tileCount, activeTiles, activeRecs;
     DevBuf tileCounter;                  // direct tile path: per-tile counters, zero between frames
     DevBuf profCounters;                 // ProfilingMode_Counters: CRB_PROF_NUM numerator / denominator pairs
-    unsigned long long hostProf[2 * CRB_PROF_NUM] = {};
+    unsigned long long hostProf[CRB_PROF_WORDS] = {};
     DevBuf visBuffer;                    // micro-triangle visibility buffer (8 B / pixel), all ones between frames
     size_t visBytes = 0;                 // extent the current surface uses
     DevBuf tileCursor;                   // direct tile path: per-tile queue cursors (alloc -> scatter)
@@ -291,7 +291,7 @@ int prepareFrame(crb_ctx* c) {
     CRB_CUDA(c, c->tileCounter.reserve(CR_MAXTILES_SQR * 4));
     if (oldTileCounter != c->tileCounter.ptr) c->needReset = true;
     CRB_CUDA(c, c->tileCursor.reserve(CR_MAXTILES_SQR * 4));
-    CRB_CUDA(c, c->profCounters.reserve(2 * CRB_PROF_NUM * sizeof(unsigned long long)));
+    CRB_CUDA(c, c->profCounters.reserve(CRB_PROF_WORDS * sizeof(unsigned long long)));
     f.profCounters = (unsigned long long*)c->profCounters.ptr;
     if (f.microMode) {
         const void* oldVis = c->visBuffer.ptr;
@@ -346,7 +346,7 @@ int launchStages(crb_ctx* c, cudaStream_t s, cudaEvent_t* ev) {
     // several setup CTAs per chunk ADD their bin counts into one column: that (large-scene) layout needs a zeroed matrix.
     // (Letting the bin scatter zero the cells it reads was measured 3x slower than this memset: 466 vs 169 us on C4.)
     if (f->numTris > 0 && f->ctasPerChunk > 1 && !f->directMode) CRB_CUDA(c, cudaMemsetAsync(c->binCountMat.ptr, 0, (size_t)f->matPitch * f->numBins * 4, s));
-    if (c->spec.profilingMode == ProfilingMode_Counters) CRB_CUDA(c, cudaMemsetAsync(c->profCounters.ptr, 0, 2 * CRB_PROF_NUM * sizeof(unsigned long long), s));
+    if (c->spec.profilingMode != ProfilingMode_Default) CRB_CUDA(c, cudaMemsetAsync(c->profCounters.ptr, 0, CRB_PROF_WORDS * sizeof(unsigned long long), s));
     c->needReset = true;   // until every launch of this frame went through
     if (ev) CRB_CUDA(c, cudaEventRecord(ev[0], s));
     int rc = c->pipe.triangleSetup(f, s);
@@ -833,6 +833,35 @@ int crb_get_profiling_info(crb_ctx* c, char* buf, size_t bufSize) {
     const float total = st[0] + st[1] + st[2] + st[3];
     const float pct = total > 0.0f ? 100.0f / total : 0.0f;
     char line[256];
+    if (c->spec.profilingMode == ProfilingMode_Timers && c->hasPipe && c->drawn) {
+        // ProfilingMode_Timers report (CudaRaster.cpp:452-487): each timer as a percentage of its stage's total, with the
+        // reference's format strings for the regions that exist in these kernels (lane-0 clock64() brackets).
+        CRB_CUDA(c, cudaDeviceSynchronize());
+        CRB_CUDA(c, cudaMemcpy(c->hostProf, c->profCounters.ptr, sizeof(c->hostProf), cudaMemcpyDeviceToHost));
+        auto pct = [&](int t, int parent) {
+            return 100.0 * (double)c->hostProf[2 * CRB_PROF_NUM + t] / std::max((double)c->hostProf[2 * CRB_PROF_NUM + parent], 1.0);
+        };
+        s += "ProfilingMode_Timers\n--------------------\n\n";
+        s += "TriangleSetup:\n- Compute\n";
+        snprintf(line, sizeof(line), "  - Cull & snap      %4.1f%%\n", pct(CRB_TIMER_SetupCullSnap, CRB_TIMER_SetupTotal)); s += line;
+        snprintf(line, sizeof(line), "  - Pleq setup       %4.1f%%\n", pct(CRB_TIMER_SetupPleq, CRB_TIMER_SetupTotal)); s += line;
+        snprintf(line, sizeof(line), "  - Clip             %4.1f%%\n", pct(CRB_TIMER_SetupClip, CRB_TIMER_SetupTotal)); s += line;
+        s += "- Memory\n";
+        snprintf(line, sizeof(line), "  - Vertex read      %4.1f%%\n", pct(CRB_TIMER_SetupVertexRead, CRB_TIMER_SetupTotal)); s += line;
+        s += "- Marshal\n";
+        snprintf(line, sizeof(line), "  - Bin histogram    %4.1f%%\n\n", pct(CRB_TIMER_SetupBinning, CRB_TIMER_SetupTotal)); s += line;
+        s += "FineRaster:\n";
+        snprintf(line, sizeof(line), "- Shader             %4.1f%%\n", pct(CRB_TIMER_FineShade, CRB_TIMER_FineTotal)); s += line;
+        s += "- Compute\n";
+        snprintf(line, sizeof(line), "  - Pixel coverage   %4.1f%%\n", pct(CRB_TIMER_FinePixelCoverage, CRB_TIMER_FineTotal)); s += line;
+        snprintf(line, sizeof(line), "  - Z kill           %4.1f%%\n", pct(CRB_TIMER_FineZKill, CRB_TIMER_FineTotal)); s += line;
+        s += "- Memory\n";
+        snprintf(line, sizeof(line), "  - Read tile        %4.1f%%\n", pct(CRB_TIMER_FineReadTile, CRB_TIMER_FineTotal)); s += line;
+        snprintf(line, sizeof(line), "  - Write tile       %4.1f%%\n", pct(CRB_TIMER_FineWriteTile, CRB_TIMER_FineTotal)); s += line;
+        s += "\n";
+        snprintf(buf, bufSize, "%s", s.c_str());
+        return CRB_OK;
+    }
     if (c->spec.profilingMode == ProfilingMode_Counters && c->hasPipe && c->drawn) {
         // ProfilingMode_Counters report (CudaRaster.cpp:424-450): the reference's format strings for the counters that exist
         // in this pipeline; bin / coarse lines come from the frame counters (their reference counters describe its own

@@ -346,6 +346,9 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
 
     BlendShaderClass blendProbe;
     const bool deferred = !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
+    ProfTimer<ProfMode> tmTotal, tm;   // ProfilingMode_Timers only
+    tmTotal.start();
+    tm.start();
 
     FineBatch& sb = s_batch[warp];
     const int tileIdx = rec.x;
@@ -395,6 +398,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     const S32 bx = (tileX << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originX;
     const S32 by = (tileY << (CR_TILE_LOG2 + CR_SUBPIXEL_LOG2)) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
     U32 profFrags = 0, profZTests = 0, profZKills = 0;   // ProfilingMode_Counters only
+    tm.stop(f, CRB_TIMER_FineReadTile);
 
     for (int base = 0; base < queueCount; base += 32) {
         // ---- issue the loads of the batches ahead
@@ -403,6 +407,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         entryB = (base + 64 + lane < queueCount) ? __ldg(&queue[base + 64 + lane]) : -1;
 
         // ---- (1) lane j: coverage mask of triangle j
+        tm.start();
         U32 tileZMax = 0xFFFFFFFFu;
         if (kDepth) tileZMax = __reduce_max_sync(0xFFFFFFFFu, max(depth[0], depth[1]));
         U32 maskLo = 0, maskHi = 0;
@@ -446,6 +451,8 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         sb.dataIdx[lane] = cur.dataIdx;
         __syncwarp();
 
+        tm.stop(f, CRB_TIMER_FinePixelCoverage);
+        tm.start();
         // ---- (2) transpose: triangles covering this lane's two pixels
         const U32 cover[2] = {warpTranspose32(maskLo, lane), warpTranspose32(maskHi, lane)};
 
@@ -492,9 +499,11 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
             }
         }
         __syncwarp();
+        tm.stop(f, CRB_TIMER_FineZKill);   // transposes + the per-pixel depth / ownership loop (in-order pipes: shading and blending too)
         cur = nxt;
     }
 
+    tm.start();
     if (deferred && kQuads) {
         // Visibility is resolved; every quad shades each DISTINCT winner of its four pixels once, on all four
         // lanes (derivatives need the neighbours' values of the same triangle), and a lane keeps the colour
@@ -537,6 +546,8 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         if (winner[1] >= 0 && bs1.m_writeColor) color[1] = bs1.m_color;
     }
 
+    tm.stop(f, CRB_TIMER_FineShade);       // visibility-first pipes: the shading of the surviving fragments
+    tm.start();
     if (ProfMode == ProfilingMode_Counters) {   // reference: FineRaster.inl:221, :684, :702, :733-734
         __syncwarp();
         const U32 zt = __reduce_add_sync(0xFFFFFFFFu, profZTests), zk = __reduce_add_sync(0xFFFFFFFFu, profZKills);
@@ -554,6 +565,8 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         depthPtr[0] = depth[0];
         depthPtr[rowStep] = depth[1];
     }
+    tm.stop(f, CRB_TIMER_FineWriteTile);
+    tmTotal.stop(f, CRB_TIMER_FineTotal);
 }
 
 }  // namespace FW

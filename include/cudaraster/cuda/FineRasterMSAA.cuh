@@ -80,6 +80,8 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
     // quads mode shades in order: where a helper pixel is shaded depends on the depth state at that moment (below)
     const bool deferred = !kQuads && !blendProbe.needsDst() && (FragmentShaderClass::CanDiscard == 0);
 
+    ProfTimer<ProfMode> tmTotal;   // ProfilingMode_Timers: the multi-sample kernel reports its total only
+    tmTotal.start();
     FineBatchMSAA& sb = s_batch[warp];
     U32* tDepth = s_depth[warp];
     U32* tAux = s_aux[warp];
@@ -326,6 +328,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
         if (kDepth || f.deferredClear)
             for (int i = 0; i < N; i++) f.depthBuffer[texel0 + p * rowStep + i * CR_TILE_SIZE] = tDepth[i * CR_TILE_SQR + qBase];
     }
+    tmTotal.stop(f, CRB_TIMER_FineTotal);
 }
 
 // Picks the kernel variant for a pipe; one warp per tile, surplus warps exit at once (the number

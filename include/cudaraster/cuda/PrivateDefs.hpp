@@ -37,12 +37,18 @@ typedef crb_atomics CRAtomics;
 // reference's report that have a meaning in this pipeline, each a numerator / denominator pair (CRProfCounter).
 #define ProfilingMode_Default 0
 #define ProfilingMode_Counters 1
-#define ProfilingMode_Timers 2   // accepted for source compatibility; reports like Default
+#define ProfilingMode_Timers 2   // clock64() brackets around the code regions of the reference's timers that exist here (lane 0 of every warp)
 enum {
     CRB_PROF_SetupViewportCull = 0, CRB_PROF_SetupBackfaceCull, CRB_PROF_SetupBetweenPixelsCull, CRB_PROF_SetupClipped, CRB_PROF_SetupSamplesPerTri,
     CRB_PROF_FineEarlyZCull, CRB_PROF_FineEmptyCull, CRB_PROF_FineZKill, CRB_PROF_FineMSAAKill, CRB_PROF_FineTriPerTile, CRB_PROF_FineFragPerTri,
     CRB_PROF_FineFragPerTile, CRB_PROF_NUM
 };
+// ProfilingMode_Timers (reference: CR_PROFILING_TIMERS, cuda/PrivateDefs.hpp:207-270): clock totals, stored behind the counters
+enum {
+    CRB_TIMER_SetupTotal = 0, CRB_TIMER_SetupVertexRead, CRB_TIMER_SetupCullSnap, CRB_TIMER_SetupPleq, CRB_TIMER_SetupClip, CRB_TIMER_SetupBinning,
+    CRB_TIMER_FineTotal, CRB_TIMER_FineReadTile, CRB_TIMER_FinePixelCoverage, CRB_TIMER_FineZKill, CRB_TIMER_FineShade, CRB_TIMER_FineWriteTile, CRB_TIMER_NUM
+};
+#define CRB_PROF_WORDS (2 * CRB_PROF_NUM + CRB_TIMER_NUM)
 
 // One coarse work item: `count` consecutive entries of one bin's queue.
 struct crb_item {
@@ -128,7 +134,7 @@ struct crb_frame {
                                   // CRB_TILECODE_GENERAL = go through triSubtris / the headers (clipped, refined or large), else
                                   // tile x0 | y0 << 8 | (nx-1) << 16 | (ny-1) << 17 | 1 << 31 of a footprint of at most 2x2 tiles
 
-    unsigned long long* profCounters;   // [CRB_PROF_NUM][2], zeroed before every frame of a ProfilingMode_Counters pipe
+    unsigned long long* profCounters;   // [CRB_PROF_WORDS]: counter pairs, then timers; zeroed before every frame of a profiling pipe
 
     crb_atomics* atomics;         // counters of THIS frame (zero when the frame starts)
     crb_atomics* nextAtomics;     // counters of the next frame: zeroed by this frame's fine raster kernel

@@ -319,10 +319,13 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     const S32 aabbLimit = (1 << (CR_MAXVIEWPORT_LOG2 + CR_SUBPIXEL_LOG2)) - 1;
 
     const int tri = blockIdx.x * CRB_SETUP_THREADS + threadIdx.x;   // one thread per input triangle
+    ProfTimer<ProfMode> tmTotal, tm;
+    tmTotal.start();
     U32 tileCode = 0;
     U32 prof = 0;   // ProfilingMode_Counters: bit 0 triangle, 1 viewport cull, 2 backface cull, 3 between-pixels cull, 4 clipped, 5 survived
     if (tri < f.numTris) {
         prof = 1;
+        tm.start();
         const int3 vidx = make_int3(__ldg(&f.indexBuffer[tri * 3 + 0]), __ldg(&f.indexBuffer[tri * 3 + 1]), __ldg(&f.indexBuffer[tri * 3 + 2]));
         const float4 v0 = __ldg(&verts[(size_t)vidx.x * stride4]);
         const float4 v1 = __ldg(&verts[(size_t)vidx.y * stride4]);
@@ -344,6 +347,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
                        ((__fmul_rn(v0.w, f.cullHiY) < v0.y) & (__fmul_rn(v1.w, f.cullHiY) < v1.y) & (__fmul_rn(v2.w, f.cullHiY) < v2.y)) |
                        ((__fmul_rn(v0.w, f.cullLoY) > v0.y) & (__fmul_rn(v1.w, f.cullLoY) > v1.y) & (__fmul_rn(v2.w, f.cullLoY) > v2.y));
         }
+        tm.stop(f, CRB_TIMER_SetupVertexRead);   // loads + the cull test that first consumes them
         if (outside) {
             f.triSubtris[tri] = 0;
             prof |= 2;
@@ -352,12 +356,14 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
             bool done = false;
             if ((v0.w >= fabsf(v0.z)) & (v1.w >= fabsf(v1.z)) & (v2.w >= fabsf(v2.z))) {
                 SnappedTri s;
+                tm.start();
                 snapTriangle(f, v0, v1, v2, s);
                 const S32 loxy = min(s.lo.x, s.lo.y), hixy = max(s.hi.x, s.hi.y);
                 if (loxy >= -32768 && hixy <= 32767 && hixy - loxy <= aabbLimit) {
                     int2 d1, d2;
                     S32 area;
                     const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
+                    tm.stop(f, CRB_TIMER_SetupCullSnap);
                     f.triSubtris[tri] = (res == 0) ? 1 : 0;
                     prof |= res == 1 ? 4u : res == 2 ? 8u : 32u;
                     if (res == 0) {
@@ -376,21 +382,28 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
                         }
                         if (!nothing) {
                             uint3 zp = make_uint3(0, 0, 0);
+                            tm.start();
                             uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
                                                                                   make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area, &zp, micro);
+                            tm.stop(f, CRB_TIMER_SetupPleq);
+                            tm.start();
                             if (micro) microRaster(f, s.p0.x, s.p0.y, s.p1.x, s.p1.y, s.p2.x, s.p2.y, zp.x, zp.y, zp.z, tri * 8 + 7, pxLoX, pxLoY, pxHiX - pxLoX + 1, pxHiY - pxLoY + 1);
                             else tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh);
+                            tm.stop(f, CRB_TIMER_SetupBinning);
                         }
                     }
                     done = true;
                 }
             }
             if (!done) prof |= 16;
+            if (!done) tm.start();
             if (!done && setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, sh) > 0) { tileCode = CRB_TILECODE_GENERAL; prof |= 32; }
+            if (!done) tm.stop(f, CRB_TIMER_SetupClip);
         }
         if (f.directMode) f.triTileCode[tri] = tileCode;
     }
 
+    tmTotal.stop(f, CRB_TIMER_SetupTotal);
     if (ProfMode == ProfilingMode_Counters) {   // reference: TriangleSetup.inl:255-258, :271, :304-305, :329
         __syncwarp();
         profCountWarp<ProfMode>(f, CRB_PROF_SetupViewportCull, (prof & 2) != 0, (prof & 1) != 0);

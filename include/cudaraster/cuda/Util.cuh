@@ -218,6 +218,22 @@ __device__ __forceinline__ void profCountWarp(const crb_frame& f, int counter, b
     }
 }
 
+// ---- ProfilingMode_Timers (reference: CR_TIMER_IN / CR_TIMER_OUT) -----------------------------------------------
+// Lane 0 of a warp brackets a code region with clock64() and adds the difference to the timer's total.
+template <int ProfMode>
+struct ProfTimer {
+    long long t0;
+    __device__ __forceinline__ void start() {
+        if (ProfMode == ProfilingMode_Timers) t0 = clock64();
+    }
+    __device__ __forceinline__ void stop(const crb_frame& f, int timer) {
+        if (ProfMode == ProfilingMode_Timers) {
+            const long long d = clock64() - t0;
+            if ((threadIdx.x & 31) == 0 && d > 0) atomicAdd(&f.profCounters[2 * CRB_PROF_NUM + timer], (unsigned long long)d);
+        }
+    }
+};
+
 // ---- warp helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ U32 laneId() { return threadIdx.x & 31; }
 __device__ __forceinline__ U32 laneMaskLt() { U32 r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }

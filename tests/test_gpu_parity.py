@@ -657,3 +657,18 @@ def test_async_overflow_is_reported_and_recovered(crb):
             _check_surfaces(r._keep["color"].numpy(), r._keep["depth"].numpy(), g, lsb=1)
         finally:
             r.close()
+
+
+def test_profiling_mode_timers(raster, crb):
+    """CR_PROFILING_MODE = ProfilingMode_Timers (reference: cuda/PrivateDefs.hpp:207-270, CudaRaster.cpp:452-487): same
+    frame as the plain pipe and a report of per-region percentages that are sane."""
+    import re
+    w, h = 320, 200
+    v, i = crb.scenes.random_soup(8000, seed=78, stride_floats=8, size=0.3)
+    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraudTimers", 3)
+    info = raster.getProfilingInfo()
+    _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3), lsb=1)
+    assert "ProfilingMode_Timers" in info and "TriangleSetup:" in info and "FineRaster:" in info
+    vals = [float(x) for x in re.findall(r"([0-9.]+)%", info)]
+    assert len(vals) == 10 and all(0.0 <= x <= 100.0 for x in vals)
+    assert sum(vals[:5]) > 20.0 and sum(vals[5:]) > 20.0 and sum(vals[:5]) <= 100.5 and sum(vals[5:]) <= 100.5

@@ -5,7 +5,7 @@ import torch
 from oracle import binding as G
 
 FLAG_DEPTH, FLAG_LERP = 1, 2
-STRIDE = {"passthrough": 16, "gouraud": 32, "gouraudDiscard": 32, "gouraudQuads": 32, "gouraudCounters": 32, "texPhong": 64}
+STRIDE = {"passthrough": 16, "gouraud": 32, "gouraudDiscard": 32, "gouraudQuads": 32, "gouraudCounters": 32, "gouraudTimers": 32, "texPhong": 64}
 
 
 def draw_cuda(raster, crb, verts, idx, width, height, shader, flags, samples_log2=0, blend="BlendReplace", clear=(0.2, 0.4, 0.8, 1.0),
