@@ -114,13 +114,14 @@ __device__ __forceinline__ void scatterBatch(WarpCells& wc, int32_t* __restrict_
     });
     __syncwarp();
     // the lowest lane of every touched cell advances its cursor and clears the word (a lane that
-    // reads the word after the clear sees 0 and does nothing)
+    // reads the word after the clear sees 0 and does nothing; lanes walk their cells at their own pace,
+    // so the word is read and cleared with atomics -- any interleaving gives the same result)
     forEachCell<SamplesLog2, CellLog2>(fp, winLoX, winLoY, winHiX, winHiY, [&](S32 cx, S32 cy) {
         const int cell = cellOf(cx, cy);
-        const unsigned m = wc.mask[cell];
+        const unsigned m = atomicOr(&wc.mask[cell], 0u);
         if (m != 0 && (m & ltMask) == 0) {
             wc.cursor[cell] += __popc(m);
-            wc.mask[cell] = 0;
+            atomicExch(&wc.mask[cell], 0u);
         }
     });
     __syncwarp();
