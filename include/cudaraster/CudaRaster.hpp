@@ -23,7 +23,8 @@
 //     <cudaraster/cuda/PixelPipe.inl> + CR_DEFINE_PIXEL_PIPE; NULL / "" = pipes built into libcrb200.so.
 //   * DebugParams is accepted and ignored: the product has no host emulation path (the CPU
 //     restatement lives in oracle/ and is test infrastructure only).
-// Additions: setSubViewport() (sort-first windows), drawTrianglesAsync()/finish(), stream selection.
+// Additions: setSubViewport() (sort-first windows), drawTrianglesAsync()/finish(), stream selection, setBinningMode(),
+// setColorLayout()/setColorPitch()/setSurfacePointers() (multi-GPU composites over peer memory), CudaSurface::resolve*().
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -239,6 +240,14 @@ public:
         return true;
     }
     crb_atomics getCounters(void) { init(); crb_atomics a; check(crb_get_counters(m_ctx, &a)); return a; }
+    // binning strategy (crb200.h): 0 = ordered two-level sort only, 1 = automatic, 2 = direct tile path whenever the pipe allows, 3 = 2 without micro-triangles
+    void setBinningMode(int mode) { init(); check(crb_set_binning_mode(m_ctx, mode)); }
+    bool lastFrameDirect(void) { init(); return crb_get_last_frame_direct(m_ctx) != 0; }
+    // colour surface addressing for multi-GPU composites: tile-major layout (peer-memory frame slots), row pitch of a larger image (sort-first windows in place)
+    void setColorLayout(bool tileMajor) { init(); check(crb_set_color_layout(m_ctx, tileMajor ? 1 : 0)); }
+    void setColorPitch(int pitchTexels) { init(); check(crb_set_color_pitch(m_ctx, pitchTexels)); }
+    // surfaces over memory the caller owns (e.g. a frame slot of another GPU mapped with crb_ipc_open); the reference's checks are the caller's business here
+    void setSurfacePointers(void* d_color, void* d_depth, const Vec2i& size, int numSamples = 1) { init(); check(crb_set_surfaces(m_ctx, d_color, d_depth, size.x, size.y, numSamples)); }
     crb_ctx* getContext(void) { init(); return m_ctx; }
 
 private:
