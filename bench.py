@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
+                    help="2 = consecutive frames alternate between two contexts / streams / surface sets, so the (issue-bound) setup of one frame "
+                         "overlaps the (latency-bound) fine raster of the other -- a double-buffered swap chain; 1 = one context, one stream")
     ap.add_argument("--composite", default="auto", choices=["auto", "peer", "push", "nccl"],
                     help="N > 1: 'peer' = every rank renders straight into rank 0's memory over NVLink (CUDA IPC, no gather); 'push' = render locally, "
                          "DMA copy of finished frames into rank 0's slots on a side stream; 'nccl' = NCCL gather of finished frames; 'auto' = peer for 2 GPUs, push beyond "
@@ -237,33 +240,64 @@ def main():
     push = world > 1 and args.composite == "push"
     sink = multigpu.PeerFrameSink(world, rank, color.tensor.numel() * 4, depth=2, device=dev) if (peer or push) else None
     peer_surfaces = [sink.surface(k, (w, h), n_samples) for k in range(2)] if peer else None
-    colors = [color] + ([crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, n_samples, device=dev)] if world > 1 and not peer else [])
+    # Frames in flight: consecutive frames are independent (own view / own surfaces), so they alternate between F contexts, each
+    # with its own stream, work buffers and depth surface -- a double-buffered swap chain.  Triangle setup is issue-bound and the
+    # fine raster latency-bound; two frames in flight fill each other's gaps (tools/probe_overlap.py: +17 % on C2).
+    F = args.frames_in_flight
+    stream = torch.cuda.current_stream(dev)
+    rasters, lane_streams, depths = [raster], [stream], [depth]
+    for _ in range(F - 1):
+        r2 = crb.CudaRaster(local)
+        r2.setPixelPipe(None, crb.pipe_name(shader, s_log2, flags, "BlendReplace"))
+        rasters.append(r2)
+        lane_streams.append(torch.cuda.Stream(device=dev))
+        depths.append(crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32, n_samples, device=dev))
+    colors = [color] + ([crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, n_samples, device=dev)] if (F > 1 or world > 1) and not peer else [])
     gatherer = multigpu.AsyncFrameGather([c.tensor for c in colors], world, rank, dst=0) if world > 1 and not (peer or push) else None
     if push:
         sink.attach_local([c.tensor for c in colors])
-    stream = torch.cuda.current_stream(dev)
 
-    def step(k, asynchronous=True):
+    def step(k, asynchronous=True, lanes=True):
+        lane = k % F if lanes else 0
+        r = rasters[lane]
         vb, ib = copies[k % NUM_INPUT_COPIES]
-        if peer:
-            raster.setSurfaces(peer_surfaces[k % 2], depth)
-            raster.setColorLayout(True)      # tile-major slot: two 128-byte lines per tile cross NVLink instead of eight 32-byte rows
-        elif push:
-            sink.before_render(k)
-            raster.setSurfaces(colors[k % 2], depth)
-        elif world > 1:
-            gatherer.before_render(k)
-            raster.setSurfaces(colors[k % 2], depth)
-        raster.setVertexBuffer(vb, 0)
-        raster.setIndexBuffer(ib, 0, n_tris)
-        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
-        raster.drawTriangles(asynchronous=asynchronous)
-        if peer:
-            sink.publish(k)
-        elif push:
-            sink.push(k)
-        elif world > 1:
-            gatherer.submit(k)
+        with torch.cuda.stream(lane_streams[lane]):
+            if peer:
+                r.setSurfaces(peer_surfaces[k % 2], depths[lane])
+                r.setColorLayout(True)      # tile-major slot: two 128-byte lines per tile cross NVLink instead of eight 32-byte rows
+            elif push:
+                sink.before_render(k)
+                r.setSurfaces(colors[k % 2], depths[lane])
+            elif world > 1:
+                gatherer.before_render(k)
+                r.setSurfaces(colors[k % 2], depths[lane])
+            else:
+                r.setSurfaces(colors[k % len(colors)], depths[lane])
+            r.setVertexBuffer(vb, 0)
+            r.setIndexBuffer(ib, 0, n_tris)
+            r.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+            r.drawTriangles(asynchronous=asynchronous)
+            if peer:
+                sink.publish(k)
+            elif push:
+                sink.push(k)
+            elif world > 1:
+                gatherer.submit(k)
+        return r
+
+    def fork_lanes():
+        for st in lane_streams[1:]:
+            st.wait_stream(stream)
+
+    def join_lanes():
+        if gatherer or push:
+            (gatherer or sink).finish()          # the last gather / copy is inside the timed region
+        for st in lane_streams[1:]:
+            stream.wait_stream(st)
+
+    def finish_all():
+        for r, st in zip(rasters, lane_streams):
+            r.finish(stream=st.cuda_stream)
 
     def sync_all():
         if world > 1:
@@ -272,15 +306,13 @@ def main():
 
     # warm-up: synchronous draws size the work buffers (overflow-retry) and collect per-stage times
     stage_times = {s: [] for s in STAGES}
-    for k in range(max(args.warmup, NUM_INPUT_COPIES)):
-        step(k, asynchronous=False)
-        st = raster.getStats()
+    for k in range(max(args.warmup, NUM_INPUT_COPIES) * F):
+        st = step(k, asynchronous=False).getStats()
         for s, key in zip(STAGES, ("setupTime", "binTime", "coarseTime", "fineTime")):
             stage_times[s].append(st[key] * 1e3)
     for s in STAGES:   # drop the cold first frames
         stage_times[s] = stage_times[s][2:] or stage_times[s]
-    if gatherer or push:
-        (gatherer or sink).finish()
+    join_lanes()
     sync_all()
     launches_per_frame = raster.getLaunchCount()
     direct = raster.lastFrameDirect()   # automatic binning mode: small-triangle frames of an order-independent pipe skip the bin / coarse sort
@@ -292,12 +324,12 @@ def main():
     # checks every frame's counters -- it raises if any frame overflowed a queue
     sync_all()
     e0.record(stream)
+    fork_lanes()
     for k in range(args.steps):
         step(k)
-    if gatherer or push:
-        (gatherer or sink).finish()          # the last gather / copy is inside the timed region
+    join_lanes()
     e1.record(stream)
-    raster.finish()
+    finish_all()
     sync_all()
     clocks = sampler.result()
     total_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -306,16 +338,29 @@ def main():
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
     value = world * n_tris / (ms_per_step * 1e-3) / 1e6
+    value_one = None
+    if F > 1:   # the same K frames with one frame in flight (one context, one stream), for comparison
+        sync_all()
+        e0.record(stream)
+        for k in range(args.steps):
+            step(k, lanes=False)
+        join_lanes()
+        e1.record(stream)
+        finish_all()
+        sync_all()
+        one_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(one_ms, op=dist.ReduceOp.MAX)
+        value_one = world * n_tris / (float(one_ms.item()) / args.steps * 1e-3) / 1e6
 
     # ---- the same K frames again with the five stage events recorded on every frame (this splits the kernel chain, so
     # it is a separate timed region): live per-stage / per-kernel durations for the roofline
     raster.setStageTiming(True)
     sync_all()
     for k in range(args.steps):
-        step(k)
-    if gatherer or push:
-        (gatherer or sink).finish()
-    raster.finish()
+        step(k, lanes=False)
+    join_lanes()
+    finish_all()
     sync_all()
     live = raster.getStageTiming()
     raster.setStageTiming(False)
@@ -387,8 +432,10 @@ def main():
         mean = {s: live[s] for s in STAGES}                               # asynchronous frames of the timed region, events on every frame
         line = {
             "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "frames_per_s": world * 1e3 / ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
+            "frames_per_s": world * 1e3 / ms_per_step, "frames_in_flight": F, "value_one_frame_in_flight": value_one, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
             "config": {"workload": desc, "triangles": int(n_tris), "resolution": [w, h], "samples": n_samples, "pipe": crb.pipe_name(shader, s_log2, flags, "BlendReplace"),
+                       "frames_in_flight": ("%d: consecutive frames alternate between %d contexts / streams / surface sets (double-buffered swap chain); stage_ms and roofline are measured with one frame in flight" % (F, F)
+                                            if F > 1 else "1"),
                        "binning": ("direct tile path: setup counts tiles -> queue allocation (timed as binRaster) -> unordered atomic scatter (timed as coarseRaster) -> fine raster keeps the (depth, index) minimum"
                                    if direct else "general path: stable two-level sort (bin raster, coarse raster), queues in submission order"),
                        "sharding": "1 GPU" if world == 1 else ("view-parallel: 1 view per rank per step; " + (
@@ -437,7 +484,8 @@ def main():
     if sink:
         sync_all()
         sink.close()
-    raster.close()
+    for r in rasters:
+        r.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
