@@ -238,7 +238,13 @@ def main():
         args.composite = "peer" if world <= 2 else "push"
     peer = world > 1 and args.composite == "peer"
     push = world > 1 and args.composite == "push"
-    sink = multigpu.PeerFrameSink(world, rank, color.tensor.numel() * 4, depth=2, device=dev) if (peer or push) else None
+    sink = None
+    if peer or push:
+        try:
+            sink = multigpu.PeerFrameSink(world, rank, color.tensor.numel() * 4, depth=2, device=dev)
+        except multigpu.PeerMemoryUnavailable as e:   # raised on every rank: fall back to the NCCL gather together
+            print("bench.py: %s -- falling back to --composite nccl" % e, file=sys.stderr)
+            args.composite, peer, push = "nccl", False, False
     peer_surfaces = [sink.surface(k, (w, h), n_samples) for k in range(2)] if peer else None
     # Frames in flight: consecutive frames are independent (own view / own surfaces), so they alternate between F contexts, each
     # with its own stream, work buffers and depth surface -- a double-buffered swap chain.  Triangle setup is issue-bound and the

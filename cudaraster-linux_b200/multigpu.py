@@ -12,6 +12,7 @@ The only exchange step is the composite: disjoint framebuffer rectangles (or who
 gathered to the display rank.  No reduction operator is needed because regions are disjoint.
 """
 import math
+import os
 
 MAX_VIEWPORT = 2048
 
@@ -119,6 +120,10 @@ class AsyncFrameGather:
         return self.recv[k % len(self.surfaces)]
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """Raised on EVERY rank when some rank cannot map the display rank's frame slots."""
+
+
 class PeerFrameSink:
     """View-parallel / sort-first composite WITHOUT a gather: rank `dst` owns the frame slots of all ranks (`depth`
     deep) and exports them through CUDA IPC; every rank renders straight into its own slot, so the fine raster's colour
@@ -141,17 +146,25 @@ class PeerFrameSink:
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         handle = torch.zeros(64, dtype=torch.uint8, device=dev)
         base = ctypes.c_void_p()
+        ok = True
         if rank == dst:
             buf = ctypes.create_string_buffer(64)
-            if self.lib.crb_ipc_alloc(total, ctypes.byref(base), buf) != 0:
-                raise RuntimeError("PeerFrameSink: crb_ipc_alloc failed")
-            handle.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+            ok = self.lib.crb_ipc_alloc(total, ctypes.byref(base), buf) == 0
+            if ok:
+                handle.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
         dist.broadcast(handle, src=dst)
         if rank != dst:
             raw = bytes(handle.cpu().numpy().tobytes())
-            if self.lib.crb_ipc_open(raw, ctypes.byref(base)) != 0:
-                raise RuntimeError("PeerFrameSink: crb_ipc_open failed (no peer access between the GPUs?)")
-        self.base = base.value
+            ok = self.lib.crb_ipc_open(raw, ctypes.byref(base)) == 0 and not os.environ.get("CRB_TEST_FAIL_IPC")
+        self.base = base.value if ok else None
+        # every rank must agree: a box without peer access between some pair of GPUs fails on SOME ranks only
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if self.base:
+                (self.lib.crb_ipc_free if rank == dst else self.lib.crb_ipc_close)(self.base)
+            self.base = None
+            raise PeerMemoryUnavailable("PeerFrameSink: CUDA IPC / peer access is not available between all GPUs of this job")
         dist.barrier()
 
     def slot_pointer(self, k, rank=None):
