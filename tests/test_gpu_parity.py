@@ -600,9 +600,11 @@ def test_sort_first_windows_rendered_in_place(raster, crb):
     fw, fh = 512, 384
     v, i = crb.scenes.random_soup(6000, seed=31, stride_floats=8, size=0.5)
     full_c, full_d = util.draw_cuda(raster, crb, v, i, fw, fh, "gouraud", 3)
-    frame = torch.zeros((fh, fw), dtype=torch.int32, device="cuda")
     vb, ib = torch.from_numpy(v).cuda(), torch.from_numpy(i).cuda()
     try:
+      for mode in (0, 2):   # ordered path, direct path (+ micro-triangles)
+        raster.setBinningMode(mode)
+        frame = torch.zeros((fh, fw), dtype=torch.int32, device="cuda")
         for (x0, y0, w, h) in [(0, 0, 256, 192), (256, 0, 256, 192), (0, 192, 256, 192), (256, 192, 256, 192)]:
             color = crb.CudaSurface.from_pointer(frame.data_ptr() + 4 * (y0 * fw + x0), (w, h), crb.CudaSurface.FORMAT_RGBA8)
             depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32)
@@ -614,10 +616,12 @@ def test_sort_first_windows_rendered_in_place(raster, crb):
             raster.setSubViewport(fw, fh, x0, y0)
             raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
             raster.drawTriangles()
+            assert raster.lastFrameDirect() == (mode == 2)
             assert np.array_equal(depth.numpy(), full_d[y0:y0 + h, x0:x0 + w])
         torch.cuda.synchronize()
         assert np.array_equal(frame.cpu().numpy().view(np.uint32), full_c)
     finally:
+        raster.setBinningMode(1)
         raster.setColorPitch(0)
         raster.setSubViewport(0, 0, 0, 0)
 
