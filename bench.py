@@ -13,7 +13,14 @@ N > 1   one process per GPU (torchrun); view-parallel sharding: e
         (the composite is inside the timed region).  Weak scaling: per-GPU work is fixed.
 
 Prints ONE JSON line (rank 0).  Keys: see the task contract; additionally
-  stage_ms     median per-stage device time (the reference's five event positions)
+  value        N = 1: the metric SURVEY.md 8(d) defines -- T / t_frame, t_frame = the sum of the four stage intervals between CUDA
+               events at the reference's five positions (CudaRaster.cpp:593-661), ONE frame in flight, median over the K frames;
+               N > 1: N * T / (K-frame bracket / K), same frames (one in flight per rank, stage events on), max over ranks,
+               composite inside
+  value_unbroken_chain / value_two_in_flight   the same K frames without stage events (one kernel chain) / alternating
+               between two contexts (double-buffered swap chain): throughput modes, not the headline
+  enqueue_ms_per_step  host time spent enqueueing one frame (a number near ms_per_step means the run is host-bound)
+  stage_ms     mean per-stage device time (the reference's five event positions)
   roofline     dominant kernel: algorithmic bytes per launch / mean launch duration vs measured HBM peak
   cpu_baseline the CPU oracle (oracle/golden.hpp) timed on this box's host cores on a bounded sample
   ref_kernels  the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref), if they run here
@@ -104,6 +111,17 @@ def make_scene(workload):
     return desc, verts, idx, w, h, shader, s_log2, flags, k_var
 
 
+def config_dict(workload, n_gpus):
+    """The `config` of the JSON line -- the same dict in both arms (b200 and reference)."""
+    desc, fn, kw, w, h, shader, s_log2, flags, k_var = WORKLOADS[workload]
+    import cudaraster_linux_b200 as crb
+    n_tris = {"c2": 1_000_000, "c3": 5_000_000, "c4": 10_000_000}[workload]
+    return {"workload": desc, "triangles": n_tris, "resolution": [w, h], "samples": 1 << s_log2, "pipe": crb.pipe_name(shader, s_log2, flags, "BlendReplace"),
+            "sharding": "1 GPU" if n_gpus == 1 else "view-parallel: 1 view of the mesh per rank per step, colour frames composited on rank 0 inside the timed region",
+            "l2": "GPU arm: inputs rotate over %d device copies and each frame rewrites its intermediates (setup records, queues, surfaces): working set > 126 MB L2; "
+                  "CPU arm: one frame per step" % NUM_INPUT_COPIES}
+
+
 def stage_bytes(counts, num_tris, k_var, pixels, samples, lerp):
     """Per-stage split of B_alg (DESIGN.md 'algorithmic bytes'); the four add up to B_alg."""
     c = counts
@@ -133,19 +151,19 @@ def run_reference_arm(args, emit):
     desc, verts, idx, w, h, shader, s_log2, flags, k_var = make_scene(args.workload)
     threads = G.hardware_threads()
     n = idx.shape[0]
-    # bounded sample: the first `sample_tris` triangles of the frame (whole frame when it is cheap)
-    sample = n if args.workload == "c2" else min(n, 1_000_000)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    # bounded sample: ONE whole frame per step (the oracle renders C2 / C3 / C4 in 1 / 3 / 2 s on 8 threads)
+    sample = n
+    for _ in range(1 if args.warmup > 0 else 0):
         cpu_oracle_frame(verts, idx[:sample], w, h, shader, s_log2, flags, threads, False)
     times = [cpu_oracle_frame(verts, idx[:sample], w, h, shader, s_log2, flags, threads, False)[0] for _ in range(args.steps)]
-    ms = 1e3 * sum(times) / len(times)
+    ms = 1e3 * statistics.median(times)
     value = sample / (ms * 1e-3) / 1e6
     line = {
         "impl": "reference", "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "frames_per_s": 1e3 / ms * (sample / n), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32",
-        "data": "synthetic", "config": {"workload": desc, "triangles": int(n), "resolution": [w, h]},
+        "data": "synthetic", "config": config_dict(args.workload, args.gpus),
         "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": threads, "kind": "port",
-                         "sample": "%d of %d triangles of the frame per step, all %d host threads (oracle/golden.hpp; the reference has no runnable CPU path)" % (sample, n, threads)},
+                         "sample": "one whole frame (%d triangles) per step, median of %d, all %d host threads (oracle/golden.hpp; the reference has no runnable CPU path)" % (sample, args.steps, threads)},
         "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -272,7 +290,7 @@ def main():
         with torch.cuda.stream(lane_streams[lane]):
             if peer:
                 r.setSurfaces(peer_surfaces[k % 2], depths[lane])
-                r.setColorLayout(True)      # tile-major slot: two 128-byte lines per tile cross NVLink instead of eight 32-byte rows
+                r.setColorLayout(n_samples == 1)   # tile-major slot (single sample only): two 128-byte lines per tile cross NVLink instead of eight 32-byte rows
             elif push:
                 sink.before_render(k)
                 r.setSurfaces(colors[k % 2], depths[lane])
@@ -325,53 +343,61 @@ def main():
     launches_per_frame = raster.getLaunchCount()
     direct = raster.lastFrameDirect()   # automatic binning mode: small-triangle frames of an order-independent pipe skip the bin / coarse sort
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # timed region: K frames enqueued back to back (crb_draw_triangles_async), one finish() that
-    # checks every frame's counters -- it raises if any frame overflowed a queue
-    sync_all()
-    e0.record(stream)
-    fork_lanes()
-    for k in range(args.steps):
-        step(k)
-    join_lanes()
-    e1.record(stream)
-    finish_all()
-    sync_all()
-    clocks = sampler.result()
-    total_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    ms_per_step = total_ms / args.steps
-    value = world * n_tris / (ms_per_step * 1e-3) / 1e6
-    value_one = None
-    if F > 1:   # the same K frames with one frame in flight (one context, one stream), for comparison
+    # N = 1: the whole frame loop is ONE C call (crb_draw_batch_async) -- no Python between frames
+    def make_batch(r, lane_colors, lane_depth):
+        frames = []
+        for k in range(args.steps):
+            vb, ib = copies[k % NUM_INPUT_COPIES]
+            frames.append({"color": lane_colors[k % len(lane_colors)], "depth": lane_depth, "vb": vb, "ib": ib, "num_tris": n_tris, "clear": ((0.2, 0.4, 0.8, 1.0), 1.0)})
+        return r.makeBatch(frames)
+    batch_one = make_batch(raster, colors, depth) if world == 1 else None
+
+    def timed_region(lanes, stage_events):
+        """K frames enqueued back to back, bracketed by barrier + synchronize and two events on the main stream.  Returns
+        (device ms per step, max over ranks; host ms spent enqueueing one step)."""
+        raster.setStageTiming(stage_events)
         sync_all()
         e0.record(stream)
-        for k in range(args.steps):
-            step(k, lanes=False)
+        if lanes:
+            fork_lanes()
+        t0 = time.perf_counter()
+        if world == 1 and not lanes:
+            raster.drawBatch(batch_one)
+        else:
+            for k in range(args.steps):
+                step(k, lanes=lanes)
+        enqueue_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         join_lanes()
         e1.record(stream)
         finish_all()
         sync_all()
-        one_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(one_ms, op=dist.ReduceOp.MAX)
-        value_one = world * n_tris / (float(one_ms.item()) / args.steps * 1e-3) / 1e6
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, enqueue_ms
 
-    # ---- the same K frames again with the five stage events recorded on every frame (this splits the kernel chain, so
-    # it is a separate timed region): live per-stage / per-kernel durations for the roofline
-    raster.setStageTiming(True)
-    sync_all()
-    for k in range(args.steps):
-        step(k, lanes=False)
-    join_lanes()
-    finish_all()
-    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- (1) THE METRIC (SURVEY.md 8d): K frames, ONE frame in flight, the reference's five stage events on every frame
+    bracket_ms, enqueue_ms = timed_region(lanes=False, stage_events=True)
+    clocks = sampler.result()
     live = raster.getStageTiming()
+    per_frame = raster.getStageTimingFrames()[-args.steps:]
+    frame_ms = float(np.median(per_frame.sum(axis=1))) if len(per_frame) else bracket_ms
     raster.setStageTiming(False)
+    if world == 1:
+        ms_per_step = frame_ms                                   # t_frame = sum of the four stage intervals, median over the K frames
+    else:
+        ms_per_step = bracket_ms                                 # max over ranks, composite included
+    value = world * n_tris / (ms_per_step * 1e-3) / 1e6
+    # ---- (2) the same K frames as one unbroken kernel chain (no stage events), and (3) alternating between two contexts
+    chain_ms, chain_enqueue_ms = timed_region(lanes=False, stage_events=False)
+    value_chain = world * n_tris / (chain_ms * 1e-3) / 1e6
+    value_two = None
+    if F > 1:
+        two_ms, _ = timed_region(lanes=True, stage_events=False)
+        value_two = world * n_tris / (two_ms * 1e-3) / 1e6
 
     composite_ok = None
     if peer or push:
@@ -440,19 +466,23 @@ def main():
         mean = {s: live[s] for s in STAGES}                               # asynchronous frames of the timed region, events on every frame
         line = {
             "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "frames_per_s": world * 1e3 / ms_per_step, "frames_in_flight": F, "value_one_frame_in_flight": value_one, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
-            "config": {"workload": desc, "triangles": int(n_tris), "resolution": [w, h], "samples": n_samples, "pipe": crb.pipe_name(shader, s_log2, flags, "BlendReplace"),
-                       "frames_in_flight": ("%d: consecutive frames alternate between %d contexts / streams / surface sets (double-buffered swap chain); stage_ms and roofline are measured with one frame in flight" % (F, F)
-                                            if F > 1 else "1"),
-                       "binning": ("direct tile path: setup counts tiles -> queue allocation (timed as binRaster) -> unordered atomic scatter (timed as coarseRaster) -> fine raster keeps the (depth, index) minimum"
-                                   if direct else "general path: stable two-level sort (bin raster, coarse raster), queues in submission order"),
-                       "sharding": "1 GPU" if world == 1 else ("view-parallel: 1 view per rank per step; " + (
-                           "every rank renders straight into its frame slot in rank 0's memory (CUDA IPC peer memory over NVLink / NVSwitch): the composite is the render, no gather; frames verified on rank 0 after the timed region: %s" % composite_ok
-                           if peer else "every rank renders locally and a DMA copy on a side stream (overlapped with the next frame) pushes the finished frame into its slot in rank 0's memory (CUDA IPC peer memory over NVLink / NVSwitch); frames verified on rank 0 after the timed region: %s" % composite_ok
-                           if push else "every step's colour frames are gathered to rank 0 over NCCL inside the timed region (side stream, overlapped with the next frame's rendering)")),
-                       "l2": "inputs rotate over %d device copies (%.0f MB) and each frame rewrites ~100 MB of intermediates, > 126 MB L2" %
-                             (NUM_INPUT_COPIES, NUM_INPUT_COPIES * (verts.nbytes + idx.nbytes) / 1e6)},
-            "stage_ms": mean, "device_frame_ms": sum(mean.values()), "stage_ms_sync_draw": med, "stage_frames": live["frames"], "gpu_launches": (launches_per_frame + (1 if peer else 0)) * args.steps, "clocks": clocks,
+            "frames_per_s": world * 1e3 / ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
+            "config": config_dict(args.workload, world),
+            "timing": ("N = 1: value = T / median over the K frames of (sum of the four stage intervals, CUDA events at the reference's five positions), one frame in flight"
+                       if world == 1 else "N > 1: value = N * T * K / bracket (barrier + synchronize on both sides, CUDA events, max over ranks), one frame in flight per rank, stage events on every frame, composite inside"),
+            "bracket_ms_per_step": bracket_ms, "enqueue_ms_per_step": enqueue_ms, "enqueue": ("one C call for the K frames (crb_draw_batch_async)" if world == 1 else "Python loop over crb_draw_triangles_async + composite calls"),
+            "value_unbroken_chain": value_chain, "unbroken_chain_ms_per_step": chain_ms, "unbroken_chain_enqueue_ms_per_step": chain_enqueue_ms,
+            "value_two_in_flight": value_two,
+            "notes": {"binning": ("direct tile path: setup counts tiles -> queue allocation (timed as binRaster) -> unordered atomic scatter (timed as coarseRaster) -> fine raster keeps the (depth, index) minimum"
+                                  if direct else "general path: stable two-level sort (bin raster, coarse raster), queues in submission order"),
+                      "composite": None if world == 1 else (
+                          "every rank renders straight into its frame slot in rank 0's memory (CUDA IPC peer memory over NVLink / NVSwitch): the composite is the render, no gather; frames verified on rank 0 after the timed region: %s" % composite_ok
+                          if peer else "every rank renders locally and a DMA copy on a side stream (overlapped with the next frame) pushes the finished frame into its slot in rank 0's memory (CUDA IPC peer memory over NVLink / NVSwitch); frames verified on rank 0 after the timed region: %s" % composite_ok
+                          if push else "every step's colour frames are gathered to rank 0 over NCCL inside the timed region (side stream, overlapped with the next frame's rendering)"),
+                      "value_two_in_flight": "consecutive frames alternate between 2 contexts / streams / surface sets (double-buffered swap chain)",
+                      "input_bytes_rotating": NUM_INPUT_COPIES * (verts.nbytes + idx.nbytes)},
+            "stage_ms": mean, "device_frame_ms": sum(mean.values()), "device_frame_ms_median": frame_ms, "stage_ms_sync_draw": med, "stage_frames": live["frames"],
+            "gpu_launches": (launches_per_frame + (1 if peer else 0)) * args.steps, "clocks": clocks,
             "e2e": {"value": world * n_tris / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "crb_draw_triangles_host_async (pinned host vertices+indices in, colour surface out; upload/render/download of consecutive frames overlap)",
                     "blocking_value": world * n_tris / (e2e_blocking_ms * 1e-3) / 1e6, "blocking_ms_per_step": e2e_blocking_ms,
@@ -463,12 +493,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             from oracle import binding as G
             threads = G.hardware_threads()
-            sample = n_tris if args.workload == "c2" else min(n_tris, 1_000_000)
+            sample = n_tris    # one WHOLE frame: bounded (1-3 s on 8 threads) and it gives the counts of the roofline for every workload
             t, r = cpu_oracle_frame(verts, idx[:sample], w, h, shader, s_log2, flags, threads, True)
             line["cpu_baseline"] = {"value": sample / t / 1e6, "unit": "Mtris/s", "cores": threads, "kind": "port",
                                     "sample": "%d of %d triangles, one frame, oracle/golden.hpp on %d host threads (%.2f s)" % (sample, n_tris, threads, t)}
-            if sample == n_tris:
-                counts = r["counts"]
+            counts = r["counts"]
         peak, peak_src = measured_peak()
         if counts is not None:
             sb = stage_bytes(counts, n_tris, k_var, ((w + 7) & ~7) * ((h + 7) & ~7), n_samples, bool(flags & 2))

@@ -28,6 +28,13 @@ class Atomics(ctypes.Structure):
                 ("numLargeTris", ctypes.c_int32), ("numQueuedCtas", ctypes.c_int32)]
 
 
+class BatchFrame(ctypes.Structure):
+    """crb_batch_frame (include/crb200.h)."""
+    _fields_ = [("color", ctypes.c_void_p), ("depth", ctypes.c_void_p), ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("numSamples", ctypes.c_int32),
+                ("vertices", ctypes.c_void_p), ("vertexBytes", ctypes.c_size_t), ("indices", ctypes.c_void_p), ("numTris", ctypes.c_int32),
+                ("clear", ctypes.c_int32), ("clearColor", ctypes.c_uint32), ("clearDepth", ctypes.c_uint32)]
+
+
 class WorkBuffers(ctypes.Structure):
     _fields_ = [("triSubtris", ctypes.c_void_p), ("triHeader", ctypes.c_void_p), ("triData", ctypes.c_void_p), ("maxSubtris", ctypes.c_int32),
                 ("binQueue", ctypes.c_void_p), ("binStart", ctypes.c_void_p), ("binTotal", ctypes.c_void_p), ("numBins", ctypes.c_int32),
@@ -82,6 +89,8 @@ def load_library():
         "crb_get_stats": (i32, [vp, ctypes.POINTER(f32 * 4)]),
         "crb_set_stage_timing": (i32, [vp, i32]),
         "crb_get_stage_timing": (i32, [vp, ctypes.POINTER(ctypes.c_double * 4), ctypes.POINTER(i32)]),
+        "crb_get_stage_timing_frames": (i32, [vp, vp, i32]),
+        "crb_draw_batch_async": (i32, [vp, vp, i32, vp]),
         "crb_get_counters": (i32, [vp, ctypes.POINTER(Atomics)]),
         "crb_get_profiling_info": (i32, [vp, ctypes.c_char_p, ctypes.c_size_t]),
         "crb_get_launch_count": (i32, [vp]),
@@ -112,7 +121,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
-                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
+                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_stage_timing_frames", "crb_draw_batch_async", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
                     "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_set_color_pitch", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_ipc_copy", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
@@ -340,6 +349,38 @@ class CudaRaster:
         out, n = (ctypes.c_double * 4)(), ctypes.c_int(0)
         self._check(self.lib.crb_get_stage_timing(self.ctx, ctypes.byref(out), ctypes.byref(n)))
         return {"triangleSetup": out[0], "binRaster": out[1], "coarseRaster": out[2], "fineRaster": out[3], "frames": n.value}
+
+    def getStageTimingFrames(self, max_frames=4096):
+        """[frames][4] float32 array: the four stage intervals (ms) of every asynchronous frame finished since setStageTiming(True)."""
+        out = np.zeros((max_frames, 4), np.float32)
+        n = self.lib.crb_get_stage_timing_frames(self.ctx, out.ctypes.data, max_frames)
+        return out[:n]
+
+    def makeBatch(self, frames):
+        """frames: list of dicts {color, depth (CudaSurface), vb, ib (tensors), num_tris, clear=((r,g,b,a), depth) or None} ->
+        a crb_batch_frame array for drawBatch (the tensors / surfaces must outlive it)."""
+        arr = (BatchFrame * len(frames))()
+        for b, fr in zip(arr, frames):
+            color, depth = fr.get("color"), fr.get("depth")
+            if color is not None:
+                b.color, b.depth = color.tensor.data_ptr(), depth.tensor.data_ptr()
+                b.width, b.height, b.numSamples = color.size[0], color.size[1], color.num_samples
+            vb, ib = fr.get("vb"), fr.get("ib")
+            if vb is not None:
+                b.vertices, b.vertexBytes = vb.data_ptr(), vb.numel() * vb.element_size()
+            if ib is not None:
+                b.indices, b.numTris = ib.data_ptr(), int(fr["num_tris"])
+            clear = fr.get("clear")
+            if clear is not None:
+                b.clear = 1
+                b.clearColor = self.lib.crb_pack_abgr(*[float(c) for c in clear[0]])
+                b.clearDepth = self.lib.crb_encode_clear_depth(float(clear[1]))
+        return arr
+
+    def drawBatch(self, batch, stream=None):
+        """crb_draw_batch_async: every frame of `batch` (makeBatch) enqueued by ONE C call; call finish()."""
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(self.lib.crb_draw_batch_async(self.ctx, ctypes.cast(batch, ctypes.c_void_p), len(batch), ctypes.c_void_p(s)))
 
     def getProfilingInfo(self):
         buf = ctypes.create_string_buffer(2048)

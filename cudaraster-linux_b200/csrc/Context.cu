@@ -92,6 +92,12 @@ struct crb_ctx {
     unsigned long long shapeHash = 0;    // shape of the frame shapeNumLarge was measured on
     int shapeNumLarge = 0;
     unsigned long long pendingShape[64] = {};
+    struct PendingFrame {                // what crb_finish needs to know about an asynchronous frame
+        int numTris = 0;
+        cudaStream_t stream = nullptr;
+        bool hadClear = false;           // the frame consumed a deferred clear (restored if it must be redrawn)
+        uint32_t clearColor = 0, clearDepth = 0;
+    } pendingFrame[64];
     bool lastFrameDirect = false;
     bool microOff = false;               // crb_set_binning_mode(3)
     bool microEnabled = true;            // CRB_MICRO=0 keeps small triangles on the tile queues (A/B measurements)
@@ -113,6 +119,7 @@ struct crb_ctx {
     cudaEvent_t ringEv[kTimingRing][5] = {};
     double stageSumMs[4] = {0, 0, 0, 0};
     int stageFrames = 0;
+    std::vector<float> stageFrameMs;     // 4 intervals per finished frame since crb_set_stage_timing (crb_get_stage_timing_frames)
 
     // crb_draw_triangles_host_async: upload / render / download of consecutive frames overlap
     struct HostPipeline {
@@ -459,16 +466,22 @@ const char* crb_last_error(const crb_ctx* c) { return c ? c->err.c_str() : "null
 
 int crb_set_surfaces(crb_ctx* c, void* d_color, void* d_depth, int width, int height, int numSamples) {
     if (!c) return CRB_ERR_INVALID;
-    c->color = (uint32_t*)d_color;
-    c->depth = (uint32_t*)d_depth;
-    if (!d_color && !d_depth) return CRB_OK;
-    // CudaRaster::setSurfaces / CudaSurface::CudaSurface checks and messages
+    if (!d_color && !d_depth) {
+        c->color = c->depth = nullptr;
+        return CRB_OK;
+    }
+    // CudaRaster::setSurfaces / CudaSurface::CudaSurface checks and messages.  Nothing is committed before every check passed: a
+    // failed call leaves the context WITHOUT surfaces (a later draw fails with "Surfaces not set!") instead of new pointers
+    // with the old dimensions.
+    c->color = c->depth = nullptr;
     if (!d_color) return setError(c, CRB_ERR_INVALID, "CudaRaster: No color buffer specified!");
     if (!d_depth) return setError(c, CRB_ERR_INVALID, "CudaRaster: No depth buffer specified!");
     if (std::min(width, height) <= 0) return setError(c, CRB_ERR_INVALID, "CudaSurface: Size must be positive!");
     if (std::max(width, height) > CR_MAXVIEWPORT_SIZE) return setError(c, CRB_ERR_LIMIT, "CudaSurface: CR_MAXVIEWPORT_SIZE exceeded!");
     if (numSamples > 8) return setError(c, CRB_ERR_LIMIT, "CudaSurface: numSamples cannot exceed 8!");
     if (numSamples < 1 || popc8(numSamples) != 1) return setError(c, CRB_ERR_INVALID, "CudaSurface: numSamples must be a power of two!");
+    c->color = (uint32_t*)d_color;
+    c->depth = (uint32_t*)d_depth;
     c->width = width;
     c->height = height;
     c->numSamples = numSamples;
@@ -640,17 +653,25 @@ int crb_finish(crb_ctx* c, void* stream) {
     if (!c) return CRB_ERR_INVALID;
     CRB_CUDA(c, cudaSetDevice(c->device));
     CRB_CUDA(c, cudaStreamSynchronize((cudaStream_t)stream));
+    // frames may have been enqueued on other streams than the one passed in: their counter copies must have landed too
+    for (int i = 0; i < c->pending; i++) {
+        bool seen = c->pendingFrame[i].stream == (cudaStream_t)stream;
+        for (int k = 0; k < i && !seen; k++) seen = c->pendingFrame[k].stream == c->pendingFrame[i].stream;
+        if (!seen) CRB_CUDA(c, cudaStreamSynchronize(c->pendingFrame[i].stream));
+    }
     int overflowed = 0, firstBad = -1;
     for (int i = 0; i < c->pending; i++) {
         if (c->stageTiming) {
             for (int k = 0; k < 4; k++) {
                 float ms = 0.0f;
                 if (cudaEventElapsedTime(&ms, c->ringEv[i][k], c->ringEv[i][k + 1]) == cudaSuccess) c->stageSumMs[k] += ms;
+                if (c->stageFrameMs.size() < (size_t)4 * 65536) c->stageFrameMs.push_back(ms);
             }
             c->stageFrames++;
         }
         crb_atomics a = c->hostAtomics[1 + i];
-        a.numSubtris += c->numTris;
+        a.numSubtris += c->pendingFrame[i].numTris;
+        if (overflowed && a.overflow != 0 && (a.overflow & 16) != 0) continue;   // a frame skipped because an EARLIER frame of the batch overflowed (sticky flag, bit 4): its counters mean nothing
         c->lastAtomics = a;
         noteFrameCounters(c, c->pendingShape[i], a);
         if (a.overflow == 0) continue;
@@ -662,7 +683,12 @@ int crb_finish(crb_ctx* c, void* stream) {
     }
     const int n = c->pending;
     c->pending = 0;
-    if (overflowed) c->needReset = true;
+    if (overflowed) {
+        c->needReset = true;
+        // the frames from firstBad on must be redrawn: give the first of them its deferred clear back
+        const crb_ctx::PendingFrame& pf = c->pendingFrame[firstBad];
+        if (pf.hadClear) { c->deferredClear = true; c->clearColor = pf.clearColor; c->clearDepth = pf.clearDepth; }
+    }
     // An overflowed frame returns early and leaves the self-cleaning scratch state (count matrices, tile counters, visibility
     // buffer) dirty, so every frame enqueued AFTER it in this batch is suspect as well: all of them must be redrawn.
     if (overflowed)
@@ -697,6 +723,8 @@ int crb_draw_triangles_async(crb_ctx* c, void* stream) {
     if (rc != CRB_OK) return rc;
     CRB_CUDA(c, cudaMemcpyAsync(&c->hostAtomics[1 + c->pending], c->frame.atomics, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
     c->pendingShape[c->pending] = frameShape(c);
+    crb_ctx::PendingFrame& pf = c->pendingFrame[c->pending];
+    pf.numTris = numTris; pf.stream = s; pf.hadClear = c->deferredClear; pf.clearColor = c->clearColor; pf.clearDepth = c->clearDepth;
     c->pending++;
     c->deferredClear = false;
     c->drawn = true;
@@ -804,6 +832,29 @@ int crb_set_stage_timing(crb_ctx* c, int enable) {
     c->stageTiming = enable != 0;
     c->stageSumMs[0] = c->stageSumMs[1] = c->stageSumMs[2] = c->stageSumMs[3] = 0.0;
     c->stageFrames = 0;
+    c->stageFrameMs.clear();
+    return CRB_OK;
+}
+
+int crb_get_stage_timing_frames(crb_ctx* c, float* outMs, int maxFrames) {
+    if (!c || (maxFrames > 0 && !outMs)) return 0;
+    const int n = std::min((int)(c->stageFrameMs.size() / 4), std::max(maxFrames, 0));
+    if (n > 0) std::memcpy(outMs, c->stageFrameMs.data(), (size_t)n * 4 * sizeof(float));
+    return n;
+}
+
+int crb_draw_batch_async(crb_ctx* c, const crb_batch_frame* frames, int numFrames, void* stream) {
+    if (!c || numFrames < 0 || (numFrames > 0 && !frames)) return CRB_ERR_INVALID;
+    for (int i = 0; i < numFrames; i++) {
+        const crb_batch_frame& b = frames[i];
+        int rc = CRB_OK;
+        if (b.color || b.depth) rc = crb_set_surfaces(c, b.color, b.depth, b.width, b.height, b.numSamples);
+        if (rc == CRB_OK && b.vertices) rc = crb_set_vertex_buffer(c, b.vertices, b.vertexBytes);
+        if (rc == CRB_OK && b.indices) rc = crb_set_index_buffer(c, b.indices, b.numTris);
+        if (rc == CRB_OK && b.clear) rc = crb_deferred_clear(c, b.clearColor, b.clearDepth);
+        if (rc == CRB_OK) rc = crb_draw_triangles_async(c, stream);
+        if (rc != CRB_OK) return rc;
+    }
     return CRB_OK;
 }
 

@@ -25,14 +25,18 @@ def grid_for(parts):
     return 1 << ((lg + 1) // 2), 1 << (lg // 2)
 
 
+def parent_cells(full_w, full_h):
+    """The parent viewports of a frame: the cells of the even grid of <= 2048 px cells that csrc/Context.cu prepareFrame()
+    sets the triangles up in (ceil(full / 2048) cells per axis, cell size rounded up to 8 px).  Returns
+    (cellW, cellH, columns, rows); every sort-first window must lie inside ONE of these cells."""
+    ncx, ncy = -(-full_w // MAX_VIEWPORT), -(-full_h // MAX_VIEWPORT)
+    return _cell(full_w, ncx), _cell(full_h, ncy), ncx, ncy
+
+
 def min_parts(full_w, full_h):
-    """Fewest power-of-two parts whose rectangles respect the 2048 px viewport limit."""
-    parts = 1
-    while True:
-        cols, rows = grid_for(parts)
-        if _cell(full_w, cols) <= MAX_VIEWPORT and _cell(full_h, rows) <= MAX_VIEWPORT:
-            return parts
-        parts *= 2
+    """Fewest rectangles a frame can be rendered in: one per parent cell."""
+    _, _, ncx, ncy = parent_cells(full_w, full_h)
+    return ncx * ncy
 
 
 def _cell(full, n):
@@ -40,18 +44,28 @@ def _cell(full, n):
 
 
 def split_frame(full_w, full_h, parts):
-    """Cuts the frame into `parts` rectangles (x0, y0, w, h); origins are multiples of 8, rectangles
-    tile the frame exactly, row-major order."""
-    parts = max(parts, min_parts(full_w, full_h))
-    cols, rows = grid_for(parts)
-    cw, ch = _cell(full_w, cols), _cell(full_h, rows)
+    """Cuts the frame into AT LEAST `parts` rectangles (x0, y0, w, h), row-major order: first into the parent cells of
+    prepareFrame() (see parent_cells), then every cell into the same power-of-two grid of sub-rectangles, so that no
+    rectangle ever straddles a cell whatever the frame size (5K, 8K, odd widths).  Origins are multiples of 8 and the
+    rectangles tile the frame exactly."""
+    cw, ch, ncx, ncy = parent_cells(full_w, full_h)
+    sub = 1
+    while ncx * ncy * sub < parts:
+        sub *= 2
+    cols, rows = grid_for(sub)
     rects = []
-    for r in range(rows):
-        for c in range(cols):
-            x0, y0 = c * cw, r * ch
-            w, h = min(cw, full_w - x0), min(ch, full_h - y0)
-            if w > 0 and h > 0:
-                rects.append((x0, y0, w, h))
+    for cy in range(ncy):
+        for cx in range(ncx):
+            px0, py0 = cx * cw, cy * ch
+            pw, ph = min(cw, full_w - px0), min(ch, full_h - py0)
+            sw, sh = _cell(pw, cols), _cell(ph, rows)
+            for r in range(rows):
+                for c in range(cols):
+                    x0, y0 = px0 + c * sw, py0 + r * sh
+                    w, h = min(sw, px0 + pw - x0), min(sh, py0 + ph - y0)
+                    if w > 0 and h > 0:
+                        rects.append((x0, y0, w, h))
+    rects.sort(key=lambda q: (q[1], q[0]))
     return rects
 
 

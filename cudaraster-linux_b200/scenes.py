@@ -208,3 +208,14 @@ def apply_view(verts, m):
     out[:, 0] = m[0] * x + m[1] * y + m[2] * w
     out[:, 1] = m[3] * x + m[4] * y + m[5] * w
     return out
+
+
+def grid_gouraud_view(nx=1000, ny=500, view=0, num_views=48, **kw):
+    """BASELINE config 5(ii): view `view` of the 48 (6 cube faces x 8 positions) views of the C2 mesh."""
+    v, i = grid_gouraud(nx, ny, **kw)
+    return apply_view(v, view_matrix_variants(num_views)[view]), i
+
+
+def grid_gouraud_4k(nx=2000, ny=1000, seed=0xC0DE0005):
+    """BASELINE config 5(i): C2-style 4 M-triangle grid for the 3840x2160 sort-first frame."""
+    return grid_gouraud(nx, ny, seed=seed)

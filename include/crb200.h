@@ -190,6 +190,26 @@ int crb_get_stats(crb_ctx* ctx, float outSeconds[4]);
  * crb_set_stage_timing was last called. */
 int crb_set_stage_timing(crb_ctx* ctx, int enable);
 int crb_get_stage_timing(crb_ctx* ctx, double outMeanMs[4], int* outFrames);
+/* The same per frame: the four stage intervals (ms) of up to maxFrames frames finished since crb_set_stage_timing, oldest
+ * first, 4 floats each; returns the number of frames written.  Mtris/s as SURVEY.md 8(d) defines it is
+ * numTris / median over frames of the sum of a frame's four intervals. */
+int crb_get_stage_timing_frames(crb_ctx* ctx, float* outMs, int maxFrames);
+
+/* A stream of frames in ONE call (new): for every element, the state setters that are non-NULL (surfaces, vertex buffer, index
+ * buffer, deferred clear) followed by crb_draw_triangles_async on `stream` -- the frame loop of an application, or of the
+ * benchmark, without a host-language round trip per frame.  Stops at the first error. */
+typedef struct crb_batch_frame {
+    void* color;                 /* NULL with depth NULL: keep the current surfaces */
+    void* depth;
+    int32_t width, height, numSamples;
+    const void* vertices;        /* NULL: keep the current vertex buffer */
+    size_t vertexBytes;
+    const void* indices;         /* NULL: keep the current index buffer */
+    int32_t numTris;
+    int32_t clear;               /* != 0: crb_deferred_clear(clearColor, clearDepth) before the draw */
+    uint32_t clearColor, clearDepth;
+} crb_batch_frame;
+int crb_draw_batch_async(crb_ctx* ctx, const crb_batch_frame* frames, int numFrames, void* stream);
 /* g_crAtomics read-back (CudaRaster.cpp:326). */
 int crb_get_counters(crb_ctx* ctx, crb_atomics* out);
 /* CudaRaster::getProfilingInfo (CudaRaster.cpp:367-497): the ProfilingMode_Default report, or -- for a pipe compiled with

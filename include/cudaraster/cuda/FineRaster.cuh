@@ -32,7 +32,13 @@ namespace FW {
 //    kernel right after it is read was measured 8 us slower on C2: 31.2 vs 23.5 us for the coarse stage.)
 // Must run after gridDepWait() and before any early return.
 __device__ __forceinline__ void finishFrameState(const crb_frame& f) {
-    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = 0;
+    // An overflowed frame leaves the self-cleaning scratch state dirty (its kernels return early), so the frames enqueued behind
+    // it must not run on it: the flag is handed on (bit 4 = "an earlier frame of the batch overflowed") and every later frame
+    // early-outs until the host has seen it (crb_finish) and reset the state.
+    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) {
+        const int sticky = (threadIdx.x == (int)(offsetof(crb_atomics, overflow) / sizeof(int)) && f.atomics->overflow != 0) ? 16 : 0;
+        reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = sticky;
+    }
     const int rows = min(f.atomics->numCoarseItems, f.maxItems);
     const int total = rows * (CR_BIN_SQR / 4);
     int4* mat = reinterpret_cast<int4*>(f.tileCountMat);
@@ -285,6 +291,23 @@ __device__ __forceinline__ void fineFetch(FineFetch& t, const crb_frame& f, S32 
     if ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0) t.z = __ldg(&f.triData[(size_t)t.dataIdx * 4]);
 }
 
+// Tile-level early Z (reference: FineRaster.inl:229-241: "zmin >= tileZMax -> skip the triangle").  The reference's cull is not a
+// pure optimisation: the header's zmin bounds the plane depth from below only where the fixed-point plane is well conditioned --
+// a sub-triangle left by clipping at w ~ 0 can span the guard band with a depth plane whose values at covered pixels lie BELOW
+// its own zmin, and whether the reference culls it depends on how its fragments happened to be batched.  Here a triangle is
+// dropped only when that is provably invisible in the result: the header test must say so AND the plane itself, evaluated
+// without wrap-around over the box of samples the triangle can cover in this tile ([x0, x1] x [y0, y1], sample units relative
+// to the tile's first sample), must stay at or behind the tile's farthest depth.  Every fragment of a culled triangle would then
+// fail the LESS test (direct path: could not even tie), so the frame equals the one rendered without early Z -- the oracle's.
+__device__ __forceinline__ bool earlyZCull(U32 zminHdr, U32 tileZMax, bool direct, U32 zbTile, U32 zx, U32 zy, int x0, int x1, int y0, int y1) {
+    if (zminHdr < tileZMax || (direct && zminHdr == tileZMax)) return false;
+    const S64 sx = (S64)(S32)zx, sy = (S64)(S32)zy;   // any representative of the slope mod 2^32 gives the same depths at integer samples
+    const S64 lo = (S64)zbTile + min(sx * x0, sx * x1) + min(sy * y0, sy * y1);
+    const S64 hi = (S64)zbTile + max(sx * x0, sx * x1) + max(sy * y0, sy * y1);
+    if (lo < 0 || hi > (S64)0xFFFFFFFFll) return false;   // the U32 plane wraps inside the box: its minimum is not at a corner
+    return direct ? lo > (S64)tileZMax : lo >= (S64)tileZMax;
+}
+
 // Per-warp staging of the current batch, lane-indexed SoA: the per-fragment gathers of the
 // ownership loop hit distinct banks for distinct triangles and broadcast for equal ones.
 struct FineBatch {
@@ -422,7 +445,10 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
             // early Z against the tile's farthest depth; on the direct path (unordered queue) a triangle AT that depth
             // may still beat a later-submitted winner of the same depth, so only strictly farther ones are dropped
             const U32 zminHdr = cur.h.w & 0xFFFFF000u;
-            const bool live = cur.entry >= 0 && (!kDepth || zminHdr < tileZMax || (f.directMode != 0 && zminHdr == tileZMax)) && colLo <= colHi && rowLo <= rowHi;
+            const U32 zbTile = cur.z.z + cur.z.x * (U32)(tileX << CR_TILE_LOG2) + cur.z.y * (U32)(tileY << CR_TILE_LOG2);
+            const bool inTile = cur.entry >= 0 && colLo <= colHi && rowLo <= rowHi;
+            const bool culledZ = kDepth && inTile && earlyZCull(zminHdr, tileZMax, f.directMode != 0, zbTile, cur.z.x, cur.z.y, colLo, colHi, rowLo, rowHi);
+            const bool live = inTile && !culledZ;
             const bool small = (colHi - colLo < 4) & (rowHi - rowLo < 4) & (hiX - loX < (64 << CR_SUBPIXEL_LOG2)) & (hiY - loY < (64 << CR_SUBPIXEL_LOG2));
             if ((f.debugFlags & 1) == 0 && __all_sync(0xFFFFFFFFu, !live || small)) {
                 if (live) coverSmall4x4(x0, y0, x1, y1, x2, y2, bx, by, colLo, rowLo, colHi - colLo + 1, rowHi - rowLo + 1, maskLo, maskHi);
@@ -433,7 +459,7 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
             }
             if (ProfMode == ProfilingMode_Counters) {   // reference: FineRaster.inl:235, :621-622
                 const bool fetched = cur.entry >= 0;
-                const bool earlyZ = fetched && kDepth && !(zminHdr < tileZMax || (f.directMode != 0 && zminHdr == tileZMax));
+                const bool earlyZ = culledZ;
                 const bool considered = fetched && !earlyZ;
                 profCountWarp<ProfMode>(f, CRB_PROF_FineEarlyZCull, earlyZ, fetched);
                 profCountWarp<ProfMode>(f, CRB_PROF_FineEmptyCull, considered && (maskLo | maskHi) == 0, considered);

@@ -141,6 +141,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
             tileZMax = __reduce_max_sync(0xFFFFFFFFu, m);
         }
         U32 maskLo = 0, maskHi = 0;
+        bool culledZ = false;
         if (cur.entry >= 0) {
             S32 a[3], b[3], c[3];
             setupTileEdges(cur.h, bx, by, a, b, c);
@@ -148,10 +149,18 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
             sb.a1[lane] = a[1]; sb.b1[lane] = b[1]; sb.c1[lane] = c[1];
             sb.a2[lane] = a[2]; sb.b2[lane] = b[2]; sb.c2[lane] = c[2];
             const U32 zminHdr = cur.h.w & 0xFFFFF000u;
-            if (!kDepth || zminHdr < tileZMax || (f.directMode != 0 && zminHdr == tileZMax)) {   // direct path: see FineRaster.cuh
-                const S32 y0 = (S32)cur.h.x >> 16, y1 = (S32)cur.h.y >> 16, y2 = (S32)cur.h.z >> 16;
-                const int rowLo = max((min(min(y0, y1), y2) - by - kMaxOfs + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0);
-                const int rowHi = min((max(max(y0, y1), y2) - by + kMaxOfs) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
+            const S32 x0 = (S32)(S16)(cur.h.x & 0xFFFF), x1 = (S32)(S16)(cur.h.y & 0xFFFF), x2 = (S32)(S16)(cur.h.z & 0xFFFF);
+            const S32 y0 = (S32)cur.h.x >> 16, y1 = (S32)cur.h.y >> 16, y2 = (S32)cur.h.z >> 16;
+            // pixels of the tile with a sample inside the triangle's bounding box
+            const int colLo = max((min(min(x0, x1), x2) - bx - kMaxOfs + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0);
+            const int colHi = min((max(max(x0, x1), x2) - bx + kMaxOfs) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
+            const int rowLo = max((min(min(y0, y1), y2) - by - kMaxOfs + (CR_SUBPIXEL_SIZE - 1)) >> CR_SUBPIXEL_LOG2, 0);
+            const int rowHi = min((max(max(y0, y1), y2) - by + kMaxOfs) >> CR_SUBPIXEL_LOG2, CR_TILE_SIZE - 1);
+            const U32 zbTile = cur.z.z + cur.z.x * (U32)(tileX << (CR_TILE_LOG2 + SamplesLog2)) + cur.z.y * (U32)(tileY << (CR_TILE_LOG2 + SamplesLog2));
+            // early Z: only what provably cannot change the frame (earlyZCull, FineRaster.cuh); direct path: ties are kept
+            culledZ = kDepth && colLo <= colHi && rowLo <= rowHi &&
+                      earlyZCull(zminHdr, tileZMax, f.directMode != 0, zbTile, cur.z.x, cur.z.y, colLo * N, colHi * N + N - 1, rowLo * N, rowHi * N + N - 1);
+            if (!culledZ && colLo <= colHi && rowLo <= rowHi) {
                 // relax every edge by its largest possible gain over the sample offsets (|ox|, |oy| <= kMaxOfs);
                 // c is clamped to +-2^30 and the relaxation is < 2^21, so nothing wraps
                 S32 cr[3];
@@ -162,7 +171,7 @@ static __global__ void __launch_bounds__(FineWarps<SamplesLog2>::Value * 32) fin
         }
         if (ProfMode == ProfilingMode_Counters) {   // reference: FineRaster.inl:235, :969-970 (pixel mask = conservative coverage)
             const bool fetched = cur.entry >= 0;
-            const bool earlyZ = fetched && kDepth && !((cur.h.w & 0xFFFFF000u) < tileZMax || (f.directMode != 0 && (cur.h.w & 0xFFFFF000u) == tileZMax));
+            const bool earlyZ = culledZ;
             const bool considered = fetched && !earlyZ;
             profCountWarp<ProfMode>(f, CRB_PROF_FineEarlyZCull, earlyZ, fetched);
             profCountWarp<ProfMode>(f, CRB_PROF_FineEmptyCull, considered && (maskLo | maskHi) == 0, considered);

@@ -37,4 +37,10 @@ def test_product_arm_line():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
-    assert "sm_mhz" in d["clocks"] and "workload" in d["config"] and "binning" in d["config"]
+    assert "sm_mhz" in d["clocks"] and "workload" in d["config"] and "binning" in d["notes"]
+    # value is the metric SURVEY.md 8(d) defines: T / (sum of the four stage intervals), one frame in flight
+    assert abs(d["value"] - 1.0 / d["device_frame_ms_median"] * 1e3) / d["value"] < 1e-6 and d["value_unbroken_chain"] > 0 and d["value_two_in_flight"] > 0
+    assert d["enqueue_ms_per_step"] > 0
+    # both arms describe the workload with the same `config`
+    ref = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], 600)
+    assert ref["config"] == d["config"]

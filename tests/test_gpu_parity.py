@@ -250,11 +250,10 @@ def test_back_to_back_frames_of_different_shape(raster, crb):
              (640, 360, 25000, 0, 1.5), (320, 200, 3000, 0, 0.8)]
     for rep in range(2):
         for w, h, n, s_log2, size in cases:
-            # 1080p: no triangles with a vertex at w ~ 0-.  Their clipped remains can span the whole guard band with an
-            # overflowed depth plane whose values fall BELOW the triangle's own zmin; the outcome then depends on when the
-            # early-Z cull (reference: FineRaster.inl:229-241) samples the tile's max depth, i.e. it is not defined by the
-            # reference's semantics either ("known divergences").
-            v, i = crb.scenes.random_soup(max(n, 1), seed=4000 + n + rep, stride_floats=8, size=size, behind_fraction=0.0 if w > 1000 else 0.05)
+            # the 1080p case keeps its triangles with a vertex at w ~ 0-: their clipped remains can span the whole guard band with
+            # an overflowed depth plane whose values fall BELOW the triangle's own zmin, which is why the tile-level early-Z
+            # only drops what the plane itself proves invisible (earlyZCull, FineRaster.cuh) and the frame equals the oracle's
+            v, i = crb.scenes.random_soup(max(n, 1), seed=4000 + n + rep, stride_floats=8, size=size)
             if n == 0:
                 i = i[:0]
             cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, s_log2)

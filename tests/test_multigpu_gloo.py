@@ -88,12 +88,16 @@ def test_sort_first_and_view_parallel_world2(tmp_path):
 def test_split_frame_properties():
     import cudaraster_linux_b200  # noqa: F401  (registers the package alias)
     from cudaraster_linux_b200 import multigpu
-    for fw, fh in ((3840, 2160), (1920, 1080), (2048, 2048), (1000, 600)):
-        for parts in (1, 2, 4, 8):
+    from oracle.binding import parent_cell
+    for fw, fh in ((3840, 2160), (1920, 1080), (2048, 2048), (1000, 600), (5120, 2880), (7680, 4320), (6000, 3000), (3010, 2000), (2049, 17)):
+        for parts in (1, 2, 4, 8, 16):
             rects = multigpu.split_frame(fw, fh, parts)
             cover = np.zeros((fh, fw), np.int32)
             for (x0, y0, w, h) in rects:
                 assert x0 % 8 == 0 and y0 % 8 == 0 and 0 < w <= 2048 and 0 < h <= 2048
+                # the containment check of csrc/Context.cu prepareFrame(), replayed: a window lies inside ONE parent cell
+                parent_cell(fw, x0, w)
+                parent_cell(fh, y0, h)
                 cover[y0:y0 + h, x0:x0 + w] += 1
             assert (cover == 1).all(), "rectangles must tile the frame exactly"
             assert len(rects) >= max(parts, multigpu.min_parts(fw, fh))
