@@ -537,7 +537,8 @@ __global__ void __launch_bounds__(kThreads, CRB_SCATTER_MIN_BLOCKS) directScatte
     if (f.atomics->numTileEntries == 0) return;   // nothing was queued (every triangle went the micro way): final since directAllocKernel ended
     const int base = (blockIdx.x * kThreads + threadIdx.x) * kScatterTris;
     uint4 c4 = make_uint4(0, 0, 0, 0);
-    if (base < f.numTris) c4 = __ldg(reinterpret_cast<const uint4*>(f.triTileCode + base));   // the buffer is padded to a multiple of 4 words
+    // (the buffer is padded to a multiple of 4 words; batches of 32 triangles none of which was queued left no words, only their flag)
+    if (base < f.numTris && f.batchQueued[base >> 5] != 0) c4 = __ldg(reinterpret_cast<const uint4*>(f.triTileCode + base));
     const bool abort = f.atomics->overflow != 0;   // a queue overflowed: the frame is redone (the host resets the counters); nothing raises the flag during this grid
     __syncthreads();
     if (abort) return;

@@ -85,6 +85,7 @@ struct crb_ctx {
     size_t visBytes = 0;                 // extent the current surface uses
     DevBuf tileCursor;                   // direct tile path: per-tile queue cursors (alloc -> scatter)
     DevBuf triTileCode;                  // direct tile path: one word per input triangle (setup -> scatter)
+    DevBuf batchQueued;                  // direct tile path: one byte per batch of 32 triangles (did setup leave their words in triTileCode?)
     // Binning strategy (crb_set_binning_mode): the direct path runs when the pipe is order independent and the last
     // completed frame of the same SHAPE (triangle count, surface, window, pipe) reported no large triangle.
     int binningMode = 1;                 // 0 never, 1 automatic, 2 try on every eligible frame
@@ -308,6 +309,7 @@ int prepareFrame(crb_ctx* c) {
         c->visBytes = std::max(c->visBytes, need);
     }
     if (f.directMode) CRB_CUDA(c, c->triTileCode.reserve(((size_t)std::max(c->numTris, 1) + 4) * 4));
+    if (f.directMode) CRB_CUDA(c, c->batchQueued.reserve((size_t)std::max(c->numTris, 1) / 32 + 16));
 
     f.triSubtris = (uint8_t*)c->triSubtris.ptr;
     f.triHeader = (uint4*)c->triHeader.ptr;
@@ -329,6 +331,7 @@ int prepareFrame(crb_ctx* c) {
     f.tileCursor = (int32_t*)c->tileCursor.ptr;
     f.visBuffer = (unsigned long long*)c->visBuffer.ptr;
     f.triTileCode = (uint32_t*)c->triTileCode.ptr;
+    f.batchQueued = (uint8_t*)c->batchQueued.ptr;
     f.atomics = (crb_atomics*)c->atomics.ptr + c->atomicsParity;
     f.nextAtomics = (crb_atomics*)c->atomics.ptr + (c->atomicsParity ^ 1);
     if (oldBinMat != c->binCountMat.ptr || oldTileMat != c->tileCountMat.ptr || c->lastNumBins != f.numBins || c->lastMatPitch != f.matPitch ||
@@ -437,7 +440,7 @@ int crb_destroy(crb_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
-                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode, &c->visBuffer, &c->profCounters};
+                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode, &c->batchQueued, &c->visBuffer, &c->profCounters};
     for (DevBuf* b : bufs) b->release();
     if (c->hp.init) {
         cudaStreamDestroy(c->hp.up);

@@ -130,6 +130,7 @@ struct crb_frame {
     // its tile state and writes the neutral value (all ones) back, so the buffer is clean for the next frame.
     int32_t microMode;            // 1 = on (implies directMode)
     unsigned long long* visBuffer; // [heightPixels][widthPixels]
+    uint8_t* batchQueued;         // [ceil(numTris / 32)] 1 = the 32 triangles of the batch have their words in triTileCode (one of them was queued)
     uint32_t* triTileCode;        // [numTris] what the scatter pass needs to know about a triangle in ONE word: 0 = nothing to place,
                                   // CRB_TILECODE_GENERAL = go through triSubtris / the headers (clipped, refined or large), else
                                   // tile x0 | y0 << 8 | (nx-1) << 16 | (ny-1) << 17 | 1 << 31 of a footprint of at most 2x2 tiles

@@ -16,6 +16,10 @@
 #pragma once
 #include "Overlap.cuh"
 
+#ifndef CRB_PLEQ_UNCLIPPED
+#define CRB_PLEQ_UNCLIPPED 1  // u / v planes of an unclipped triangle: two of the three vertex values are exactly zero
+#endif
+
 namespace FW {
 
 struct SnappedTri {
@@ -71,7 +75,7 @@ __device__ __forceinline__ int prepareTriangle(const crb_frame& f, const Snapped
 }
 
 // Writes one sub-triangle record and returns its packed header (for the bin histogram).
-template <int SamplesLog2, U32 RenderModeFlags>
+template <int SamplesLog2, U32 RenderModeFlags, bool Unclipped = false>
 __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, uint4* td, int3 vidx, float4 v0, float4 v1, float4 v2,
                                                float2 b0, float2 b1, float2 b2, const SnappedTri& s, int2 d1, int2 d2, S32 area, uint3* zpOut = nullptr,
                                                bool microOnly = false) {
@@ -119,8 +123,14 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
         float3 uvert = make_float3(__fmul_rn(b0.x, wvert.x), __fmul_rn(b1.x, wvert.y), __fmul_rn(b2.x, wvert.z));
         float3 vvert = make_float3(__fmul_rn(b0.y, wvert.x), __fmul_rn(b1.y, wvert.y), __fmul_rn(b2.y, wvert.z));
         uint3 wp = setupPleq(wvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
-        uint3 up = setupPleq(uvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
-        uint3 vp = setupPleq(vvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+        uint3 up, vp;
+        if (CRB_PLEQ_UNCLIPPED && Unclipped) {   // b = (0,0), (1,0), (0,1): uvert = (0, wvert.y, 0), vvert = (0, 0, wvert.z)
+            up = setupPleqUnit<1>(wvert.y, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+            vp = setupPleqUnit<2>(wvert.z, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+        } else {
+            up = setupPleq(uvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+            vp = setupPleq(vvert, wv0, d1, d2, areaRcp, SamplesLog2 + 1);
+        }
         const U32 ox2 = (U32)f.subX0 << (SamplesLog2 + 1), oy2 = (U32)f.subY0 << (SamplesLog2 + 1);
         wp.z += wp.x * ox2 + wp.y * oy2;
         up.z += up.x * ox2 + up.y * oy2;
@@ -183,29 +193,32 @@ static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 
 // more than CRB_DIRECT_MAX_TILES tiles on an axis are put on a per-CTA list and counted by the whole CTA together
 // at the end of the kernel (a thread walking thousands of tiles alone would be a long tail).  Either way the CTA
 // reports whether it met such a large sub-triangle: the automatic binning mode only goes direct while there are none.
-struct SetupShared {
-    int binCount[CR_MAXBINS_SQR];
-    int queuedAny;   // direct path: this CTA counted a sub-triangle into the tile counters
-    int sawLarge;
-    int numLarge;
+struct SetupCtaShared {   // per CTA
+    int sawLarge;          // the CTA met a large sub-triangle
+    int numLarge;          // the CTA's list of large sub-triangles (record slots)
     int largeSlot[CRB_SETUP_THREADS];
+    int binCount[CR_MAXBINS_SQR];   // bin histogram of the CTA's chunk (general path)
+};
+struct SetupShared {      // a VIEW of the binning scratch in shared memory (passed by value: two pointers)
+    int* queuedAny;        // direct path: a sub-triangle of this CTA went to the tile counters
+    SetupCtaShared* cta;
 };
 
 // Returns the triangle's tile code (crb_frame::triTileCode) on the direct path, 0 on the general path.
 // DeferSmall: the caller counts a footprint of at most 2x2 tiles itself from the returned code.  (Unused: counting
 // warp-aggregated with __match_any_sync at the end of the kernel measured 37.6 vs 38.5 us on C2 but 225 vs 215 us on C4.)
 template <int SamplesLog2, bool DeferSmall>
-__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, SetupShared& sh) {
-    int* s_binCount = sh.binCount;
+__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, const SetupShared sh) {
+    int* s_binCount = sh.cta->binCount;
     TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
     const CellRange t = cellRange<CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1);
     const bool large = (t.nx > CRB_DIRECT_MAX_TILES) | (t.ny > CRB_DIRECT_MAX_TILES);
-    if (large) sh.sawLarge = 1;
+    if (large) sh.cta->sawLarge = 1;
     if (f.directMode) {
-        sh.queuedAny = 1;
+        *sh.queuedAny = 1;
         if (large) {
-            const int k = atomicAdd(&sh.numLarge, 1);
-            if (k < CRB_SETUP_THREADS) { sh.largeSlot[k] = slot; return CRB_TILECODE_GENERAL; }
+            const int k = atomicAdd(&sh.cta->numLarge, 1);
+            if (k < CRB_SETUP_THREADS) { sh.cta->largeSlot[k] = slot; return CRB_TILECODE_GENERAL; }
             // list full (only clipped triangles can push more than one entry per thread): count it alone
         }
         if (!t.refine) {   // at most 2x2 tiles, never refined: the rectangle IS the tile set
@@ -247,7 +260,7 @@ __device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int sl
 
 // Cold path: clip against the view window, fan the polygon, re-snap / re-cull every sub-triangle.
 template <int SamplesLog2, U32 RenderModeFlags>
-__device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, int3 vidx, float4 v0, float4 v1, float4 v2, SetupShared& sh) {
+__device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, int3 vidx, float4 v0, float4 v1, float4 v2, const SetupShared sh) {
     const F32 lo[3] = {f.clipLoX, f.clipLoY, -1.0f}, hi[3] = {f.clipHiX, f.clipHiY, 1.0f};
     const float4 d1 = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), __fsub_rn(v1.w, v0.w));
     const float4 d2 = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), __fsub_rn(v2.w, v0.w));
@@ -304,19 +317,114 @@ __device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, in
     return numSub;
 }
 
+// One input triangle, vertices in registers: cull / snap / cull / plane equations / records / binning.  Returns the triangle's
+// tile code (direct path).  prof: ProfilingMode_Counters bits (1 viewport cull, 2 backface cull, 3 between-pixels cull, 4 clipped, 5 survived).
+template <int SamplesLog2, U32 RenderModeFlags, int ProfMode>
+__device__ __forceinline__ U32 setupOneTriangle(const crb_frame& f, int tri, int3 vidx, float4 v0, float4 v1, float4 v2, const SetupShared sh, U32& prof, ProfTimer<ProfMode>& tm) {
+    const S32 aabbLimit = (1 << (CR_MAXVIEWPORT_LOG2 + CR_SUBPIXEL_LOG2)) - 1;
+    U32 tileCode = 0;
+    // all three vertices outside one plane of the view window -> culled
+    const F32 wx0h = __fmul_rn(v0.w, f.clipHiX), wx1h = __fmul_rn(v1.w, f.clipHiX), wx2h = __fmul_rn(v2.w, f.clipHiX);
+    const F32 wx0l = __fmul_rn(v0.w, f.clipLoX), wx1l = __fmul_rn(v1.w, f.clipLoX), wx2l = __fmul_rn(v2.w, f.clipLoX);
+    const F32 wy0h = __fmul_rn(v0.w, f.clipHiY), wy1h = __fmul_rn(v1.w, f.clipHiY), wy2h = __fmul_rn(v2.w, f.clipHiY);
+    const F32 wy0l = __fmul_rn(v0.w, f.clipLoY), wy1l = __fmul_rn(v1.w, f.clipLoY), wy2l = __fmul_rn(v2.w, f.clipLoY);
+    bool outside = ((wx0h < v0.x) & (wx1h < v1.x) & (wx2h < v2.x)) | ((wx0l > v0.x) & (wx1l > v1.x) & (wx2l > v2.x)) |
+                   ((wy0h < v0.y) & (wy1h < v1.y) & (wy2h < v2.y)) | ((wy0l > v0.y) & (wy1l > v1.y) & (wy2l > v2.y)) |
+                   ((v0.w < v0.z) & (v1.w < v1.z) & (v2.w < v2.z)) | ((v0.w < -v0.z) & (v1.w < -v1.z) & (v2.w < -v2.z));
+    if (f.windowed) {
+        // sort-first window: also cull what lies wholly outside the surface rectangle (a pure cull:
+        // a half-space that holds all three vertices holds the triangle, whatever the sign of w)
+        outside |= ((__fmul_rn(v0.w, f.cullHiX) < v0.x) & (__fmul_rn(v1.w, f.cullHiX) < v1.x) & (__fmul_rn(v2.w, f.cullHiX) < v2.x)) |
+                   ((__fmul_rn(v0.w, f.cullLoX) > v0.x) & (__fmul_rn(v1.w, f.cullLoX) > v1.x) & (__fmul_rn(v2.w, f.cullLoX) > v2.x)) |
+                   ((__fmul_rn(v0.w, f.cullHiY) < v0.y) & (__fmul_rn(v1.w, f.cullHiY) < v1.y) & (__fmul_rn(v2.w, f.cullHiY) < v2.y)) |
+                   ((__fmul_rn(v0.w, f.cullLoY) > v0.y) & (__fmul_rn(v1.w, f.cullLoY) > v1.y) & (__fmul_rn(v2.w, f.cullLoY) > v2.y));
+    }
+    tm.stop(f, CRB_TIMER_SetupVertexRead);   // loads + the cull test that first consumes them
+    if (outside) {
+        f.triSubtris[tri] = 0;
+        prof |= 2;
+        return 0;
+    }
+    // inside the depth range: snap; inside the S16 guard band and small enough -> fast path
+    bool done = false;
+    if ((v0.w >= fabsf(v0.z)) & (v1.w >= fabsf(v1.z)) & (v2.w >= fabsf(v2.z))) {
+        SnappedTri s;
+        tm.start();
+        snapTriangle(f, v0, v1, v2, s);
+        const S32 loxy = min(s.lo.x, s.lo.y), hixy = max(s.hi.x, s.hi.y);
+        if (loxy >= -32768 && hixy <= 32767 && hixy - loxy <= aabbLimit) {
+            int2 d1, d2;
+            S32 area;
+            const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
+            tm.stop(f, CRB_TIMER_SetupCullSnap);
+            f.triSubtris[tri] = (res == 0) ? 1 : 0;
+            prof |= res == 1 ? 4u : res == 2 ? 8u : 32u;
+            if (res == 0) {
+                // Micro mode: a footprint of at most 4x4 pixel centres (and an extent that keeps the S32 edge functions of
+                // microRaster exact) is rasterized right here and never queued; one without any pixel centre inside the
+                // surface is dropped.  Same pixel range as triFootprint (Overlap.cuh).
+                bool micro = false, nothing = false;
+                S32 pxLoX = 0, pxLoY = 0, pxHiX = 0, pxHiY = 0;
+                if (SamplesLog2 == 0 && (RenderModeFlags & CRB_FLAG_DEPTH) != 0 && f.microMode) {
+                    pxLoX = max((s.lo.x + f.originX + 7) >> CR_SUBPIXEL_LOG2, 0);
+                    pxLoY = max((s.lo.y + f.originY + 7) >> CR_SUBPIXEL_LOG2, 0);
+                    pxHiX = min((s.hi.x + f.originX - 8) >> CR_SUBPIXEL_LOG2, f.widthPixels - 1);
+                    pxHiY = min((s.hi.y + f.originY - 8) >> CR_SUBPIXEL_LOG2, f.heightPixels - 1);
+                    nothing = (pxLoX > pxHiX) | (pxLoY > pxHiY);
+                    micro = !nothing & (pxHiX - pxLoX < 4) & (pxHiY - pxLoY < 4) & (s.hi.x - s.lo.x < (64 << CR_SUBPIXEL_LOG2)) & (s.hi.y - s.lo.y < (64 << CR_SUBPIXEL_LOG2));
+                }
+                if (!nothing) {
+                    uint3 zp = make_uint3(0, 0, 0);
+                    tm.start();
+                    uint4 h = setupTriangle<SamplesLog2, RenderModeFlags, true>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
+                                                                                make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area, &zp, micro);
+                    tm.stop(f, CRB_TIMER_SetupPleq);
+                    tm.start();
+                    if (micro) microRaster(f, s.p0.x, s.p0.y, s.p1.x, s.p1.y, s.p2.x, s.p2.y, zp.x, zp.y, zp.z, tri * 8 + 7, pxLoX, pxLoY, pxHiX - pxLoX + 1, pxHiY - pxLoY + 1);
+                    else tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh);
+                    tm.stop(f, CRB_TIMER_SetupBinning);
+                }
+            }
+            done = true;
+        }
+    }
+    if (!done) {
+        prof |= 16;
+        tm.start();
+        if (setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, sh) > 0) { tileCode = CRB_TILECODE_GENERAL; prof |= 32; }
+        tm.stop(f, CRB_TIMER_SetupClip);
+    }
+    return tileCode;
+}
+
+// The large sub-triangles of a CTA (direct path), counted into the tile counters by all its threads together (their headers
+// were written by this CTA before the barrier that precedes the call).
+template <int SamplesLog2>
+__device__ __forceinline__ void countLargeSubtris(const crb_frame& f, const SetupShared sh) {
+    const int numLarge = min(sh.cta->numLarge, CRB_SETUP_THREADS);
+    for (int k = 0; k < numLarge; k++) {
+        const uint4 h = f.triHeader[sh.cta->largeSlot[k]];
+        const TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
+        forEachCellStrided<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, CRB_SETUP_THREADS,
+                                                      [&](S32 tx, S32 ty) { atomicAdd(&f.tileCounter[tx + ty * f.widthTiles], 1); });
+    }
+}
+
+// One thread per input triangle, one CTA per chunk (or slice of a chunk).
 template <class VertexClass, int SamplesLog2, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
-    __shared__ SetupShared sh;
-    int* const s_binCount = sh.binCount;
+    __shared__ SetupCtaShared scratch;
+    __shared__ int s_queuedAny;
+    int* const s_binCount = scratch.binCount;
+    const SetupShared sh = {&s_queuedAny, &scratch};
     gridDepLaunchDependents();
     for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
-    if (threadIdx.x == 0) sh.sawLarge = sh.numLarge = sh.queuedAny = 0;
+    if (threadIdx.x == 0) scratch.sawLarge = scratch.numLarge = s_queuedAny = 0;
     __syncthreads();
     gridDepWait();   // the previous frame's kernels still read the work buffers written below
 
     const int stride4 = (int)(sizeof(VertexClass) / sizeof(float4));
     const float4* __restrict__ verts = reinterpret_cast<const float4*>(f.vertexBuffer);
-    const S32 aabbLimit = (1 << (CR_MAXVIEWPORT_LOG2 + CR_SUBPIXEL_LOG2)) - 1;
 
     const int tri = blockIdx.x * CRB_SETUP_THREADS + threadIdx.x;   // one thread per input triangle
     ProfTimer<ProfMode> tmTotal, tm;
@@ -330,77 +438,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
         const float4 v0 = __ldg(&verts[(size_t)vidx.x * stride4]);
         const float4 v1 = __ldg(&verts[(size_t)vidx.y * stride4]);
         const float4 v2 = __ldg(&verts[(size_t)vidx.z * stride4]);
-
-        // all three vertices outside one plane of the view window -> culled
-        const F32 wx0h = __fmul_rn(v0.w, f.clipHiX), wx1h = __fmul_rn(v1.w, f.clipHiX), wx2h = __fmul_rn(v2.w, f.clipHiX);
-        const F32 wx0l = __fmul_rn(v0.w, f.clipLoX), wx1l = __fmul_rn(v1.w, f.clipLoX), wx2l = __fmul_rn(v2.w, f.clipLoX);
-        const F32 wy0h = __fmul_rn(v0.w, f.clipHiY), wy1h = __fmul_rn(v1.w, f.clipHiY), wy2h = __fmul_rn(v2.w, f.clipHiY);
-        const F32 wy0l = __fmul_rn(v0.w, f.clipLoY), wy1l = __fmul_rn(v1.w, f.clipLoY), wy2l = __fmul_rn(v2.w, f.clipLoY);
-        bool outside = ((wx0h < v0.x) & (wx1h < v1.x) & (wx2h < v2.x)) | ((wx0l > v0.x) & (wx1l > v1.x) & (wx2l > v2.x)) |
-                       ((wy0h < v0.y) & (wy1h < v1.y) & (wy2h < v2.y)) | ((wy0l > v0.y) & (wy1l > v1.y) & (wy2l > v2.y)) |
-                       ((v0.w < v0.z) & (v1.w < v1.z) & (v2.w < v2.z)) | ((v0.w < -v0.z) & (v1.w < -v1.z) & (v2.w < -v2.z));
-        if (f.windowed) {
-            // sort-first window: also cull what lies wholly outside the surface rectangle (a pure cull:
-            // a half-space that holds all three vertices holds the triangle, whatever the sign of w)
-            outside |= ((__fmul_rn(v0.w, f.cullHiX) < v0.x) & (__fmul_rn(v1.w, f.cullHiX) < v1.x) & (__fmul_rn(v2.w, f.cullHiX) < v2.x)) |
-                       ((__fmul_rn(v0.w, f.cullLoX) > v0.x) & (__fmul_rn(v1.w, f.cullLoX) > v1.x) & (__fmul_rn(v2.w, f.cullLoX) > v2.x)) |
-                       ((__fmul_rn(v0.w, f.cullHiY) < v0.y) & (__fmul_rn(v1.w, f.cullHiY) < v1.y) & (__fmul_rn(v2.w, f.cullHiY) < v2.y)) |
-                       ((__fmul_rn(v0.w, f.cullLoY) > v0.y) & (__fmul_rn(v1.w, f.cullLoY) > v1.y) & (__fmul_rn(v2.w, f.cullLoY) > v2.y));
-        }
-        tm.stop(f, CRB_TIMER_SetupVertexRead);   // loads + the cull test that first consumes them
-        if (outside) {
-            f.triSubtris[tri] = 0;
-            prof |= 2;
-        } else {
-            // inside the depth range: snap; inside the S16 guard band and small enough -> fast path
-            bool done = false;
-            if ((v0.w >= fabsf(v0.z)) & (v1.w >= fabsf(v1.z)) & (v2.w >= fabsf(v2.z))) {
-                SnappedTri s;
-                tm.start();
-                snapTriangle(f, v0, v1, v2, s);
-                const S32 loxy = min(s.lo.x, s.lo.y), hixy = max(s.hi.x, s.hi.y);
-                if (loxy >= -32768 && hixy <= 32767 && hixy - loxy <= aabbLimit) {
-                    int2 d1, d2;
-                    S32 area;
-                    const int res = prepareTriangle<SamplesLog2>(f, s, d1, d2, area);
-                    tm.stop(f, CRB_TIMER_SetupCullSnap);
-                    f.triSubtris[tri] = (res == 0) ? 1 : 0;
-                    prof |= res == 1 ? 4u : res == 2 ? 8u : 32u;
-                    if (res == 0) {
-                        // Micro mode: a footprint of at most 4x4 pixel centres (and an extent that keeps the S32 edge functions of
-                        // microRaster exact) is rasterized right here and never queued; one without any pixel centre inside the
-                        // surface is dropped.  Same pixel range as triFootprint (Overlap.cuh).
-                        bool micro = false, nothing = false;
-                        S32 pxLoX = 0, pxLoY = 0, pxHiX = 0, pxHiY = 0;
-                        if (SamplesLog2 == 0 && (RenderModeFlags & CRB_FLAG_DEPTH) != 0 && f.microMode) {
-                            pxLoX = max((s.lo.x + f.originX + 7) >> CR_SUBPIXEL_LOG2, 0);
-                            pxLoY = max((s.lo.y + f.originY + 7) >> CR_SUBPIXEL_LOG2, 0);
-                            pxHiX = min((s.hi.x + f.originX - 8) >> CR_SUBPIXEL_LOG2, f.widthPixels - 1);
-                            pxHiY = min((s.hi.y + f.originY - 8) >> CR_SUBPIXEL_LOG2, f.heightPixels - 1);
-                            nothing = (pxLoX > pxHiX) | (pxLoY > pxHiY);
-                            micro = !nothing & (pxHiX - pxLoX < 4) & (pxHiY - pxLoY < 4) & (s.hi.x - s.lo.x < (64 << CR_SUBPIXEL_LOG2)) & (s.hi.y - s.lo.y < (64 << CR_SUBPIXEL_LOG2));
-                        }
-                        if (!nothing) {
-                            uint3 zp = make_uint3(0, 0, 0);
-                            tm.start();
-                            uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[tri], &f.triData[(size_t)tri * 4], vidx, v0, v1, v2, make_float2(0.0f, 0.0f),
-                                                                                  make_float2(1.0f, 0.0f), make_float2(0.0f, 1.0f), s, d1, d2, area, &zp, micro);
-                            tm.stop(f, CRB_TIMER_SetupPleq);
-                            tm.start();
-                            if (micro) microRaster(f, s.p0.x, s.p0.y, s.p1.x, s.p1.y, s.p2.x, s.p2.y, zp.x, zp.y, zp.z, tri * 8 + 7, pxLoX, pxLoY, pxHiX - pxLoX + 1, pxHiY - pxLoY + 1);
-                            else tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh);
-                            tm.stop(f, CRB_TIMER_SetupBinning);
-                        }
-                    }
-                    done = true;
-                }
-            }
-            if (!done) prof |= 16;
-            if (!done) tm.start();
-            if (!done && setupClippedTriangle<SamplesLog2, RenderModeFlags>(f, tri, vidx, v0, v1, v2, sh) > 0) { tileCode = CRB_TILECODE_GENERAL; prof |= 32; }
-            if (!done) tm.stop(f, CRB_TIMER_SetupClip);
-        }
-        if (f.directMode) f.triTileCode[tri] = tileCode;
+        tileCode = setupOneTriangle<SamplesLog2, RenderModeFlags, ProfMode>(f, tri, vidx, v0, v1, v2, sh, prof, tm);
     }
 
     tmTotal.stop(f, CRB_TIMER_SetupTotal);
@@ -414,17 +452,14 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     }
     // publish this CTA's bin histogram: one column of binCountMat[bin][chunk]
     __syncthreads();
-    if (threadIdx.x == 0 && sh.sawLarge != 0) atomicAdd(&f.atomics->numLargeTris, 1);   // CTAs with a large sub-triangle (zero / non-zero is what matters)
+    if (threadIdx.x == 0 && scratch.sawLarge != 0) atomicAdd(&f.atomics->numLargeTris, 1);   // CTAs with a large sub-triangle (zero / non-zero is what matters)
     if (f.directMode) {
-        if (threadIdx.x == 0 && sh.queuedAny != 0) atomicAdd(&f.atomics->numQueuedCtas, 1);
-        // the large sub-triangles of this CTA, all threads together (their headers were written by this CTA before the barrier)
-        const int numLarge = min(sh.numLarge, CRB_SETUP_THREADS);
-        for (int k = 0; k < numLarge; k++) {
-            const uint4 h = f.triHeader[sh.largeSlot[k]];
-            const TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
-            forEachCellStrided<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, CRB_SETUP_THREADS,
-                                                          [&](S32 tx, S32 ty) { atomicAdd(&f.tileCounter[tx + ty * f.widthTiles], 1); });
-        }
+        // One word per triangle for the scatter pass -- but only where something was queued: a batch of 32 triangles that were all
+        // culled or rasterized right here (every batch of a micro-triangle frame) leaves ONE byte instead of 128 B of zeros.
+        if (s_queuedAny != 0 && tri < f.numTris) f.triTileCode[tri] = tileCode;
+        if ((threadIdx.x & 31) == 0 && tri < f.numTris) f.batchQueued[tri >> 5] = (uint8_t)(s_queuedAny != 0);
+        if (threadIdx.x == 0 && s_queuedAny != 0) atomicAdd(&f.atomics->numQueuedCtas, 1);
+        countLargeSubtris<SamplesLog2>(f, sh);
         return;
     }
     int* col = f.binCountMat + blockIdx.x / f.ctasPerChunk;

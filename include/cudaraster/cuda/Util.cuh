@@ -147,13 +147,8 @@ static __device__ __noinline__ int clipTriangleWithWindow(float2* bary, float4 v
 // values at the three vertices -> (x slope, y slope, constant) such that
 // plane(sx, sy) = x*sx + y*sy + z in sample units (samplesLog2 selects the unit).  All integer
 // after the initial float -> U32 truncation; S64 intermediates; shifts are arithmetic.
-__device__ __forceinline__ uint3 setupPleq(float3 values, int2 v0, int2 d1, int2 d2, F32 areaRcp, int samplesLog2) {
-    F32 mx = fmaxf(fmaxf(values.x, values.y), values.z);
-    int sh = min(max((__float_as_int(mx) >> 23) - (127 + 22), 0), 8);
-    S32 t0 = (S32)(f32ToU32Rzi(values.x) >> sh);
-    S32 t1 = (S32)((f32ToU32Rzi(values.y) >> sh) - (U32)t0);
-    S32 t2 = (S32)((f32ToU32Rzi(values.z) >> sh) - (U32)t0);
-
+// Integer part shared by the two entry points below: t0 = value at vertex 0, t1 / t2 = differences to it (all >> sh).
+__device__ __forceinline__ uint3 setupPleqFixed(S32 t0, S32 t1, S32 t2, int sh, int2 v0, int2 d1, int2 d2, F32 areaRcp, int samplesLog2) {
     U32 rcpMant = ((U32)__float_as_int(areaRcp) & 0x007FFFFFu) | 0x00800000u;
     int rcpShift = (23 + 127) - (__float_as_int(areaRcp) >> 23);
 
@@ -173,6 +168,27 @@ __device__ __forceinline__ uint3 setupPleq(float3 values, int2 v0, int2 d1, int2
     p.z -= (U32)(((xc >> 13) * vcx + (yc >> 13) * vcy) >> (rcpShift - (sh + 13)));
     p.z -= p.x * (U32)cx + p.y * (U32)cy;
     return p;
+}
+
+__device__ __forceinline__ uint3 setupPleq(float3 values, int2 v0, int2 d1, int2 d2, F32 areaRcp, int samplesLog2) {
+    F32 mx = fmaxf(fmaxf(values.x, values.y), values.z);
+    int sh = min(max((__float_as_int(mx) >> 23) - (127 + 22), 0), 8);
+    S32 t0 = (S32)(f32ToU32Rzi(values.x) >> sh);
+    S32 t1 = (S32)((f32ToU32Rzi(values.y) >> sh) - (U32)t0);
+    S32 t2 = (S32)((f32ToU32Rzi(values.z) >> sh) - (U32)t0);
+    return setupPleqFixed(t0, t1, t2, sh, v0, d1, d2, areaRcp, samplesLog2);
+}
+
+// The plane through (0, value, 0) (Which = 1) or (0, 0, value) (Which = 2): the u / v planes of an UNCLIPPED triangle, whose
+// barycentrics at the vertices are (0,0), (1,0), (0,1) -- the reference multiplies them out (TriangleSetup.inl:160-166:
+// 0 * w0', 1 * w1', 0 * w2') and gets exactly these values: 0 * x is +-0 (or NaN for a non-finite x), which the float -> U32
+// conversion turns into 0 and fmaxf ignores next to a value >= 0; an all-NaN triple gives the zero plane on both routes.
+template <int Which>
+__device__ __forceinline__ uint3 setupPleqUnit(F32 value, int2 v0, int2 d1, int2 d2, F32 areaRcp, int samplesLog2) {
+    F32 mx = fmaxf(0.0f, value);
+    int sh = min(max((__float_as_int(mx) >> 23) - (127 + 22), 0), 8);
+    const S32 t = (S32)(f32ToU32Rzi(value) >> sh);
+    return setupPleqFixed(0, Which == 1 ? t : 0, Which == 2 ? t : 0, sh, v0, d1, d2, areaRcp, samplesLog2);
 }
 
 // ---- programmatic dependent launch (sm_90+) --------------------------------------------------------
