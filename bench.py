@@ -23,7 +23,8 @@ Prints ONE JSON line (rank 0).  Keys: see the task contract; additionally
   stage_ms     mean per-stage device time (the reference's five event positions)
   roofline     dominant kernel: algorithmic bytes per launch / mean launch duration vs measured HBM peak
   cpu_baseline the CPU oracle (oracle/golden.hpp) timed on this box's host cores on a bounded sample
-  ref_kernels  the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref), if they run here
+  ref_kernels  the reference's own CUDA kernels rebuilt for sm_100a with the synchronisation patch (oracle/_ref/libcrref_cuda_sync.so),
+               frame checked against the oracle in the same run, and the speed-up of this pipeline over them
   e2e          the same metric through crb_draw_triangles_host (pinned HOST buffers, H2D + D2H inside)
 
 --impl reference times the CPU restatement of the path (the reference has no runnable CPU path of
@@ -172,19 +173,23 @@ def run_reference_arm(args, emit):
 
 
 def time_ref_kernels(workload, timeout=240):
-    """Times the reference's own CUDA kernels rebuilt for sm_100a in a SUBPROCESS (they are
-    implicitly warp-synchronous Fermi code and may hang or fault on Blackwell)."""
-    lib = os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so")
+    """Times the reference's own CUDA kernels rebuilt for sm_100a, with the synchronisation patch that lets them run on
+    Blackwell (oracle/ref_kernels/b200_sync_patch.py), in a SUBPROCESS (Fermi code: it may still hang or fault).  The frame is
+    checked against the CPU oracle in the same run: a number only counts when `status` says pixel-exact."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda_sync.so")
     if not os.path.exists(lib):
         return {"status": "not built"}
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "7"] + (["--check"] if workload == "c2" else []),
-                           capture_output=True, text=True, timeout=timeout)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "23", "--check"],
+                           capture_output=True, text=True, timeout=timeout, env=dict(os.environ, CRREF_LIBRARY=lib))
     except subprocess.TimeoutExpired:
         return {"status": "hang (killed after %d s)" % timeout}
     for ln in reversed(r.stdout.strip().splitlines()):
         if ln.startswith("{"):
-            return json.loads(ln)
+            d = json.loads(ln)
+            if d.get("status") == "ok":
+                d["status"] = "sync-patched, pixel-exact (depth and colour equal to the oracle's frame)"
+            return d
     return {"status": "failed rc=%d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:].replace("\n", " | "))}
 
 
@@ -516,7 +521,10 @@ def main():
                 except Exception:
                     pass
         if not args.no_ref_kernels and world == 1:
-            line["ref_kernels"] = time_ref_kernels(args.workload)
+            rk = time_ref_kernels(args.workload)
+            if "Mtris/s" in rk:   # the north_star's comparison: same metric (T / sum of the four stage intervals, median), same frame, same GPU
+                rk["speedup_of_this_pipeline"] = value / rk["Mtris/s"]
+            line["ref_kernels"] = rk
         emit(line)
     if sink:
         sync_all()

@@ -1,0 +1,223 @@
+#!/usr/bin/env python
+"""Synchronisation patch for the reference's bin / coarse / fine-raster kernels (TEST / BASELINE INFRASTRUCTURE).
+
+    python b200_sync_patch.py <dir holding a TEMPORARY COPY of /root/reference/src/cudaraster/cuda>
+
+The reference kernels are implicitly warp-synchronous Fermi code: shared-memory scans and broadcasts
+without barriers, votes that assume a converged warp, and a ROP whose same-address store conflicts are resolved by Fermi's
+arbitration (the highest lane's store survives; B200 keeps the lowest lane's: profiles/r1_ref_kernels.md).  Under independent
+thread scheduling (sm_70+) they drop almost every triangle.  This script makes the lock-step assumptions EXPLICIT and changes
+nothing else: __syncwarp() between the write and the read of every warp-level exchange, full-mask *_sync votes where the
+source relies on a converged warp, shuffle broadcasts where a leader hands a value to its group, and the store arbitration
+spelled out (highest lane of the lanes that hit the same address).  One optimisation path is switched off instead of
+repaired: CoarseRaster case B records emits with __ballot inside loops whose trip counts differ per lane, which no barrier
+can fix; case C computes the same emit masks with atomics and now takes those triangles too.
+
+Nothing of the reference is stored here: edits are addressed by LINE NUMBER and guarded by the CRC32 of the original
+(stripped) line, so a different revision of the reference makes the script fail instead of mis-patching.  The patched copy
+lives in a temporary directory for the duration of one compile (oracle/Makefile: _ref/libcrref_cuda_sync.so).
+Not patched: the multi-sample fine raster (FineRaster.inl:758-1126), quad-mode dFdx / dFdy (PixelPipe.hpp:59-69)."""
+import os
+import sys
+import zlib
+
+W16, W8 = "0xFFFFu", "0xFFu"
+
+
+def scan_min16(k):
+    return "p[0] = t; __syncwarp(%s); t = ::min(t, p[-%d]); __syncwarp(%s);" % (W16, k, W16)
+
+
+def scan_or32(k):
+    return "p[0] = aabbMask; __syncwarp(); aabbMask |= p[-%d]; __syncwarp();" % k
+
+
+def scan_sum32(k):
+    return "*p = sum; __syncwarp(); if (threadIdx.x >= %d) sum += p[-%d]; __syncwarp();" % (k, k)
+
+
+def scan_sum8(k):
+    return "sum += p[-%d]; __syncwarp(%s); p[0] = sum; __syncwarp(%s);" % (k, W8, W8)
+
+
+def fine_max(k):
+    return "z = ::max(z, temp[threadIdx.x + 16 - %d]); __syncwarp(); temp[threadIdx.x + 16] = z; __syncwarp();" % k
+
+
+def fine_sum(k):
+    return "value += temp[threadIdx.x + 16 - %d]; __syncwarp(); temp[threadIdx.x + 16] = value; __syncwarp();" % k
+
+
+ROP_WARP = r'''
+// [b200_sync_patch] Warp-uniform restatement of executeROP_SingleSample for independent thread scheduling: every lane of the
+// warp calls it (active = this lane has a fragment for the ROP).  Same rounds as the original loops -- all pending lanes
+// "store", one store per address survives, lanes whose fragment is still in front of the stored depth (or, without depth
+// test, that have not blended yet) go again -- with the arbitration the original relies on made explicit: of the lanes that
+// hit the same pixel, the HIGHEST lane's stores (depth and colour) survive, as on the reference's target hardware.
+template <class BlendShaderClass, U32 RenderModeFlags>
+__device__ __inline__ void executeROP_SingleSample_warp(bool active, int triIdx, int pixelX, int pixelY, U32 color, U32 depth,
+                                                        volatile U32* tileColor, volatile U32* tileDepth, int pixelInTile)
+{
+    BlendShaderClass bs;
+    bool pend = active;
+    for (;;)
+    {
+        const U32 act = __ballot_sync(0xFFFFFFFFu, pend);
+        if (act == 0)
+            break;
+        bool win = false;
+        if (pend)
+        {
+            const U32 peers = __match_any_sync(act, pixelInTile);
+            win = ((31 - __clz(peers)) == (int)threadIdx.x);
+            if (win)
+            {
+                if ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0)
+                    tileDepth[pixelInTile] = depth;
+                else if (bs.needsDst())
+                    tileDepth[pixelInTile] = threadIdx.x;   // the original's lock word (SURVEY.md A.7: it reaches the depth surface)
+                U32 sColor = ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0 || bs.needsDst()) ? tileColor[pixelInTile] : 0;
+                runBlendShader<BlendShaderClass>(bs, triIdx, pixelX, pixelY, 0, color, sColor);
+                if (bs.m_writeColor)
+                    tileColor[pixelInTile] = bs.m_color;
+            }
+        }
+        __syncwarp();
+        if (pend)
+        {
+            if ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0)
+                pend = (depth < tileDepth[pixelInTile]);
+            else if (bs.needsDst())
+                pend = !win;
+            else
+                pend = false;
+        }
+        __syncwarp();
+    }
+}
+'''
+
+# (file, line, crc32 of the original stripped line, op, text)   op: "r" replace the line, "a" insert after it, "b" insert before it
+EDITS = [
+    # ---- BinRaster.inl ------------------------------------------------------------------------------------------------
+    ("BinRaster.inl", 107, 0x0a9593d6, "r", "if (threadIdx.x == 31) s_broadcast[threadIdx.y + 16] = myIdx + num;   // the warp's inclusive total: the highest lane's value"),
+    ("BinRaster.inl", 116, 0x2e79d646, "r", "val += ptr[-1]; __syncwarp(%s); *ptr = val; __syncwarp(%s);" % (W16, W16)),
+    ("BinRaster.inl", 119, 0x3f04bc3f, "r", "val += ptr[-2]; __syncwarp(%s); *ptr = val; __syncwarp(%s);" % (W16, W16)),
+    ("BinRaster.inl", 122, 0x1dfe68cd, "r", "val += ptr[-4]; __syncwarp(%s); *ptr = val; __syncwarp(%s);" % (W16, W16)),
+    ("BinRaster.inl", 125, 0x580bc129, "r", "val += ptr[-8]; __syncwarp(%s); *ptr = val; __syncwarp(%s);" % (W16, W16)),
+    ("BinRaster.inl", 133, 0x85794fa3, "r", "if (thrInBlock == CR_BIN_WARPS - 1) s_bufCount = bufCount + val;   // the block total: the highest lane's value"),
+    ("BinRaster.inl", 183, 0x00000000, "r", "__syncwarp();   // the warp's cleared masks before its lanes OR into them"),
+    ("BinRaster.inl", 208, 0x5fb23c1b, "a", "const U32 crb_lanes = __ballot_sync(0xFFFFFFFFu, thrInBlock < bufCount);"),
+    ("BinRaster.inl", 230, 0xac0b52ab, "r", "if (!__any_sync(crb_lanes, multi))"),
+    ("BinRaster.inl", 237, 0x9d45c095, "r", "U32 crb_rem = crb_lanes; do"),
+    ("BinRaster.inl", 239, 0xb1f2909d, "r", "int winner = __shfl_sync(crb_rem, binIdx, __ffs(crb_rem) - 1);   // one lane's bin, broadcast (was: racing stores to one word)"),
+    ("BinRaster.inl", 240, 0xa1213e40, "r", ""),
+    ("BinRaster.inl", 242, 0xebaf0b37, "r", "U32 mask = __ballot_sync(crb_rem, won);"),
+    ("BinRaster.inl", 243, 0xcd2fc55e, "r", "if (won) s_outMask[threadIdx.y][winner] = mask; crb_rem &= ~mask;"),
+    ("BinRaster.inl", 250, 0xe3b87f28, "r", "if (!__any_sync(crb_lanes, complex))"),
+    ("BinRaster.inl", 332, 0xce8426a8, "r", "U32 crb_base = 0; if (overIndex == 0)"),
+    ("BinRaster.inl", 333, 0x77b208d4, "r", "crb_base = atomicAdd((U32*)&s_overTotal, __popc(mask));"),
+    ("BinRaster.inl", 334, 0x6e59be60, "r", "overIndex += __shfl_sync(mask, crb_base, __ffs(mask) - 1);"),
+    # ---- CoarseRaster.inl ---------------------------------------------------------------------------------------------
+    ("CoarseRaster.inl", 195, 0x9970b84a, "r", scan_min16(1)),
+    ("CoarseRaster.inl", 198, 0x8bc517a4, "r", scan_min16(2)),
+    ("CoarseRaster.inl", 201, 0xaeae4878, "r", scan_min16(4)),
+    ("CoarseRaster.inl", 204, 0xe478f7c0, "r", scan_min16(8)),
+    ("CoarseRaster.inl", 209, 0x07009ade, "r", "p[0] = t; __syncwarp(%s);" % W16),
+    ("CoarseRaster.inl", 297, 0x09a03faf, "r", "if (__any_sync(0xFFFFFFFFu, triIdx != -1))"),
+    ("CoarseRaster.inl", 328, 0xfe2f9c63, "r", "if (__all_sync(0xFFFFFFFFu, sizex <= 2 && sizey <= 2))"),
+    ("CoarseRaster.inl", 354, 0xd4a14fec, "r", scan_or32(1)),
+    ("CoarseRaster.inl", 355, 0xd6e7f1b5, "r", scan_or32(2)),
+    ("CoarseRaster.inl", 356, 0xd26a8d07, "r", scan_or32(4)),
+    ("CoarseRaster.inl", 357, 0xdb707463, "r", scan_or32(8)),
+    ("CoarseRaster.inl", 358, 0xbd44e155, "r", scan_or32(16)),
+    ("CoarseRaster.inl", 359, 0x91b67ffb, "r", "p[0] = aabbMask; __syncwarp(); aabbMask = s_scanTemp[threadIdx.y][47]; __syncwarp();"),
+    ("CoarseRaster.inl", 389, 0x7d7181f8, "r", "if (false)   // case B (ballots inside per-lane loops) needs lock-step lanes: case C records the same emits with atomics"),
+    ("CoarseRaster.inl", 473, 0xebad45d0, "r", "if (!__any_sync(0xFFFFFFFFu, tileEmits >= 2))"),
+    ("CoarseRaster.inl", 476, 0x471509eb, "r", "*p = (__popc(__ballot_sync(0xFFFFFFFFu, tileEmits & 1) & m) << emitShift) | __popc(__ballot_sync(0xFFFFFFFFu, tileAllocs & 1) & m);"),
+    ("CoarseRaster.inl", 487, 0x7b459027, "r", scan_sum32(1)),
+    ("CoarseRaster.inl", 488, 0x2a9975fa, "r", scan_sum32(2)),
+    ("CoarseRaster.inl", 489, 0x8920be40, "r", scan_sum32(4)),
+    ("CoarseRaster.inl", 490, 0x15222f75, "r", scan_sum32(8)),
+    ("CoarseRaster.inl", 491, 0xbdf5bac4, "r", scan_sum32(16)),
+    ("CoarseRaster.inl", 509, 0xc833e389, "r", "p[0] = sum; __syncwarp(%s);" % W8),
+    ("CoarseRaster.inl", 511, 0x28f59f5e, "r", scan_sum8(1)),
+    ("CoarseRaster.inl", 514, 0x3988f527, "r", scan_sum8(2)),
+    ("CoarseRaster.inl", 517, 0x1b7221d5, "r", scan_sum8(4)),
+    ("CoarseRaster.inl", 764, 0x2a71b0e7, "r", "s_scanTemp[0][(tileInBin >> 5) + 16] = __popc(__ballot_sync(0xFFFFFFFFu, ofs >= 0 | force));"),
+    ("CoarseRaster.inl", 776, 0x28f59f5e, "r", scan_sum8(1)),
+    ("CoarseRaster.inl", 779, 0x3988f527, "r", scan_sum8(2)),
+    ("CoarseRaster.inl", 782, 0x1b7221d5, "r", scan_sum8(4)),
+    ("CoarseRaster.inl", 794, 0xa740b33d, "r", "const bool crb_act = !(s_tileStreamCurrOfs[tileInBin] < 0); const U32 crb_m = __ballot_sync(0xFFFFFFFFu, crb_act); if (!crb_act)"),
+    ("CoarseRaster.inl", 799, 0x2e3810c4, "r", "activeIdx += __popc(crb_m & getLaneMaskLt());"),
+    # ---- Util.inl: sortShared (odd-even transposition inside 16-wide subranges = 8 neighbouring lanes) -------------------
+    ("Util.inl", 395, 0x9a1013ce, "r", "const U32 crb_sm = __ballot_sync(0xFFFFFFFFu, base < numItems - 1); if (base < numItems - 1)"),
+    ("Util.inl", 410, 0x00000000, "r", "__syncwarp(crb_sm);"),
+    ("Util.inl", 421, 0xfcb6e20c, "a", "__syncwarp(crb_sm);"),
+    # ---- FineRaster.inl (single-sample kernel) ----------------------------------------------------------------------------
+    ("FineRaster.inl", 179, 0x93b39f60, "r", "if ((RenderModeFlags & RenderModeFlag_EnableDepth) != 0 && __any_sync(0xFFFFFFFFu, tileZUpd))"),
+    ("FineRaster.inl", 181, 0x287b3206, "b", "__syncwarp();   // the depths other lanes stored in the ROP"),
+    ("FineRaster.inl", 182, 0x2fb76ec4, "r", "temp[threadIdx.x + 16] = z; __syncwarp();"),
+    ("FineRaster.inl", 183, 0xe2093585, "r", fine_max(1)),
+    ("FineRaster.inl", 184, 0x2b163d3a, "r", fine_max(2)),
+    ("FineRaster.inl", 185, 0x62592a05, "r", fine_max(4)),
+    ("FineRaster.inl", 186, 0xf0c7047b, "r", fine_max(8)),
+    ("FineRaster.inl", 187, 0xb5a5b451, "r", fine_max(16)),
+    ("FineRaster.inl", 311, 0x155dc696, "r", "__syncwarp(); temp[threadIdx.x + 16] = value; __syncwarp();"),
+    ("FineRaster.inl", 312, 0x84c19677, "r", fine_sum(1)),
+    ("FineRaster.inl", 313, 0x0f12a86e, "r", fine_sum(2)),
+    ("FineRaster.inl", 314, 0xc3c5d21d, "r", fine_sum(4)),
+    ("FineRaster.inl", 315, 0x811a20ba, "r", fine_sum(8)),
+    ("FineRaster.inl", 316, 0xf3b94d05, "r", fine_sum(16)),
+    ("FineRaster.inl", 496, 0x00000000, "a", ROP_WARP),
+    ("FineRaster.inl", 541, 0xd4d3d96c, "a", "__syncwarp();"),
+    ("FineRaster.inl", 542, 0x1d76227c, "a", "__syncwarp();"),
+    ("FineRaster.inl", 581, 0x00000000, "r", "__syncwarp();   // the tile other lanes cleared / loaded"),
+    ("FineRaster.inl", 634, 0x9ffc803c, "r", "U32 goodMask = __ballot_sync(0xFFFFFFFFu, pop != 0);"),
+    ("FineRaster.inl", 647, 0xfcb6e20c, "a", "__syncwarp();   // the triangles other lanes queued"),
+    ("FineRaster.inl", 656, 0x2521c94b, "r", "temp[threadIdx.x + 16] = 0; __syncwarp();"),
+    ("FineRaster.inl", 663, 0x00000000, "r", "__syncwarp();"),
+    ("FineRaster.inl", 665, 0x473daac5, "r", "U32 boundaryMask = __ballot_sync(0xFFFFFFFFu, temp[ropLane.x + 16]);"),
+    ("FineRaster.inl", 669, 0x0c1df870, "b", "bool crb_rop = false; U32 crb_color = 0, crb_depth = 0, crb_px = 0, crb_py = 0; int crb_pix = 0, crb_tri = 0;"),
+    ("FineRaster.inl", 720, 0x4f1ed2f1, "r", "crb_rop = true; crb_tri = triIdx; crb_px = pixelX; crb_py = pixelY; crb_color = fragShader.m_color; crb_depth = depth; crb_pix = pixelInTile;"),
+    ("FineRaster.inl", 721, 0xe013601e, "r", ""),
+    ("FineRaster.inl", 722, 0x158a82f3, "r", ""),
+    ("FineRaster.inl", 723, 0xbee8eb56, "r", ""),
+    ("FineRaster.inl", 727, 0x00000000, "r", "executeROP_SingleSample_warp<BlendShaderClass, RenderModeFlags>(crb_rop, crb_tri, crb_px, crb_py, crb_color, crb_depth, tileColor, tileDepth, crb_pix);"),
+]
+
+
+def main():
+    root = sys.argv[1]
+    show = len(sys.argv) > 2 and sys.argv[2] == "--crc"
+    by_file = {}
+    for e in EDITS:
+        by_file.setdefault(e[0], []).append(e)
+    for name, edits in by_file.items():
+        path = os.path.join(root, name)
+        lines = open(path).read().split("\n")
+        out = {}
+        for _, n, crc, op, text in edits:
+            got = zlib.crc32(lines[n - 1].strip().encode()) & 0xFFFFFFFF
+            if show:
+                print("%s:%d %08x" % (name, n, got))
+            if crc is not None and got != crc:
+                sys.exit("%s:%d is not the line this patch was written for (crc %08x, expected %08x)" % (name, n, got, crc))
+            out.setdefault(n, []).append((op, text))
+        res = []
+        for i, ln in enumerate(lines, 1):
+            ops = out.get(i, [])
+            for op, text in ops:
+                if op == "b":
+                    res.append(text)
+            rep = [t for op, t in ops if op == "r"]
+            res.append(rep[0] if rep else ln)
+            for op, text in ops:
+                if op == "a":
+                    res.append(text)
+        open(path, "w").write("\n".join(res))
+    print("b200_sync_patch: %d edits applied to %d files" % (len(EDITS), len(by_file)))
+
+
+if __name__ == "__main__":
+    main()

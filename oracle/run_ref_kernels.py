@@ -59,18 +59,36 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--frames", type=int, default=7)
     ap.add_argument("--check", action="store_true", help="compare depth/colour with the CPU oracle")
+    ap.add_argument("--check-product", action="store_true", help="compare depth/colour with the B200 pipeline (libcrb200.so)")
     ap.add_argument("--check-setup", action="store_true", help="compare triSubtris/triHeader/triData with the CPU oracle, bit for bit")
     args = ap.parse_args()
     import bench
+    blend = "BlendReplace"
     if args.workload.startswith("soup"):
         # parity scene: mixed sizes, frustum-crossing and w <= 0 triangles (exercises the clipper)
         import cudaraster_linux_b200 as crb
-        shader, flags, s_log2 = {"soup": ("gouraud", 3, 0), "soup_msaa": ("gouraud", 3, 2), "soup_pass": ("passthrough", 1, 0)}[args.workload]
+        shader, flags, s_log2 = {"soup": ("gouraud", 3, 0), "soup_msaa": ("gouraud", 3, 2), "soup_pass": ("passthrough", 1, 0), "soup_blend": ("gouraud", 3, 0)}[args.workload]
+        if args.workload == "soup_blend":
+            blend = "BlendSrcOver"   # reads dst: every fragment of a pixel must reach the ROP in submission order
         w, h, desc = 640, 360, args.workload
         verts, idx = crb.scenes.random_soup(20000, seed=1237, stride_floats=8 if shader == "gouraud" else 4)
+        if blend != "BlendReplace":
+            verts[:, 7] = np.random.default_rng(3).uniform(0.2, 1.0, verts.shape[0]).astype(np.float32)   # alpha
+    elif args.workload == "c1":
+        import cudaraster_linux_b200 as crb
+        w, h, desc, shader, flags, s_log2 = 1024, 768, "C1 cube", "passthrough", 1, 0
+        verts, idx = crb.scenes.cube(w, h)
+    elif args.workload == "ties":
+        # the same mesh submitted twice with other colours: every fragment of the second copy ties in depth with the first and must lose
+        import cudaraster_linux_b200 as crb
+        w, h, desc, shader, flags, s_log2 = 512, 384, "duplicated grid (depth ties)", "gouraud", 3, 0
+        v, i = crb.scenes.grid_gouraud(160, 100)
+        verts = np.concatenate([v, v])
+        verts[v.shape[0]:, 4:8] = np.random.default_rng(9).uniform(0, 1, (v.shape[0], 4)).astype(np.float32)
+        idx = np.concatenate([i, i + v.shape[0]])
     else:
         desc, verts, idx, w, h, shader, s_log2, flags, _ = bench.make_scene(args.workload)
-    pipe = "ref_%s_s%d_f%d_BlendReplace" % (shader, s_log2, flags)
+    pipe = "ref_%s_s%d_f%d_%s" % (shader, s_log2, flags, blend)
     lib = load()
     names = [lib.crref_pipe_name(i).decode() for i in range(lib.crref_num_pipes())]
     if pipe not in names:
@@ -79,7 +97,10 @@ def main():
     color, depth, times, atomics = draw(lib, pipe, verts, idx, w, h, s_log2, frames=args.frames)
     steady = times[2:] if len(times) > 3 else times
     med = [statistics.median(t[i] for t in steady) * 1e3 for i in range(4)]
-    out = {"status": "ok", "what": "reference kernels rebuilt for sm_100a behind oracle/ref_kernels/shim.h, launch shapes of CudaRaster.cpp:593-655",
+    libname = os.path.basename(os.environ.get("CRREF_LIBRARY") or "libcrref_cuda.so")
+    out = {"status": "ok", "library": libname,
+           "what": ("reference kernels with the synchronisation patch (oracle/ref_kernels/b200_sync_patch.py: lock-step assumptions made explicit, nothing else changed)"
+                    if "sync" in libname else "reference kernels, unmodified sources") + ", rebuilt for sm_100a behind oracle/ref_kernels/shim.h, launch shapes of CudaRaster.cpp:593-655",
            "stage_ms": dict(zip(("triangleSetup", "binRaster", "coarseRaster", "fineRaster"), med)), "frame_ms": sum(med),
            "Mtris/s": idx.shape[0] / (sum(med) * 1e-3) / 1e6, "atomics": atomics}
     if args.check_setup:
@@ -99,11 +120,22 @@ def main():
             out["setup"] = {"status": "mismatch: %s" % str(e)[:200]}
     if args.check:
         from tests import util
-        g = util.draw_gold(verts, idx, w, h, shader, flags, s_log2)
+        g = util.draw_gold(verts, idx, w, h, shader, flags, s_log2, blend)
         out["depth_mismatch_texels"] = int((depth != g["depth"]).sum())
         out["color_max_lsb"] = util.color_max_diff(color, g["color"])
         out["color_mismatch_texels"] = int((color != g["color"]).sum())
         if out["depth_mismatch_texels"]:
+            out["status"] = "mismatch"
+    if args.check_product:
+        # the B200 pipeline (through its C ABI) against the reference's kernels, frame against frame
+        import cudaraster_linux_b200 as crb
+        from tests import util
+        r = crb.CudaRaster(0)
+        cc, cd = util.draw_cuda(r, crb, verts, idx, w, h, shader, flags, s_log2, blend, pipe="PixelPipe_passthrough" if args.workload == "c1" else None)
+        out["product_depth_mismatch_texels"] = int((cd != depth).sum())
+        out["product_color_max_lsb"] = util.color_max_diff(cc, color)
+        r.close()
+        if out["product_depth_mismatch_texels"] and out["status"] == "ok":
             out["status"] = "mismatch"
     print(json.dumps(out))
     return 0

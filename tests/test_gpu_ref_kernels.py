@@ -5,8 +5,11 @@ warp-synchronous and is not guaranteed to terminate on Bl
 
 What is asserted: the reference's TRIANGLE SETUP kernel (per-thread code) produces bit-identical
 triSubtris / triHeader / triData to the CPU oracle -- this pins the oracle's snap / cull / clip /
-plane-equation arithmetic to the reference's real device code.  The later stages are reported, not
-asserted: they mis-execute on sm_100a (profiles/r1_ref_kernels.md)."""
+plane-equation arithmetic to the reference's real device code.  The UNMODIFIED bin / coarse / fine kernels mis-execute on
+sm_100a (implicitly warp-synchronous Fermi code, profiles/r1_ref_kernels.md); with the synchronisation patch
+(oracle/ref_kernels/b200_sync_patch.py -> oracle/_ref/libcrref_cuda_sync.so: lock-step assumptions made explicit, nothing else
+changed) the WHOLE reference pipeline runs on the B200 and its frames are asserted equal to the oracle's and to the product's:
+queue order, LESS depth test and ROP order are thereby pinned to the reference's own kernels, not only to the oracle's reading."""
 import json
 import os
 import subprocess
@@ -18,12 +21,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(workload):
-    lib = os.path.join(ROOT, "oracle", "_ref", "libcrref_cuda.so")
+def _run(workload, libname="libcrref_cuda.so", extra=("--check", "--check-setup")):
+    lib = os.path.join(ROOT, "oracle", "_ref", libname)
     if not os.path.exists(lib):
-        pytest.skip("oracle/_ref/libcrref_cuda.so not built (needs /root/reference at build time)")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "2", "--check", "--check-setup"],
-                       capture_output=True, text=True, timeout=300)
+        pytest.skip("oracle/_ref/%s not built (needs /root/reference at build time)" % libname)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_kernels.py"), "--workload", workload, "--frames", "2"] + list(extra),
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, CRREF_LIBRARY=lib))
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, "reference kernels failed: rc=%d %s" % (r.returncode, (r.stderr or r.stdout)[-500:])
     return json.loads(lines[-1])
@@ -57,3 +60,15 @@ def test_reference_device_functions_match_oracle(size):
         assert out["coverMSAA_fast_s%d" % s]["mismatch"] == 0 and out["coverMSAA_fast_s%d" % s]["partial"] > 100
     for s in (0, 1, 2, 3):
         assert out["shade_gouraud_s%d" % s]["bary_bit_mismatch"] == 0 and out["shade_gouraud_s%d" % s]["color_max_lsb"] <= 1
+
+
+@pytest.mark.parametrize("workload", ["c1", "soup", "soup_pass", "soup_blend", "ties", "c2", "c4"])
+def test_reference_pipeline_sync_patched_equals_oracle_and_product(workload):
+    """The reference's four kernels (synchronisation patch only) on the B200: C1 cube, clipped / w <= 0 soups, ordered SrcOver
+    blending through its ROP, a duplicated mesh whose fragments all tie in depth, and BASELINE configs 2 and 4 at FULL size.
+    Depth bit-exact and colour exact against the oracle AND against the product's frame."""
+    out = _run(workload, "libcrref_cuda_sync.so", ("--check", "--check-product") + (("--check-setup",) if workload.startswith("soup") else ()))
+    print(json.dumps(out))
+    assert out["status"] == "ok", out
+    assert out["depth_mismatch_texels"] == 0 and out["color_mismatch_texels"] == 0
+    assert out["product_depth_mismatch_texels"] == 0 and out["product_color_max_lsb"] <= 1
