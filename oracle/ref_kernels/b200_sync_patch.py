@@ -16,7 +16,7 @@ can fix; case C computes the same emit masks with atomics and now takes those tr
 Nothing of the reference is stored here: edits are addressed by LINE NUMBER and guarded by the CRC32 of the original
 (stripped) line, so a different revision of the reference makes the script fail instead of mis-patching.  The patched copy
 lives in a temporary directory for the duration of one compile (oracle/Makefile: _ref/libcrref_cuda_sync.so).
-Not patched: the multi-sample fine raster (FineRaster.inl:758-1126), quad-mode dFdx / dFdy (PixelPipe.hpp:59-69)."""
+Not patched: quad-mode dFdx / dFdy (PixelPipe.hpp:59-69)."""
 import os
 import sys
 import zlib
@@ -93,6 +93,86 @@ __device__ __inline__ void executeROP_SingleSample_warp(bool active, int triIdx,
                 pend = false;
         }
         __syncwarp();
+    }
+}
+'''
+
+
+ROP_WARP_MSAA = r'''
+// [b200_sync_patch] Warp-uniform restatement of the per-sample ROP loop of fineRasterImpl_MultiSample (executeROP_MultiSample
+// called for every sample of a fragment): every lane of the warp calls it.  Same lock word (temp[pixelInTile + 16]), same rounds,
+// same surface traffic as the original; the store arbitration among lanes that hit the same pixel is explicit (highest lane).
+template <class BlendShaderClass, int SamplesLog2, U32 RenderModeFlags>
+__device__ __inline__ void executeROP_MultiSample_warp(bool active, int triIdx, int pixelX, int pixelY, int surfX0, U32 sampleMask, U32 color,
+                                                       U32 zx, U32 zy, U32 zbase, U32 oldZMax, int pixelInTile,
+                                                       volatile U32* temp, volatile U32* tileDepth, U32 tileZMax, bool& tileZUpd)
+{
+    BlendShaderClass bs;
+    const bool depthOn = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
+    volatile U32* lock = &temp[pixelInTile + 16];
+    U32 newZMax = 0;
+    int surfX = surfX0;
+    for (int i = 0; i < (1 << SamplesLog2); i++)
+    {
+        const bool covered = active && ((sampleMask & (1 << i)) != 0);
+        const U32 depth = zx * c_msaaPatterns[SamplesLog2][i] + zy * i + zbase;
+        U32 oldDepth = 0;
+        bool pend = covered;
+        if (depthOn)
+        {
+            if (active)
+            {
+                oldDepth = surf2Dread<U32>(s_depthBuffer, surfX, pixelY);
+                *lock = oldDepth;
+            }
+            __syncwarp();
+            pend = covered && depth < oldDepth;
+        }
+        for (;;)
+        {
+            const U32 act = __ballot_sync(0xFFFFFFFFu, pend);
+            if (act == 0)
+                break;
+            bool win = false;
+            if (pend)
+            {
+                const U32 peers = __match_any_sync(act, pixelInTile);
+                win = ((31 - __clz(peers)) == (int)threadIdx.x);
+                if (win)
+                {
+                    if (depthOn)
+                        *lock = depth;
+                    else if (bs.needsDst())
+                        *lock = threadIdx.x;
+                    U32 dst = (depthOn || bs.needsDst()) ? surf2Dread<U32>(s_colorBuffer, surfX, pixelY) : 0;
+                    if (depthOn || bs.needsDst())
+                        runBlendShader<BlendShaderClass>(bs, triIdx, pixelX, pixelY, i, color, dst);
+                    else
+                        runBlendShader<BlendShaderClass>(bs, triIdx, pixelX, i, pixelY, color, 0);   // argument order of the original's dst-less path
+                    if (bs.m_writeColor)
+                        surf2Dwrite<U32>(bs.m_color, s_colorBuffer, surfX, pixelY);
+                }
+            }
+            __syncwarp();
+            if (pend)
+                pend = depthOn ? (depth < *lock) : (bs.needsDst() ? !win : false);
+            __syncwarp();
+        }
+        if (depthOn && active)
+        {
+            const U32 newDepth = *lock;
+            if (newDepth != oldDepth)
+                surf2Dwrite<U32>(newDepth, s_depthBuffer, surfX, pixelY);
+            newZMax = ::max(newZMax, newDepth);
+        }
+        __syncwarp();
+        surfX += 1 << (CR_TILE_LOG2 + 2);
+    }
+    if (active && newZMax < oldZMax)
+    {
+        tileDepth[pixelInTile] = newZMax;
+        if (oldZMax == tileZMax)
+            tileZUpd = true;
     }
 }
 '''
@@ -184,6 +264,41 @@ EDITS = [
     ("FineRaster.inl", 722, 0x158a82f3, "r", ""),
     ("FineRaster.inl", 723, 0xbee8eb56, "r", ""),
     ("FineRaster.inl", 727, 0x00000000, "r", "executeROP_SingleSample_warp<BlendShaderClass, RenderModeFlags>(crb_rop, crb_tri, crb_px, crb_py, crb_color, crb_depth, tileColor, tileDepth, crb_pix);"),
+    # ---- FineRaster.inl (multi-sample kernel) -----------------------------------------------------------------------------
+    ("FineRaster.inl", 852, 0x00000000, "a", ROP_WARP_MSAA),
+    ("FineRaster.inl", 897, 0xd4d3d96c, "a", "__syncwarp();"),
+    ("FineRaster.inl", 898, 0x1d76227c, "a", "__syncwarp();"),
+    ("FineRaster.inl", 935, 0x00000000, "r", "__syncwarp();   // the per-pixel bounds other lanes initialised"),
+    ("FineRaster.inl", 982, 0x9ffc803c, "r", "U32 goodMask = __ballot_sync(0xFFFFFFFFu, pop != 0);"),
+    ("FineRaster.inl", 995, 0xfcb6e20c, "a", "__syncwarp();   // the triangles other lanes queued"),
+    ("FineRaster.inl", 1004, 0x2521c94b, "r", "temp[threadIdx.x + 16] = 0; __syncwarp();"),
+    ("FineRaster.inl", 1011, 0x00000000, "r", "__syncwarp();"),
+    ("FineRaster.inl", 1013, 0x473daac5, "r", "U32 boundaryMask = __ballot_sync(0xFFFFFFFFu, temp[ropLane.x + 16]);"),
+    ("FineRaster.inl", 1017, 0x0c1df870, "b", "bool crb_rop = false; U32 crb_mask = 0, crb_color = 0, crb_zx = 0, crb_zy = 0, crb_zbase = 0, crb_oldZMax = 0, crb_px = 0, crb_py = 0; int crb_pix = 0, crb_tri = 0, crb_surfX = 0;"),
+    ("FineRaster.inl", 1087, 0x84060788, "r", "crb_rop = true; crb_mask = sampleMask; crb_color = fragShader.m_color; crb_zx = zdata.x; crb_zy = zdata.y; crb_zbase = zbase; crb_oldZMax = oldZMax; "
+                                              "crb_px = pixelX; crb_py = pixelY; crb_pix = pixelInTile; crb_tri = triIdx; crb_surfX = tileSurfX + ((pixelInTile & 7) << 2);"),
+    ("FineRaster.inl", 1088, 0x1a4f4c75, "r", ""),
+    ("FineRaster.inl", 1090, 0x3960bd0e, "r", ""),
+    ("FineRaster.inl", 1091, 0x15d54739, "r", ""),
+    ("FineRaster.inl", 1092, 0x7f572d57, "r", ""),
+    ("FineRaster.inl", 1093, 0xeba1cefd, "r", ""),
+    ("FineRaster.inl", 1094, 0x82e37028, "r", ""),
+    ("FineRaster.inl", 1095, 0x8799314f, "r", ""),
+    ("FineRaster.inl", 1096, 0x7340bb3a, "r", ""),
+    ("FineRaster.inl", 1097, 0xb832be03, "r", ""),
+    ("FineRaster.inl", 1098, 0x994b6a50, "r", ""),
+    ("FineRaster.inl", 1100, 0xf5c0e507, "r", ""),
+    ("FineRaster.inl", 1101, 0xfcb6e20c, "r", ""),
+    ("FineRaster.inl", 1103, 0x061cff3e, "r", ""),
+    ("FineRaster.inl", 1104, 0x15d54739, "r", ""),
+    ("FineRaster.inl", 1105, 0x1d54207b, "r", ""),
+    ("FineRaster.inl", 1106, 0x5e7025d1, "r", ""),
+    ("FineRaster.inl", 1107, 0x67f4cb43, "r", ""),
+    ("FineRaster.inl", 1108, 0xa5e18a19, "r", ""),
+    ("FineRaster.inl", 1109, 0x4f8656a2, "r", ""),
+    ("FineRaster.inl", 1110, 0xfcb6e20c, "r", ""),
+    ("FineRaster.inl", 1114, 0x00000000, "r", "executeROP_MultiSample_warp<BlendShaderClass, SamplesLog2, RenderModeFlags>(crb_rop, crb_tri, crb_px, crb_py, crb_surfX, crb_mask, crb_color, "
+                                              "crb_zx, crb_zy, crb_zbase, crb_oldZMax, crb_pix, temp, tileDepth, tileZMax, tileZUpd);"),
 ]
 
 

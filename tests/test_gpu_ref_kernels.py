@@ -62,13 +62,22 @@ def test_reference_device_functions_match_oracle(size):
         assert out["shade_gouraud_s%d" % s]["bary_bit_mismatch"] == 0 and out["shade_gouraud_s%d" % s]["color_max_lsb"] <= 1
 
 
-@pytest.mark.parametrize("workload", ["c1", "soup", "soup_pass", "soup_blend", "ties", "c2", "c4"])
+@pytest.mark.parametrize("workload", ["c1", "soup", "soup_pass", "soup_blend", "soup_msaa_front", "soup_msaa", "ties", "c2", "c4"])
 def test_reference_pipeline_sync_patched_equals_oracle_and_product(workload):
     """The reference's four kernels (synchronisation patch only) on the B200: C1 cube, clipped / w <= 0 soups, ordered SrcOver
-    blending through its ROP, a duplicated mesh whose fragments all tie in depth, and BASELINE configs 2 and 4 at FULL size.
+    blending through its ROP, 4x MSAA (per-sample ROP on the surfaces), a duplicated mesh whose fragments all tie in depth, and BASELINE configs 2 and 4 at FULL size.
     Depth bit-exact and colour exact against the oracle AND against the product's frame."""
     out = _run(workload, "libcrref_cuda_sync.so", ("--check", "--check-product") + (("--check-setup",) if workload.startswith("soup") else ()))
     print(json.dumps(out))
+    if workload == "soup_msaa":
+        # The one place where the reference's kernels and the oracle may part: a sub-triangle left by clipping at w ~ 0 whose
+        # fixed-point depth plane yields depths BELOW the triangle's own zmin; the reference's zmin-based culls
+        # (FineRaster.inl:229-241, :1048-1062) then drop fragments the plane would have let through (DESIGN.md "known divergences":
+        # 1 sample of 921 600 here; none in soup_msaa_front, the same soup without vertices at w <= 0).  Product == oracle there.
+        assert out["depth_mismatch_texels"] <= 4 and out["product_depth_mismatch_texels"] == out["depth_mismatch_texels"]
+        for _, _, ref_depth, oracle_depth in out.get("depth_mismatches", []):
+            assert ref_depth > oracle_depth      # the reference CULLED a fragment the plane equation puts in front
+        return
     assert out["status"] == "ok", out
     assert out["depth_mismatch_texels"] == 0 and out["color_mismatch_texels"] == 0
     assert out["product_depth_mismatch_texels"] == 0 and out["product_color_max_lsb"] <= 1
