@@ -25,7 +25,7 @@ class _PipeSpec(ctypes.Structure):
 class Atomics(ctypes.Structure):
     _fields_ = [("numSubtris", ctypes.c_int32), ("numBinEntries", ctypes.c_int32), ("numCoarseItems", ctypes.c_int32),
                 ("numTileEntries", ctypes.c_int32), ("numActiveTiles", ctypes.c_int32), ("overflow", ctypes.c_int32),
-                ("numLargeTris", ctypes.c_int32), ("numQueuedCtas", ctypes.c_int32)]
+                ("numLargeTris", ctypes.c_int32), ("numQueuedCtas", ctypes.c_int32), ("allocBarrier", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class BatchFrame(ctypes.Structure):

@@ -35,6 +35,8 @@
 // stage reads contiguous runs instead of chasing segment pointers.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "../../include/cudaraster/cuda/Overlap.cuh"
 
 using namespace FW;
@@ -463,9 +465,32 @@ __global__ void __launch_bounds__(kThreads) directAllocKernel(const __grid_const
     if (threadIdx.x == 0) s_abort = f.atomics->overflow | ((f.microMode != 0 && f.atomics->numQueuedCtas == 0) ? 1 : 0);
     __syncthreads();
     if (s_abort != 0) return;
+    // The LARGE sub-triangles setup listed (final: setup has ended) are counted here, one whole CTA per triangle at a time and
+    // every CTA of the grid taking its share, followed by a grid barrier: the scan below needs the complete counts.  The grid
+    // is small (one CTA per 256 tiles, <= 256 CTAs of 256 threads) and therefore co-resident, which is what lets a CTA wait
+    // for the others; frames without large triangles skip both.
+    const int numLarge = min(f.atomics->numLargeTris, f.maxLarge);
+    if (numLarge > 0) {
+        for (int k = blockIdx.x; k < numLarge; k += gridDim.x) {
+            const uint4 h = __ldg(&f.triHeader[f.largeList[k].y]);
+            const TriFootprint fp = f.samplesLog2 == 0 ? triFootprint<0>(h.x, h.y, h.z, f) : triFootprint<1>(h.x, h.y, h.z, f);
+            auto count = [&](S32 tx, S32 ty) { atomicAdd(&f.tileCounter[tx + ty * f.widthTiles], 1); };
+            auto countSpan = [&](S32 ty, S32 xa, S32 xb) { for (S32 tx = xa; tx <= xb; tx++) atomicAdd(&f.tileCounter[tx + ty * f.widthTiles], 1); };
+            if (f.samplesLog2 == 0) forEachCellCoop<0, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, kThreads, count, countSpan);
+            else forEachCellCoop<1, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, kThreads, count, countSpan);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&f.atomics->allocBarrier, 1);
+            while (*(volatile int*)&f.atomics->allocBarrier < (int)gridDim.x) __nanosleep(64);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     const int t = blockIdx.x * kThreads + threadIdx.x;
     const bool inside = t < f.numTiles;
-    const int cnt = inside ? f.tileCounter[t] : 0;
+    const int cnt = inside ? *(volatile int*)&f.tileCounter[t] : 0;   // (volatile: other CTAs' reductions landed behind the barrier above)
     if (cnt != 0) f.tileCounter[t] = 0;   // clean for the next frame's setup
     // micro mode: every tile is active (a tile without queue entries may hold fragments in the visibility buffer) and
     // the fine raster addresses tiles directly, numActiveTiles == numTiles
@@ -497,9 +522,9 @@ __global__ void __launch_bounds__(kThreads) directAllocKernel(const __grid_const
 // placed entry costs two scattered memory operations: the atomic and the store -- the kernel is bound by the rate at
 // which an SM issues scattered accesses, not by latency.  (Measured and rejected: warp-aggregated atomics with
 // __match_any_sync -- 25 vs 19 us on C2, 109 vs 52 us on C4: the match costs more than the atomics it saves.)
-// Clipped, refined and large triangles go through triSubtris / the headers; sub-triangles that span more than
-// CRB_DIRECT_MAX_TILES tiles on an axis go on a per-CTA list and are scattered by the whole CTA together (same split
-// as the count pass in triangle setup).
+// Clipped and refined triangles go through triSubtris / the headers; sub-triangles that span more than CRB_DIRECT_MAX_TILES tiles
+// on an axis are on triangle setup's global list and are scattered by whole CTAs at the end of the kernel (same split as the
+// count pass).
 #ifndef CRB_SCATTER_MIN_BLOCKS
 #define CRB_SCATTER_MIN_BLOCKS 6
 #endif
@@ -507,7 +532,7 @@ constexpr int kScatterTris = 4;
 
 // The uncommon triangle of the scatter pass (kept out of line: its S64 edge tests must not cost the common path registers).
 template <int SamplesLog2>
-static __device__ __noinline__ void scatterGeneralTriangle(const crb_frame& f, int tri, int* s_numLarge, int* s_largeEntry, int* s_largeSlot) {
+static __device__ __noinline__ void scatterGeneralTriangle(const crb_frame& f, int tri) {
     auto place = [&](S32 tile, S32 entry) {
         f.tileQueue[atomicSub(&f.tileCursor[tile], 1) - 1] = entry;
     };
@@ -519,19 +544,13 @@ static __device__ __noinline__ void scatterGeneralTriangle(const crb_frame& f, i
         const uint4 hs = n == 1 ? h : __ldg(&f.triHeader[slot]);
         const TriFootprint fp = triFootprint<SamplesLog2>(hs.x, hs.y, hs.z, f);
         const CellRange r = cellRange<CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1);
-        if ((r.nx > CRB_DIRECT_MAX_TILES) | (r.ny > CRB_DIRECT_MAX_TILES)) {
-            const int q = atomicAdd(s_numLarge, 1);
-            if (q < kThreads) { s_largeEntry[q] = entry; s_largeSlot[q] = slot; continue; }
-        }
+        if ((r.nx > CRB_DIRECT_MAX_TILES) | (r.ny > CRB_DIRECT_MAX_TILES)) continue;   // on the large list (same rule as triangle setup)
         forEachCell<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, [&](S32 tx, S32 ty) { place(tx + ty * f.widthTiles, entry); });
     }
 }
 
 template <int SamplesLog2>
 __global__ void __launch_bounds__(kThreads, CRB_SCATTER_MIN_BLOCKS) directScatterKernel(const __grid_constant__ crb_frame f) {
-    __shared__ int s_numLarge;
-    __shared__ int s_largeEntry[kThreads], s_largeSlot[kThreads];
-    if (threadIdx.x == 0) s_numLarge = 0;
     gridDepLaunchDependents();
     gridDepWait();
     if (f.atomics->numTileEntries == 0) return;   // nothing was queued (every triangle went the micro way): final since directAllocKernel ended
@@ -569,17 +588,30 @@ __global__ void __launch_bounds__(kThreads, CRB_SCATTER_MIN_BLOCKS) directScatte
 
 #pragma unroll 1
     for (int k = 0; k < kScatterTris; k++)   // clipped, refined or large: through the headers
-        if (code[k] == CRB_TILECODE_GENERAL) scatterGeneralTriangle<SamplesLog2>(f, base + k, &s_numLarge, s_largeEntry, s_largeSlot);
+        if (code[k] == CRB_TILECODE_GENERAL) scatterGeneralTriangle<SamplesLog2>(f, base + k);
     auto place = [&](S32 tile, S32 entry) {
         f.tileQueue[atomicSub(&f.tileCursor[tile], 1) - 1] = entry;
     };
-    __syncthreads();
-    const int numLarge = min(s_numLarge, kThreads);
-    for (int k = 0; k < numLarge; k++) {
-        const S32 entry = s_largeEntry[k];
-        const uint4 hs = __ldg(&f.triHeader[s_largeSlot[k]]);
+    // the large sub-triangles of the frame (triangle setup's global list), one whole CTA per triangle at a time, all CTAs sharing the list
+    const int numLarge = min(f.atomics->numLargeTris, f.maxLarge);
+    for (int k = blockIdx.x; k < numLarge; k += gridDim.x) {
+        const int2 e = f.largeList[k];
+        const uint4 hs = __ldg(&f.triHeader[e.y]);
         const TriFootprint fp = triFootprint<SamplesLog2>(hs.x, hs.y, hs.z, f);
-        forEachCellStrided<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, kThreads, [&](S32 tx, S32 ty) { place(tx + ty * f.widthTiles, entry); });
+        // a span of a row: eight slots are taken (eight independent atomics in flight) before the first entry is stored
+        auto placeSpan = [&](S32 ty, S32 xa, S32 xb) {
+            int* const cur = f.tileCursor + ty * f.widthTiles;
+            for (S32 x0 = xa; x0 <= xb; x0 += 8) {
+                int pos[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (x0 + j <= xb) pos[j] = atomicSub(cur + x0 + j, 1) - 1;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (x0 + j <= xb) f.tileQueue[pos[j]] = e.x;
+            }
+        };
+        forEachCellCoop<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, kThreads, [&](S32 tx, S32 ty) { place(tx + ty * f.widthTiles, e.x); }, placeSpan);
     }
 }
 
@@ -613,7 +645,9 @@ extern "C" int crb_launch_direct_alloc(const crb_frame* f, void* stream) {
 
 extern "C" int crb_launch_direct_scatter(const crb_frame* f, void* stream) {
     if (f->numTris <= 0) return CRB_OK;
-    const int grid = (f->numTris + kThreads * kScatterTris - 1) / (kThreads * kScatterTris);
+    // one thread per 4 triangles -- but never fewer CTAs than it takes to fill the GPU: the CTAs share out the list of large
+    // sub-triangles, however few input triangles the frame has
+    const int grid = std::max((f->numTris + kThreads * kScatterTris - 1) / (kThreads * kScatterTris), 2 * std::max(f->numSMs, 1));
     const cudaError_t e = f->samplesLog2 == 0 ? launchChained(directScatterKernel<0>, grid, kThreads, (cudaStream_t)stream, *f)
                                               : launchChained(directScatterKernel<1>, grid, kThreads, (cudaStream_t)stream, *f);
     return e == cudaSuccess ? checkLaunch() : CRB_ERR_CUDA;

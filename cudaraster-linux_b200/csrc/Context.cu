@@ -73,7 +73,7 @@ struct crb_ctx {
     std::string pipeName;
 
     // work buffers
-    int maxSubtris = 1, maxBinEntries = 1, maxTileEntries = 1, maxItems = 1;
+    int maxSubtris = 1, maxBinEntries = 1, maxTileEntries = 1, maxItems = 1, maxLarge = 16384;
     DevBuf triSubtris, triHeader, triData;
     DevBuf binCountMat, binStart, binTotal, binQueue;
     DevBuf items, binItemBase, binItemCount, tileCountMat;
@@ -85,14 +85,10 @@ struct crb_ctx {
     size_t visBytes = 0;                 // extent the current surface uses
     DevBuf tileCursor;                   // direct tile path: per-tile queue cursors (alloc -> scatter)
     DevBuf triTileCode;                  // direct tile path: one word per input triangle (setup -> scatter)
+    DevBuf largeList;                    // direct tile path: {entry, slot} of the large sub-triangles (setup -> alloc, scatter)
     DevBuf batchQueued;                  // direct tile path: one byte per batch of 32 triangles (did setup leave their words in triTileCode?)
-    // Binning strategy (crb_set_binning_mode): the direct path runs when the pipe is order independent and the last
-    // completed frame of the same SHAPE (triangle count, surface, window, pipe) reported no large triangle.
-    int binningMode = 1;                 // 0 never, 1 automatic, 2 try on every eligible frame
-    bool shapeValid = false;
-    unsigned long long shapeHash = 0;    // shape of the frame shapeNumLarge was measured on
-    int shapeNumLarge = 0;
-    unsigned long long pendingShape[64] = {};
+    // Binning strategy (crb_set_binning_mode): the direct path runs whenever the pipe is order independent.
+    int binningMode = 1;                 // 0 never, 1 automatic (= 2), 2 on every eligible frame
     struct PendingFrame {                // what crb_finish needs to know about an asynchronous frame
         int numTris = 0;
         cudaStream_t stream = nullptr;
@@ -164,27 +160,13 @@ constexpr int kAsyncRing = 64;
 
 int popc8(int v) { return __builtin_popcount((unsigned)v & 0xFF); }
 
-// What the direct-path decision is keyed on: a frame of the same shape as one that had no large triangle.
-unsigned long long frameShape(const crb_ctx* c) {
-    unsigned long long h = 1469598103934665603ull;
-    auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
-    mix((unsigned)c->numTris); mix((unsigned)c->width); mix((unsigned)c->height); mix((unsigned)c->samplesLog2);
-    mix((unsigned)c->fullWidth); mix((unsigned)c->fullHeight); mix((unsigned)c->subX0); mix((unsigned)c->subY0);
-    for (char ch : c->pipeName) mix((unsigned char)ch);
-    return h;
-}
-
+// The direct tile path serves every frame of an order-independent pipe: triangles of any size are exact there (large ones are
+// counted and scattered by whole CTAs, row spans found by bisection -- Overlap.cuh forEachCellStrided), so the decision needs
+// no knowledge of the scene: the first frame of a shape and frames with a changing triangle count take it as well.
 bool wantDirect(const crb_ctx* c) {
     if (c->binningMode == 0 || !c->hasPipe || !c->pipe.orderIndependent) return false;
     if (c->spec.profilingMode != ProfilingMode_Default) return false;   // the counters describe the ordered two-level path
-    if (c->binningMode == 2) return true;
-    return c->shapeValid && c->shapeHash == frameShape(c) && c->shapeNumLarge == 0;
-}
-
-// Book-keeping after the counters of a completed frame came back.
-void noteFrameCounters(crb_ctx* c, unsigned long long shape, const crb_atomics& a) {
-    if (a.overflow != 0) return;
-    c->shapeValid = true; c->shapeHash = shape; c->shapeNumLarge = a.numLargeTris;
+    return true;
 }
 
 // Fills the frame block and (re)allocates the work buffers for the current capacities.
@@ -309,6 +291,8 @@ int prepareFrame(crb_ctx* c) {
         c->visBytes = std::max(c->visBytes, need);
     }
     if (f.directMode) CRB_CUDA(c, c->triTileCode.reserve(((size_t)std::max(c->numTris, 1) + 4) * 4));
+    if (f.directMode) CRB_CUDA(c, c->largeList.reserve((size_t)c->maxLarge * 8));
+    f.maxLarge = c->maxLarge;
     if (f.directMode) CRB_CUDA(c, c->batchQueued.reserve((size_t)std::max(c->numTris, 1) / 32 + 16));
 
     f.triSubtris = (uint8_t*)c->triSubtris.ptr;
@@ -332,6 +316,7 @@ int prepareFrame(crb_ctx* c) {
     f.visBuffer = (unsigned long long*)c->visBuffer.ptr;
     f.triTileCode = (uint32_t*)c->triTileCode.ptr;
     f.batchQueued = (uint8_t*)c->batchQueued.ptr;
+    f.largeList = (int2*)c->largeList.ptr;
     f.atomics = (crb_atomics*)c->atomics.ptr + c->atomicsParity;
     f.nextAtomics = (crb_atomics*)c->atomics.ptr + (c->atomicsParity ^ 1);
     if (oldBinMat != c->binCountMat.ptr || oldTileMat != c->tileCountMat.ptr || c->lastNumBins != f.numBins || c->lastMatPitch != f.matPitch ||
@@ -440,7 +425,7 @@ int crb_destroy(crb_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->triSubtris, &c->triHeader, &c->triData, &c->binCountMat, &c->binStart, &c->binTotal, &c->binQueue, &c->items, &c->binItemBase,
-                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode, &c->batchQueued, &c->visBuffer, &c->profCounters};
+                      &c->binItemCount, &c->tileCountMat, &c->tileQueue, &c->tileStart, &c->tileCount, &c->activeTiles, &c->activeRecs, &c->atomics, &c->hostVerts, &c->hostIdx, &c->tileCounter, &c->tileCursor, &c->triTileCode, &c->batchQueued, &c->largeList, &c->visBuffer, &c->profCounters};
     for (DevBuf* b : bufs) b->release();
     if (c->hp.init) {
         cudaStreamDestroy(c->hp.up);
@@ -541,6 +526,12 @@ int crb_set_pixel_pipe_by_name(crb_ctx* c, void* module, const char* name) {
     d.coarseRaster = (crb_stage_fn)dlsym(handle, (n + "_coarseRaster").c_str());
     d.fineRaster = (crb_stage_fn)dlsym(handle, (n + "_fineRaster").c_str());
     typedef int (*ProbeFn)(void);
+    ProbeFn frameBytes = (ProbeFn)dlsym(handle, (n + "_frameBytes").c_str());
+    if (frameBytes && frameBytes() != (int)sizeof(crb_frame)) {
+        c->hasPipe = false;
+        return setError(c, CRB_ERR_INVALID, "CudaRaster: pixel pipe module '%s' was built against other headers than this library (frame block %d vs %d bytes): rebuild it!", name,
+                        frameBytes(), (int)sizeof(crb_frame));
+    }
     ProbeFn probe = (ProbeFn)dlsym(handle, (n + "_orderIndependent").c_str());   // optional (pipes built before ABI 2 lack it)
     d.orderIndependent = 0;
     if (probe) {
@@ -587,7 +578,6 @@ int crb_set_binning_mode(crb_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 3) return CRB_ERR_INVALID;
     c->binningMode = mode == 3 ? 2 : mode;
     c->microOff = mode == 3;
-    c->shapeValid = false;
     return CRB_OK;
 }
 
@@ -638,7 +628,6 @@ int crb_draw_triangles(crb_ctx* c, void* stream) {
         crb_atomics a = *c->hostAtomics;
         a.numSubtris += numTris;
         c->lastAtomics = a;
-        noteFrameCounters(c, frameShape(c), a);
         if (a.overflow == 0) break;
         c->needReset = true;   // the kernels of an overflowed frame return early and leave the count matrices dirty
         if (attempt > 8) return setError(c, CRB_ERR_LIMIT, "CudaRaster: work buffers keep overflowing (flags %d)", a.overflow);
@@ -646,6 +635,7 @@ int crb_draw_triangles(crb_ctx* c, void* stream) {
         if (a.overflow & 1) c->maxSubtris = std::max(c->maxSubtris, a.numSubtris + 4096);
         if (a.overflow & (2 | 8)) c->maxBinEntries = std::max(c->maxBinEntries, a.numBinEntries + a.numBinEntries / 16 + 16384);
         if (a.overflow & 4) c->maxTileEntries = std::max(c->maxTileEntries, a.numTileEntries + a.numTileEntries / 16 + 65536);
+        if (a.overflow & 32) c->maxLarge = std::max(c->maxLarge, a.numLargeTris + a.numLargeTris / 4 + 4096);
     }
     c->deferredClear = false;
     c->drawn = true;
@@ -676,13 +666,13 @@ int crb_finish(crb_ctx* c, void* stream) {
         a.numSubtris += c->pendingFrame[i].numTris;
         if (overflowed && a.overflow != 0 && (a.overflow & 16) != 0) continue;   // a frame skipped because an EARLIER frame of the batch overflowed (sticky flag, bit 4): its counters mean nothing
         c->lastAtomics = a;
-        noteFrameCounters(c, c->pendingShape[i], a);
         if (a.overflow == 0) continue;
         overflowed++;
         if (firstBad < 0) firstBad = i;
         if (a.overflow & 1) c->maxSubtris = std::max(c->maxSubtris, a.numSubtris + 4096);
         if (a.overflow & (2 | 8)) c->maxBinEntries = std::max(c->maxBinEntries, a.numBinEntries + a.numBinEntries / 16 + 16384);
         if (a.overflow & 4) c->maxTileEntries = std::max(c->maxTileEntries, a.numTileEntries + a.numTileEntries / 16 + 65536);
+        if (a.overflow & 32) c->maxLarge = std::max(c->maxLarge, a.numLargeTris + a.numLargeTris / 4 + 4096);
     }
     const int n = c->pending;
     c->pending = 0;
@@ -725,7 +715,6 @@ int crb_draw_triangles_async(crb_ctx* c, void* stream) {
     rc = launchStages(c, s, c->stageTiming ? c->ringEv[c->pending] : nullptr);
     if (rc != CRB_OK) return rc;
     CRB_CUDA(c, cudaMemcpyAsync(&c->hostAtomics[1 + c->pending], c->frame.atomics, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
-    c->pendingShape[c->pending] = frameShape(c);
     crb_ctx::PendingFrame& pf = c->pendingFrame[c->pending];
     pf.numTris = numTris; pf.stream = s; pf.hadClear = c->deferredClear; pf.clearColor = c->clearColor; pf.clearDepth = c->clearDepth;
     c->pending++;

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 2
+#define CRB_ABI_VERSION 3
 
 typedef enum crb_status {
     CRB_OK = 0,
@@ -61,9 +61,11 @@ typedef struct crb_atomics {
     int32_t numCoarseItems;    /* work items the coarse stage processed                        */
     int32_t numTileEntries;    /* triangle-tile pairs written to the tile queue                */
     int32_t numActiveTiles;    /* tiles the fine stage touches                                 */
-    int32_t overflow;          /* bit0 subtris, bit1 bin queue, bit2 tile queue, bit3 items */
-    int32_t numLargeTris;      /* setup CTAs (256 triangles) that met a sub-triangle spanning > CRB_DIRECT_MAX_TILES tiles on an axis */
+    int32_t overflow;          /* bit0 subtris, bit1 bin queue, bit2 tile queue, bit3 items, bit4 an earlier frame of the batch overflowed, bit5 large list */
+    int32_t numLargeTris;      /* direct path: sub-triangles spanning > CRB_DIRECT_MAX_TILES tiles on an axis (counted and scattered by whole CTAs from a global list) */
     int32_t numQueuedCtas;     /* direct path: setup CTAs that put at least one sub-triangle on a tile queue (0 = everything went the micro way) */
+    int32_t allocBarrier;      /* direct path: grid barrier of the queue-allocation kernel (internal) */
+    int32_t reserved;
 } crb_atomics;
 
 /* Everything a stage launcher needs; filled by crb_draw_triangles().  Opaque to C callers,
@@ -134,10 +136,11 @@ int crb_set_subviewport(crb_ctx* ctx, int fullWidth, int fullHeight, int x0, int
  * the tiles of every triangle, one kernel allocates the tile queues and one scatters the entries with atomics, in
  * arbitrary order -- valid only for order-independent pipes (crb_pipe_desc.orderIndependent); it is built for frames
  * of small triangles (a triangle spanning more than CRB_DIRECT_MAX_TILES tiles on an axis is handled by a whole CTA
- * at a time, correct but slower than the bins of the general path).  mode 0 = never, 1 = automatic (default: direct
- * when the last completed frame of the same shape -- triangle count, surface, window, pipe -- had no such triangle),
- * 2 = direct on every frame whose pipe allows it, 3 = like 2 but without the micro-triangle visibility buffer (below;
- * a testing aid).  Surfaces are bit-identical on all paths.
+ * at a time: rows of tiles are shared out over its threads and the covered span of a row is found by bisection).  mode 0 =
+ * never, 1 = automatic (default) = 2 = direct on every frame whose pipe allows it -- the decision needs no knowledge of the
+ * scene, so the first frame and frames with a changing triangle count take the direct path too --, 3 = like 2 but without
+ * the micro-triangle visibility buffer (below; a testing aid: setup then writes every record in full).  Surfaces are
+ * bit-identical on all paths.
  * Micro-triangles: on single-sample direct frames, triangle setup rasterizes every triangle whose pixel-centre
  * footprint is at most 4x4 pixels itself -- exact coverage, plane depth, one 64-bit atomicMin of (depth << 32 | index)
  * per covered pixel into a per-pixel visibility buffer -- and never queues it; the fine raster merges the buffer

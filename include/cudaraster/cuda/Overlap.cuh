@@ -75,9 +75,18 @@ __device__ __forceinline__ void forEachCell(const TriFootprint& t, S32 winLoX, S
         }
 }
 
-// The same enumeration shared out over `stride` cooperating threads (thread `first` of them): used for the few
-// triangles that span many cells, where one thread walking the whole rectangle would be a long tail.  Visits
-// exactly the cells forEachCell visits (a rectangle larger than 2x2 cells is always refined).
+// The same enumeration shared out over `stride` cooperating threads (thread `first` of them), for the few triangles that span
+// many cells, where one thread walking the whole rectangle would be a long tail.  Two forms that visit exactly the cells
+// forEachCell visits (a rectangle larger than 2x2 cells is always refined):
+//   forEachCellStrided    the cells of the rectangle dealt out one by one, three edge tests per cell -- footprints of a few
+//                         hundred cells;
+//   forEachCellRowSpans   threads take ROWS of cells; in a row the cells the edge tests accept form one span, because every
+//                         test is monotone in the cell's x (the edge function is linear in the sample position and the sample
+//                         extent of a cell, clamped to the footprint, moves monotonically with x): the ends of the span are
+//                         found by bisection with the very predicate forEachCell applies, ~3 x log2(width) edge evaluations
+//                         per row instead of 3 x width -- footprints of thousands of cells (a full-screen triangle has 32 400
+//                         tiles at 1080p).
+// forEachCellCoop picks by the size of the rectangle.
 template <int SamplesLog2, int CellLog2, class Fn>
 __device__ __forceinline__ void forEachCellStrided(const TriFootprint& t, S32 winLoX, S32 winLoY, S32 winHiX, S32 winHiY, int first, int stride, Fn fn) {
     if (t.empty) return;
@@ -95,6 +104,61 @@ __device__ __forceinline__ void forEachCellStrided(const TriFootprint& t, S32 wi
         }
         fn(cx, cy);
     }
+}
+
+template <int SamplesLog2>
+__device__ __forceinline__ bool cellEdgeAccepts(const TriFootprint& t, int i, S32 pxA, S32 pyA, S32 pxB, S32 pyB) {
+    const S32 in = SamplesLog2 == 0 ? 8 : 1, out = SamplesLog2 == 0 ? 8 : 15;
+    const S64 X0 = (S64)pxA * 16 + in, X1 = (S64)pxB * 16 + out, Y0 = (S64)pyA * 16 + in, Y1 = (S64)pyB * 16 + out;
+    const S32 ex = i == 1 ? t.x1 : t.x0, ey = i == 1 ? t.y1 : t.y0;
+    const S32 dx = i == 0 ? t.x1 - t.x0 : i == 1 ? t.x2 - t.x1 : t.x0 - t.x2, dy = i == 0 ? t.y1 - t.y0 : i == 1 ? t.y2 - t.y1 : t.y0 - t.y2;
+    const S64 px = dy < 0 ? X1 : X0, py = dx > 0 ? Y1 : Y0;
+    const S64 e = ((S64)ex - px) * dy - ((S64)ey - py) * dx;
+    const S64 tie = (dy > 0 || (dy == 0 && dx <= 0)) ? 1 : 0;
+    return e - tie >= 0;   // == !(cellRejected's test of edge i)
+}
+
+template <int SamplesLog2, int CellLog2, class SpanFn>
+__device__ __forceinline__ void forEachCellRowSpans(const TriFootprint& t, S32 winLoX, S32 winLoY, S32 winHiX, S32 winHiY, int first, int stride, SpanFn spanFn) {
+    if (t.empty) return;
+    S32 cLoX = t.pxLoX >> CellLog2, cHiX = t.pxHiX >> CellLog2, cLoY = t.pxLoY >> CellLog2, cHiY = t.pxHiY >> CellLog2;
+    const bool refine = (cHiX - cLoX > 1) | (cHiY - cLoY > 1);
+    cLoX = max(cLoX, winLoX); cHiX = min(cHiX, winHiX); cLoY = max(cLoY, winLoY); cHiY = min(cHiY, winHiY);
+    if (cHiX < cLoX || cHiY < cLoY) return;
+    const S32 cell = 1 << CellLog2;
+    for (S32 cy = cLoY + first; cy <= cHiY; cy += stride) {
+        S32 xa = cLoX, xb = cHiX;   // the span of accepted cells of this row
+        if (refine) {
+            const S32 pyA = max(cy << CellLog2, t.pxLoY), pyB = min((cy << CellLog2) + cell - 1, t.pxHiY);
+            auto accepts = [&](int i, S32 cx) { return cellEdgeAccepts<SamplesLog2>(t, i, max(cx << CellLog2, t.pxLoX), pyA, min((cx << CellLog2) + cell - 1, t.pxHiX), pyB); };
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const S32 dy = i == 0 ? t.y1 - t.y0 : i == 1 ? t.y2 - t.y1 : t.y0 - t.y2;
+                if (xa > xb) break;
+                if (dy < 0) {          // the edge function grows with x: accepted cells are the right part of the row
+                    if (!accepts(i, xb)) { xa = xb + 1; break; }
+                    S32 lo = xa, hi = xb;   // smallest accepted x in [lo, hi]; hi is accepted
+                    while (lo < hi) { const S32 mid = (lo + hi) >> 1; if (accepts(i, mid)) hi = mid; else lo = mid + 1; }
+                    xa = lo;
+                } else if (dy > 0) {   // it falls with x: the left part
+                    if (!accepts(i, xa)) { xa = xb + 1; break; }
+                    S32 lo = xa, hi = xb;   // largest accepted x in [lo, hi]; lo is accepted
+                    while (lo < hi) { const S32 mid = (lo + hi + 1) >> 1; if (accepts(i, mid)) lo = mid; else hi = mid - 1; }
+                    xb = lo;
+                } else if (!accepts(i, xa)) { xa = xb + 1; break; }   // constant along the row
+            }
+        }
+        if (xa <= xb) spanFn(cy, xa, xb);   // cells (xa..xb, cy)
+    }
+}
+
+// fn(cx, cy) takes one cell, spanFn(cy, xa, xb) the cells xa..xb of row cy (so that a caller whose per-cell work has a long
+// latency -- an atomic whose result it needs -- can keep several cells of a span in flight).
+template <int SamplesLog2, int CellLog2, class Fn, class SpanFn>
+__device__ __forceinline__ void forEachCellCoop(const TriFootprint& t, S32 winLoX, S32 winLoY, S32 winHiX, S32 winHiY, int first, int stride, Fn fn, SpanFn spanFn) {
+    const S32 nx = (t.pxHiX >> CellLog2) - (t.pxLoX >> CellLog2) + 1, ny = (t.pxHiY >> CellLog2) - (t.pxLoY >> CellLog2) + 1;
+    if (nx >= 32 && ny * 4 >= stride) forEachCellRowSpans<SamplesLog2, CellLog2>(t, winLoX, winLoY, winHiX, winHiY, first, stride, spanFn);   // enough rows to keep a good part of the threads busy
+    else forEachCellStrided<SamplesLog2, CellLog2>(t, winLoX, winLoY, winHiX, winHiY, first, stride, fn);
 }
 
 // Cell rectangle of a footprint inside an inclusive cell window: first cell, extent (0 = nothing)

@@ -58,6 +58,8 @@ inline int probeOrderIndependent() {
         if (cached < 0) cached = FW::probeOrderIndependent<FRAGMENT_SHADER, BLEND_SHADER, SAMPLES_LOG2, RENDER_MODE_FLAGS>();               \
         return cached;                                                                                                                      \
     }                                                                                                                                       \
+    /* layout guard: the module and the library must have been built from the same headers (crb_frame travels by value) */                 \
+    extern "C" int PIPE_NAME##_frameBytes(void) { return (int)sizeof(crb_frame); }                                                         \
     extern "C" const crb_pipe_spec PIPE_NAME##_spec = {                                                                                     \
         /* samplesLog2 */ SAMPLES_LOG2,                                                                                                     \
         /* vertexStructSize */ (int)sizeof(VERTEX_STRUCT),                                                                                  \

@@ -130,6 +130,8 @@ struct crb_frame {
     // its tile state and writes the neutral value (all ones) back, so the buffer is clean for the next frame.
     int32_t microMode;            // 1 = on (implies directMode)
     unsigned long long* visBuffer; // [heightPixels][widthPixels]
+    int2* largeList;              // [maxLarge] {queue entry, record slot} of the LARGE sub-triangles (> CRB_DIRECT_MAX_TILES tiles on an axis), appended
+    int32_t maxLarge;             // by setup; the allocation and scatter kernels walk it with whole CTAs (one large triangle per CTA at a time)
     uint8_t* batchQueued;         // [ceil(numTris / 32)] 1 = the 32 triangles of the batch have their words in triTileCode (one of them was queued)
     uint32_t* triTileCode;        // [numTris] what the scatter pass needs to know about a triangle in ONE word: 0 = nothing to place,
                                   // CRB_TILECODE_GENERAL = go through triSubtris / the headers (clipped, refined or large), else

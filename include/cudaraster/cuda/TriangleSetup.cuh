@@ -187,20 +187,17 @@ static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 
     }
 }
 
-// What binning needs from a finished sub-triangle (header h, stored in record `slot`).  General path: the bins it
-// touches go into the CTA's bin histogram.  Direct tile path (crb_frame::directMode): every tile it touches is
-// counted straight into the per-tile counters with fire-and-forget global reductions; sub-triangles that span
-// more than CRB_DIRECT_MAX_TILES tiles on an axis are put on a per-CTA list and counted by the whole CTA together
-// at the end of the kernel (a thread walking thousands of tiles alone would be a long tail).  Either way the CTA
-// reports whether it met such a large sub-triangle: the automatic binning mode only goes direct while there are none.
+// What binning needs from a finished sub-triangle (header h, queue entry `entry`, stored in record `slot`).  General path: the
+// bins it touches go into the CTA's bin histogram.  Direct tile path (crb_frame::directMode): every tile it touches is counted
+// straight into the per-tile counters with fire-and-forget global reductions; sub-triangles that span more than
+// CRB_DIRECT_MAX_TILES tiles on an axis go on a GLOBAL list (crb_frame::largeList) instead: the queue-allocation kernel counts
+// them and the scatter kernel places them with one whole CTA per triangle, all SMs sharing the list -- a thread walking
+// thousands of tiles alone, or the one CTA that happens to hold the scene's big triangles, would be a long tail.
 struct SetupCtaShared {   // per CTA
-    int sawLarge;          // the CTA met a large sub-triangle
-    int numLarge;          // the CTA's list of large sub-triangles (record slots)
-    int largeSlot[CRB_SETUP_THREADS];
     int binCount[CR_MAXBINS_SQR];   // bin histogram of the CTA's chunk (general path)
 };
 struct SetupShared {      // a VIEW of the binning scratch in shared memory (passed by value: two pointers)
-    int* queuedAny;        // direct path: a sub-triangle of this CTA went to the tile counters
+    int* queuedAny;        // direct path: a sub-triangle of this CTA went to the tile counters (or onto the large list)
     SetupCtaShared* cta;
 };
 
@@ -208,18 +205,17 @@ struct SetupShared {      // a VIEW of the binning scratch in shared memory (pas
 // DeferSmall: the caller counts a footprint of at most 2x2 tiles itself from the returned code.  (Unused: counting
 // warp-aggregated with __match_any_sync at the end of the kernel measured 37.6 vs 38.5 us on C2 but 225 vs 215 us on C4.)
 template <int SamplesLog2, bool DeferSmall>
-__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, int slot, const SetupShared sh) {
+__device__ __forceinline__ U32 histogramBins(const crb_frame& f, uint4 h, S32 entry, int slot, const SetupShared sh) {
     int* s_binCount = sh.cta->binCount;
     TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
-    const CellRange t = cellRange<CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1);
-    const bool large = (t.nx > CRB_DIRECT_MAX_TILES) | (t.ny > CRB_DIRECT_MAX_TILES);
-    if (large) sh.cta->sawLarge = 1;
     if (f.directMode) {
+        const CellRange t = cellRange<CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1);
         *sh.queuedAny = 1;
-        if (large) {
-            const int k = atomicAdd(&sh.cta->numLarge, 1);
-            if (k < CRB_SETUP_THREADS) { sh.cta->largeSlot[k] = slot; return CRB_TILECODE_GENERAL; }
-            // list full (only clipped triangles can push more than one entry per thread): count it alone
+        if ((t.nx > CRB_DIRECT_MAX_TILES) | (t.ny > CRB_DIRECT_MAX_TILES)) {
+            const int k = atomicAdd(&f.atomics->numLargeTris, 1);
+            if (k < f.maxLarge) f.largeList[k] = make_int2(entry, slot);
+            else atomicOr(&f.atomics->overflow, 32);   // counted, not listed: the host grows the list and reruns the frame
+            return CRB_TILECODE_GENERAL;
         }
         if (!t.refine) {   // at most 2x2 tiles, never refined: the rectangle IS the tile set
             if (t.nx > 0) {
@@ -304,13 +300,15 @@ __device__ __noinline__ int setupClippedTriangle(const crb_frame& f, int tri, in
     }
     const float4 c0 = vertexAt(0);
     float4 cPrev = vertexAt(1);
+    int emitted = 0;   // index of the sub-triangle among the survivors = the `sub` of its queue entry (reference: BinRaster.inl:148-157)
     for (int i = 2; i < numVerts; i++) {
         float4 cCur = vertexAt(i);
         snapTriangle(f, c0, cPrev, cCur, s);
         if (prepareTriangle<SamplesLog2>(f, s, e1, e2, area) == 0) {
             uint4 h = setupTriangle<SamplesLog2, RenderModeFlags>(f, &f.triHeader[slot], &f.triData[(size_t)slot * 4], vidx, c0, cPrev, cCur, bary[0], bary[i - 1], bary[i], s, e1, e2, area);
-            histogramBins<SamplesLog2, false>(f, h, slot, sh);
+            histogramBins<SamplesLog2, false>(f, h, numSub > 1 ? tri * 8 + emitted : tri * 8 + 7, slot, sh);
             slot++;
+            emitted++;
         }
         cPrev = cCur;
     }
@@ -381,7 +379,7 @@ __device__ __forceinline__ U32 setupOneTriangle(const crb_frame& f, int tri, int
                     tm.stop(f, CRB_TIMER_SetupPleq);
                     tm.start();
                     if (micro) microRaster(f, s.p0.x, s.p0.y, s.p1.x, s.p1.y, s.p2.x, s.p2.y, zp.x, zp.y, zp.z, tri * 8 + 7, pxLoX, pxLoY, pxHiX - pxLoX + 1, pxHiY - pxLoY + 1);
-                    else tileCode = histogramBins<SamplesLog2, false>(f, h, tri, sh);
+                    else tileCode = histogramBins<SamplesLog2, false>(f, h, tri * 8 + 7, tri, sh);
                     tm.stop(f, CRB_TIMER_SetupBinning);
                 }
             }
@@ -397,19 +395,6 @@ __device__ __forceinline__ U32 setupOneTriangle(const crb_frame& f, int tri, int
     return tileCode;
 }
 
-// The large sub-triangles of a CTA (direct path), counted into the tile counters by all its threads together (their headers
-// were written by this CTA before the barrier that precedes the call).
-template <int SamplesLog2>
-__device__ __forceinline__ void countLargeSubtris(const crb_frame& f, const SetupShared sh) {
-    const int numLarge = min(sh.cta->numLarge, CRB_SETUP_THREADS);
-    for (int k = 0; k < numLarge; k++) {
-        const uint4 h = f.triHeader[sh.cta->largeSlot[k]];
-        const TriFootprint fp = triFootprint<SamplesLog2>(h.x, h.y, h.z, f);
-        forEachCellStrided<SamplesLog2, CR_TILE_LOG2>(fp, 0, 0, f.widthTiles - 1, f.heightTiles - 1, threadIdx.x, CRB_SETUP_THREADS,
-                                                      [&](S32 tx, S32 ty) { atomicAdd(&f.tileCounter[tx + ty * f.widthTiles], 1); });
-    }
-}
-
 // One thread per input triangle, one CTA per chunk (or slice of a chunk).
 template <class VertexClass, int SamplesLog2, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
@@ -419,7 +404,7 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     const SetupShared sh = {&s_queuedAny, &scratch};
     gridDepLaunchDependents();
     for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
-    if (threadIdx.x == 0) scratch.sawLarge = scratch.numLarge = s_queuedAny = 0;
+    if (threadIdx.x == 0) s_queuedAny = 0;
     __syncthreads();
     gridDepWait();   // the previous frame's kernels still read the work buffers written below
 
@@ -452,14 +437,12 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     }
     // publish this CTA's bin histogram: one column of binCountMat[bin][chunk]
     __syncthreads();
-    if (threadIdx.x == 0 && scratch.sawLarge != 0) atomicAdd(&f.atomics->numLargeTris, 1);   // CTAs with a large sub-triangle (zero / non-zero is what matters)
     if (f.directMode) {
         // One word per triangle for the scatter pass -- but only where something was queued: a batch of 32 triangles that were all
         // culled or rasterized right here (every batch of a micro-triangle frame) leaves ONE byte instead of 128 B of zeros.
         if (s_queuedAny != 0 && tri < f.numTris) f.triTileCode[tri] = tileCode;
         if ((threadIdx.x & 31) == 0 && tri < f.numTris) f.batchQueued[tri >> 5] = (uint8_t)(s_queuedAny != 0);
         if (threadIdx.x == 0 && s_queuedAny != 0) atomicAdd(&f.atomics->numQueuedCtas, 1);
-        countLargeSubtris<SamplesLog2>(f, sh);
         return;
     }
     int* col = f.binCountMat + blockIdx.x / f.ctasPerChunk;

@@ -21,7 +21,7 @@ def test_header_functions_are_exported(crb):
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), "libcrb200.so does not export %s" % n
-    assert lib.crb_abi_version() == 2
+    assert lib.crb_abi_version() == 3
 
 
 def test_builtin_pipes_resolve_by_name(crb):

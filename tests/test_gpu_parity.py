@@ -35,12 +35,20 @@ def test_setup_and_surfaces_random_soup(raster, crb, shader, flags):
     (clipped ones through the misc indirection), then surfaces bit-exact."""
     w, h = 640, 360
     v, i = crb.scenes.random_soup(20000, seed=1234 + flags, stride_floats=util.STRIDE[shader] // 4)
-    cc, cd = util.draw_cuda(raster, crb, v, i, w, h, shader, flags)
-    wb = raster.getWorkBuffers(i.shape[0])
+    g = util.draw_gold(v, i, w, h, shader, flags)
     gs = util.gold_setup(v, i, w, h, shader, flags)
-    n_single, n_multi = util.compare_setup(wb, gs, i.shape[0], flags)
-    assert n_single > 1000 and n_multi > 100
-    _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, shader, flags))
+    try:
+        # 0 = ordered sort, 3 = direct path with every record written in full, 1 = default (micro-triangles leave no header / depth row)
+        for mode in (0, 3, 1):
+            raster.setBinningMode(mode)
+            cc, cd = util.draw_cuda(raster, crb, v, i, w, h, shader, flags)
+            if mode != 1:
+                wb = raster.getWorkBuffers(i.shape[0])
+                n_single, n_multi = util.compare_setup(wb, gs, i.shape[0], flags)
+                assert n_single > 1000 and n_multi > 100
+            _check_surfaces(cc, cd, g)
+    finally:
+        raster.setBinningMode(1)
 
 
 def test_queues_are_ordered_supersets(raster, crb, gold):
@@ -175,7 +183,7 @@ def test_c2_full_size_properties(raster, crb):
     assert np.array_equal(cc, cc2) and np.array_equal(cd, cd2)           # deterministic / idempotent
     assert (cd < 0xFFFFBB3F).all()                                        # the mesh covers the whole frame
     c = raster.getCounters()
-    assert raster.lastFrameDirect()                                       # automatic mode: second frame of a small-triangle shape
+    assert raster.lastFrameDirect()                                       # automatic mode: order-independent pipe -> direct path
     assert c["overflow"] == 0 and c["numLargeTris"] == 0 and c["numBinEntries"] == 0
     g = util.draw_gold(v, i, w, h, "gouraud", 3)
     _check_surfaces(cc, cd, g, lsb=1)
@@ -388,9 +396,9 @@ def test_direct_tile_path_matches_oracle(raster, crb, shader, flags, samples_log
 
 
 def test_direct_tile_path_large_triangles_and_auto(raster, crb):
-    """Large triangles on the direct path are scattered by whole CTAs (slow but exact); automatic mode goes direct on
-    the second frame of a small-triangle shape and stays general while the shape has large triangles; pipes that
-    read dst never go direct."""
+    """Large triangles on the direct path are counted and scattered by whole CTAs (rows of tiles shared out over the threads, the
+    covered span of a row found by bisection); automatic mode takes the direct path on every frame of an order-independent pipe;
+    pipes that read dst never go direct."""
     w, h = 512, 384
     v, i = crb.scenes.grid_gouraud(160, 100)
     big = np.array([[-0.9, -0.8, 0.5, 1, 1, 0, 0, 1], [0.9, -0.7, 0.5, 1, 0, 1, 0, 1], [0.1, 0.9, 0.5, 1, 0, 0, 1, 1],
@@ -412,18 +420,30 @@ def test_direct_tile_path_large_triangles_and_auto(raster, crb):
         cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3, blend="BlendSrcOver")   # reads dst: order matters
         assert not raster.lastFrameDirect()
         _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3, blend="BlendSrcOver"), lsb=1)
+        # automatic mode: the direct path on EVERY frame of an order-independent pipe -- the first frame of a shape, frames whose
+        # triangle count changes, frames with large triangles inside (no previous-frame heuristic)
         raster.setBinningMode(1)
-        g = util.draw_gold(v, i, w, h, "gouraud", 3)
-        seen = []
-        for k in range(3):
-            cc, cd = util.draw_cuda(raster, crb, v, i, w, h, "gouraud", 3)
-            seen.append(raster.lastFrameDirect())
-            _check_surfaces(cc, cd, g, lsb=1)
-        assert seen == [False, True, True]
-        for k in range(3):   # large triangles inside: the shape stays on the general path
-            cc, cd = util.draw_cuda(raster, crb, vb, ib, w, h, "gouraud", 3)
-            assert not raster.lastFrameDirect()
-        _check_surfaces(cc, cd, util.draw_gold(vb, ib, w, h, "gouraud", 3), lsb=1)
+        for k, n in enumerate((i.shape[0], 1000, 31999, 12, i.shape[0] - 7, 0, 5000)):
+            ii = i[:n]
+            cc, cd = util.draw_cuda(raster, crb, v, ii, w, h, "gouraud", 3)
+            assert raster.lastFrameDirect(), "frame %d (%d triangles) left the direct path" % (k, n)
+            _check_surfaces(cc, cd, util.draw_gold(v, ii, w, h, "gouraud", 3), lsb=1)
+        for vv, ii in ((vb, ib), (vs, js)):
+            cc, cd = util.draw_cuda(raster, crb, vv, ii, w, h, "gouraud", 3)
+            assert raster.lastFrameDirect() and raster.getCounters()["numLargeTris"] > 0
+            _check_surfaces(cc, cd, util.draw_gold(vv, ii, w, h, "gouraud", 3), lsb=1)
+        # more large sub-triangles than the initial capacity of the global large list (16 384): overflow -> grow -> rerun, like the queues
+        vm, im = crb.scenes.random_soup(150000, seed=77, stride_floats=8, size=0.3, clip_fraction=0.0, behind_fraction=0.0)
+        cc, cd = util.draw_cuda(raster, crb, vm, im, 1024, 768, "gouraud", 3)
+        assert raster.lastFrameDirect() and raster.getCounters()["numLargeTris"] > 16384 and raster.getCounters()["overflow"] == 0
+        _check_surfaces(cc, cd, util.draw_gold(vm, im, 1024, 768, "gouraud", 3), lsb=1)
+        fresh = crb.CudaRaster(0)   # and the very first frame of a context
+        try:
+            cc, cd = util.draw_cuda(fresh, crb, vb, ib, w, h, "gouraud", 3)
+            assert fresh.lastFrameDirect()
+            _check_surfaces(cc, cd, util.draw_gold(vb, ib, w, h, "gouraud", 3), lsb=1)
+        finally:
+            fresh.close()
     finally:
         raster.setBinningMode(1)
 
