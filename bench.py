@@ -348,15 +348,24 @@ def main():
     launches_per_frame = raster.getLaunchCount()
     direct = raster.lastFrameDirect()   # automatic binning mode: small-triangle frames of an order-independent pipe skip the bin / coarse sort
 
-    # N = 1: the whole frame loop is ONE C call (crb_draw_batch_async) -- no Python between frames
-    def make_batch(r, lane_colors, lane_depth):
+    # The whole frame loop is ONE C call (crb_draw_batch_async) -- no Python between frames.  N > 1: every frame carries its
+    # composite step (peer: the frame mark behind a render that went straight into rank 0's memory; push: DMA copy of the
+    # finished frame into its slot on the library's side stream + mark); the NCCL composite keeps the Python loop.
+    def make_batch(r, lane_depth):
         frames = []
         for k in range(args.steps):
             vb, ib = copies[k % NUM_INPUT_COPIES]
-            frames.append({"color": lane_colors[k % len(lane_colors)], "depth": lane_depth, "vb": vb, "ib": ib, "num_tris": n_tris, "clear": ((0.2, 0.4, 0.8, 1.0), 1.0)})
+            fr = {"depth": lane_depth, "vb": vb, "ib": ib, "num_tris": n_tris, "clear": ((0.2, 0.4, 0.8, 1.0), 1.0)}
+            if peer:
+                fr.update(color=peer_surfaces[k % 2], signal_word=sink.mark_pointer(k), signal_value=k + 1)
+            elif push:
+                fr.update(color=colors[k % 2], push_dst=sink.slot_pointer(k), push_bytes=colors[k % 2].tensor.numel() * 4, slot=k % 2,
+                          signal_word=sink.mark_pointer(k), signal_value=k + 1)
+            else:
+                fr.update(color=colors[k % len(colors)])
+            frames.append(fr)
         return r.makeBatch(frames)
-    batch_one = make_batch(raster, colors, depth) if world == 1 else None
-
+    batch_one = make_batch(raster, depth) if (world == 1 or peer or push) else None
     def timed_region(lanes, stage_events):
         """K frames enqueued back to back, bracketed by barrier + synchronize and two events on the main stream.  Returns
         (device ms per step, max over ranks; host ms spent enqueueing one step)."""
@@ -366,8 +375,11 @@ def main():
         if lanes:
             fork_lanes()
         t0 = time.perf_counter()
-        if world == 1 and not lanes:
+        if batch_one is not None and not lanes:
+            if peer:
+                raster.setColorLayout(n_samples == 1)
             raster.drawBatch(batch_one)
+            raster.batchJoin()                  # the side-stream copies are inside the timed region
         else:
             for k in range(args.steps):
                 step(k, lanes=lanes)
@@ -475,7 +487,7 @@ def main():
             "config": config_dict(args.workload, world),
             "timing": ("N = 1: value = T / median over the K frames of (sum of the four stage intervals, CUDA events at the reference's five positions), one frame in flight"
                        if world == 1 else "N > 1: value = N * T * K / bracket (barrier + synchronize on both sides, CUDA events, max over ranks), one frame in flight per rank, stage events on every frame, composite inside"),
-            "bracket_ms_per_step": bracket_ms, "enqueue_ms_per_step": enqueue_ms, "enqueue": ("one C call for the K frames (crb_draw_batch_async)" if world == 1 else "Python loop over crb_draw_triangles_async + composite calls"),
+            "bracket_ms_per_step": bracket_ms, "enqueue_ms_per_step": enqueue_ms, "enqueue": ("one C call for the K frames, composite included (crb_draw_batch_async)" if batch_one is not None else "Python loop over crb_draw_triangles_async + NCCL gather calls"),
             "value_unbroken_chain": value_chain, "unbroken_chain_ms_per_step": chain_ms, "unbroken_chain_enqueue_ms_per_step": chain_enqueue_ms,
             "value_two_in_flight": value_two,
             "notes": {"binning": ("direct tile path: setup counts tiles -> queue allocation (timed as binRaster) -> unordered atomic scatter (timed as coarseRaster) -> fine raster keeps the (depth, index) minimum"

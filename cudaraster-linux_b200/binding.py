@@ -32,7 +32,8 @@ class BatchFrame(ctypes.Structure):
     """crb_batch_frame (include/crb200.h)."""
     _fields_ = [("color", ctypes.c_void_p), ("depth", ctypes.c_void_p), ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("numSamples", ctypes.c_int32),
                 ("vertices", ctypes.c_void_p), ("vertexBytes", ctypes.c_size_t), ("indices", ctypes.c_void_p), ("numTris", ctypes.c_int32),
-                ("clear", ctypes.c_int32), ("clearColor", ctypes.c_uint32), ("clearDepth", ctypes.c_uint32)]
+                ("clear", ctypes.c_int32), ("clearColor", ctypes.c_uint32), ("clearDepth", ctypes.c_uint32),
+                ("pushDst", ctypes.c_void_p), ("pushBytes", ctypes.c_size_t), ("signalWord", ctypes.c_void_p), ("signalValue", ctypes.c_uint32), ("surfaceSlot", ctypes.c_int32)]
 
 
 class WorkBuffers(ctypes.Structure):
@@ -91,6 +92,9 @@ def load_library():
         "crb_get_stage_timing": (i32, [vp, ctypes.POINTER(ctypes.c_double * 4), ctypes.POINTER(i32)]),
         "crb_get_stage_timing_frames": (i32, [vp, vp, i32]),
         "crb_draw_batch_async": (i32, [vp, vp, i32, vp]),
+        "crb_batch_join": (i32, [vp, vp]),
+        "crb_compute_chunk_bounds": (i32, [vp, i32, vp, i32, vp, vp]),
+        "crb_set_chunk_bounds": (i32, [vp, vp]),
         "crb_get_counters": (i32, [vp, ctypes.POINTER(Atomics)]),
         "crb_get_profiling_info": (i32, [vp, ctypes.c_char_p, ctypes.c_size_t]),
         "crb_get_launch_count": (i32, [vp]),
@@ -121,7 +125,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
-                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_stage_timing_frames", "crb_draw_batch_async", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
+                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_stage_timing_frames", "crb_draw_batch_async", "crb_batch_join", "crb_compute_chunk_bounds", "crb_set_chunk_bounds", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
                     "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_set_color_pitch", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_ipc_copy", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
@@ -375,12 +379,35 @@ class CudaRaster:
                 b.clear = 1
                 b.clearColor = self.lib.crb_pack_abgr(*[float(c) for c in clear[0]])
                 b.clearDepth = self.lib.crb_encode_clear_depth(float(clear[1]))
+            if fr.get("push_dst"):      # composite: copy the finished colour surface into a peer frame slot (side stream)
+                b.pushDst, b.pushBytes, b.surfaceSlot = int(fr["push_dst"]), int(fr["push_bytes"]), int(fr.get("slot", 0))
+            if fr.get("signal_word"):   # frame mark for the consumer
+                b.signalWord, b.signalValue = int(fr["signal_word"]), int(fr["signal_value"])
         return arr
 
     def drawBatch(self, batch, stream=None):
         """crb_draw_batch_async: every frame of `batch` (makeBatch) enqueued by ONE C call; call finish()."""
         s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         self._check(self.lib.crb_draw_batch_async(self.ctx, ctypes.cast(batch, ctypes.c_void_p), len(batch), ctypes.c_void_p(s)))
+
+    def computeChunkBounds(self, vb, ib, num_tris, vertex_stride, stream=None):
+        """Per-chunk clip-space bounds of a mesh for the sort-first geometry cull (crb_compute_chunk_bounds): a float32 CUDA tensor
+        [ceil(num_tris / 256), 4]; make it once per mesh, pass it to setChunkBounds after setVertexBuffer / setIndexBuffer."""
+        out = self.torch.empty(((int(num_tris) + 255) // 256, 4), dtype=self.torch.float32, device=vb.device)
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = self.lib.crb_compute_chunk_bounds(vb.data_ptr(), int(vertex_stride), ib.data_ptr(), int(num_tris), out.data_ptr(), ctypes.c_void_p(s))
+        if rc != 0:
+            raise CrbError("CudaRaster: crb_compute_chunk_bounds failed with status %d" % rc)
+        return out
+
+    def setChunkBounds(self, bounds):
+        self._keep["bounds"] = bounds
+        self._check(self.lib.crb_set_chunk_bounds(self.ctx, None if bounds is None else bounds.data_ptr()))
+
+    def batchJoin(self, stream=None):
+        """Makes the stream wait for the composite copies of drawBatch (crb_batch_join)."""
+        s = self.torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(self.lib.crb_batch_join(self.ctx, ctypes.c_void_p(s)))
 
     def getProfilingInfo(self):
         buf = ctypes.create_string_buffer(2048)

@@ -18,6 +18,7 @@
 #include "../../include/cudaraster/cuda/PrivateDefs.hpp"
 #include "../../include/cudaraster/cuda/Util.cuh"
 
+extern "C" int crb_ipc_signal(void* d_word, uint32_t value, void* stream);
 extern "C" int crb_bin_launches(const crb_frame* f);
 extern "C" int crb_coarse_launches(const crb_frame* f);
 extern "C" int crb_launch_direct_alloc(const crb_frame* f, void* stream);
@@ -66,6 +67,7 @@ struct crb_ctx {
     size_t vertexBytes = 0;
     const int32_t* indices = nullptr;
     int numTris = 0;
+    const float* chunkBounds = nullptr;  // crb_set_chunk_bounds: belongs to the current vertex / index buffers
     bool verticesSet = false, indicesSet = false;  // an EMPTY buffer is still a buffer (CudaRaster.cpp:220-233)
     bool hasPipe = false;
     crb_pipe_desc pipe{};
@@ -99,7 +101,9 @@ struct crb_ctx {
     bool microOff = false;               // crb_set_binning_mode(3)
     bool microEnabled = true;            // CRB_MICRO=0 keeps small triangles on the tile queues (A/B measurements)
     DevBuf atomics;
-    crb_atomics* hostAtomics = nullptr;  // pinned; slot 0 = synchronous draws, slots 1.. = ring of asynchronous frames
+    crb_atomics* hostAtomics = nullptr;  // pinned + mapped; slot 0 = synchronous draws, slots 1.. = ring of asynchronous frames
+    crb_atomics* hostAtomicsDev = nullptr;   // the same memory as the device sees it: the fine raster kernel stores the frame's counters there itself
+    int counterSlot = 0;                 // slot the next frame reports into
     int pending = 0;                     // asynchronous frames not yet checked by crb_finish
     DevBuf hostVerts, hostIdx;           // device staging for crb_draw_triangles_host
 
@@ -127,6 +131,14 @@ struct crb_ctx {
         cudaEvent_t uploaded[2] = {}, rendered[2] = {}, downloaded = nullptr;
         long long frames = 0;
     } hp;
+
+    // crb_draw_batch_async: composite copies (frames pushed into a peer GPU's frame slots) on a side stream
+    struct Composite {
+        bool init = false, any = false;
+        cudaStream_t side = nullptr;
+        cudaEvent_t rendered[4] = {}, pushed[4] = {}, last = nullptr;
+        bool pushedValid[4] = {false, false, false, false};
+    } comp;
 
     cudaEvent_t ev[5] = {};
     crb_frame frame{};
@@ -203,6 +215,7 @@ int prepareFrame(crb_ctx* c) {
         if (c->subX0 + c->width > px0 + pw || c->subY0 + c->height > py0 + ph)
             return setError(c, CRB_ERR_INVALID, "CudaRaster: a sort-first window must lie inside one %dx%d cell of the frame!", cellW, cellH);
         f.windowed = 1;
+        f.chunkBounds = (const float4*)c->chunkBounds;
         f.fullWidth = c->fullWidth;
         f.fullHeight = c->fullHeight;
         f.viewportWidth = pw;
@@ -319,6 +332,7 @@ int prepareFrame(crb_ctx* c) {
     f.largeList = (int2*)c->largeList.ptr;
     f.atomics = (crb_atomics*)c->atomics.ptr + c->atomicsParity;
     f.nextAtomics = (crb_atomics*)c->atomics.ptr + (c->atomicsParity ^ 1);
+    f.hostCounters = c->hostAtomicsDev + c->counterSlot;
     if (oldBinMat != c->binCountMat.ptr || oldTileMat != c->tileCountMat.ptr || c->lastNumBins != f.numBins || c->lastMatPitch != f.matPitch ||
         c->lastNumChunks != f.numChunks || c->lastCtasPerChunk != f.ctasPerChunk)
         c->needReset = true;
@@ -414,7 +428,8 @@ int crb_create(int device, crb_ctx** out) {
     if (micro && micro[0] == '0') c->microEnabled = false;
     const char* dbg = getenv("CRB_DEBUG_FLAGS");
     c->debugFlags = dbg ? atoi(dbg) : 0;
-    if (cudaMallocHost((void**)&c->hostAtomics, sizeof(crb_atomics) * (1 + kAsyncRing)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    if (cudaHostAlloc((void**)&c->hostAtomics, sizeof(crb_atomics) * (1 + kAsyncRing), cudaHostAllocMapped) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
+    if (cudaHostGetDevicePointer((void**)&c->hostAtomicsDev, c->hostAtomics, 0) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
     std::memset(c->hostAtomics, 0, sizeof(crb_atomics) * (1 + kAsyncRing));
     *out = c;
     return CRB_OK;
@@ -439,6 +454,11 @@ int crb_destroy(crb_ctx* c) {
             c->hp.idx[i].release();
         }
         cudaEventDestroy(c->hp.downloaded);
+    }
+    if (c->comp.init) {
+        cudaStreamDestroy(c->comp.side);
+        for (int k = 0; k < 4; k++) { cudaEventDestroy(c->comp.rendered[k]); cudaEventDestroy(c->comp.pushed[k]); }
+        cudaEventDestroy(c->comp.last);
     }
     if (c->hostAtomics) cudaFreeHost(c->hostAtomics);
     for (int i = 0; i < 5; i++)
@@ -547,6 +567,7 @@ int crb_set_pixel_pipe_by_name(crb_ctx* c, void* module, const char* name) {
 
 int crb_set_vertex_buffer(crb_ctx* c, const void* d_vertices, size_t bytes) {
     if (!c) return CRB_ERR_INVALID;
+    if (c->vertices != d_vertices) c->chunkBounds = nullptr;
     c->vertices = d_vertices;
     c->vertexBytes = bytes;
     c->verticesSet = d_vertices != nullptr || bytes == 0;
@@ -556,9 +577,17 @@ int crb_set_vertex_buffer(crb_ctx* c, const void* d_vertices, size_t bytes) {
 int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
     if (!c) return CRB_ERR_INVALID;
     if (numTris < 0) return setError(c, CRB_ERR_INVALID, "CudaRaster: negative triangle count!");
+    if (c->indices != (const int32_t*)d_indices || c->numTris != numTris) c->chunkBounds = nullptr;
     c->indices = (const int32_t*)d_indices;
     c->numTris = numTris;
     c->indicesSet = d_indices != nullptr || numTris == 0;
+    return CRB_OK;
+}
+
+int crb_set_chunk_bounds(crb_ctx* c, const float* d_bounds) {
+    if (!c) return CRB_ERR_INVALID;
+    static_assert(CRB_CHUNK_BOUNDS_TRIS == CRB_SETUP_THREADS, "one bounds record per setup CTA");
+    c->chunkBounds = d_bounds;
     return CRB_OK;
 }
 
@@ -618,12 +647,13 @@ int crb_draw_triangles(crb_ctx* c, void* stream) {
     for (int attempt = 0;; attempt++) {
         if (c->maxSubtris > CR_MAXSUBTRIS_SIZE) return setError(c, CRB_ERR_LIMIT, "CudaRaster: CR_MAXSUBTRIS_SIZE exceeded!");
         c->maxItems = c->maxBinEntries / CRB_ITEM_ENTRIES + CR_MAXBINS_SQR + 1;
+        c->counterSlot = 0;
         rc = prepareFrame(c);
         if (rc != CRB_OK) return rc;
         rc = launchStages(c, s, c->ev);
         if (rc != CRB_OK) return rc;
-        // counters back to the host (reference: CudaRaster.cpp:326 -- one blocking round trip per frame)
-        CRB_CUDA(c, cudaMemcpyAsync(c->hostAtomics, c->frame.atomics, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
+        // counters back on the host (reference: CudaRaster.cpp:326 -- one blocking round trip per frame): the fine raster kernel
+        // stored them into the mapped block itself, no copy is enqueued
         CRB_CUDA(c, cudaStreamSynchronize(s));
         crb_atomics a = *c->hostAtomics;
         a.numSubtris += numTris;
@@ -652,6 +682,7 @@ int crb_finish(crb_ctx* c, void* stream) {
         for (int k = 0; k < i && !seen; k++) seen = c->pendingFrame[k].stream == c->pendingFrame[i].stream;
         if (!seen) CRB_CUDA(c, cudaStreamSynchronize(c->pendingFrame[i].stream));
     }
+    if (c->comp.init && c->comp.any) CRB_CUDA(c, cudaStreamSynchronize(c->comp.side));
     int overflowed = 0, firstBad = -1;
     for (int i = 0; i < c->pending; i++) {
         if (c->stageTiming) {
@@ -710,11 +741,11 @@ int crb_draw_triangles_async(crb_ctx* c, void* stream) {
     if (c->maxSubtris > CR_MAXSUBTRIS_SIZE) return setError(c, CRB_ERR_LIMIT, "CudaRaster: CR_MAXSUBTRIS_SIZE exceeded!");
     c->maxItems = c->maxBinEntries / CRB_ITEM_ENTRIES + CR_MAXBINS_SQR + 1;
     c->launchCount = 0;
+    c->counterSlot = 1 + c->pending;   // the frame's fine raster kernel stores its counters there (mapped host memory): no copy between frames
     rc = prepareFrame(c);
     if (rc != CRB_OK) return rc;
     rc = launchStages(c, s, c->stageTiming ? c->ringEv[c->pending] : nullptr);
     if (rc != CRB_OK) return rc;
-    CRB_CUDA(c, cudaMemcpyAsync(&c->hostAtomics[1 + c->pending], c->frame.atomics, sizeof(crb_atomics), cudaMemcpyDeviceToHost, s));
     crb_ctx::PendingFrame& pf = c->pendingFrame[c->pending];
     pf.numTris = numTris; pf.stream = s; pf.hadClear = c->deferredClear; pf.clearColor = c->clearColor; pf.clearDepth = c->clearDepth;
     c->pending++;
@@ -837,16 +868,53 @@ int crb_get_stage_timing_frames(crb_ctx* c, float* outMs, int maxFrames) {
 
 int crb_draw_batch_async(crb_ctx* c, const crb_batch_frame* frames, int numFrames, void* stream) {
     if (!c || numFrames < 0 || (numFrames > 0 && !frames)) return CRB_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    crb_ctx::Composite& cp = c->comp;
     for (int i = 0; i < numFrames; i++) {
         const crb_batch_frame& b = frames[i];
         int rc = CRB_OK;
+        const int slot = b.surfaceSlot & 3;
+        if (b.pushDst) {
+            CRB_CUDA(c, cudaSetDevice(c->device));
+            if (!cp.init) {
+                CRB_CUDA(c, cudaStreamCreateWithFlags(&cp.side, cudaStreamNonBlocking));
+                for (int k = 0; k < 4; k++) {
+                    CRB_CUDA(c, cudaEventCreateWithFlags(&cp.rendered[k], cudaEventDisableTiming));
+                    CRB_CUDA(c, cudaEventCreateWithFlags(&cp.pushed[k], cudaEventDisableTiming));
+                }
+                CRB_CUDA(c, cudaEventCreateWithFlags(&cp.last, cudaEventDisableTiming));
+                cp.init = true;
+            }
+            if (cp.pushedValid[slot]) CRB_CUDA(c, cudaStreamWaitEvent(s, cp.pushed[slot], 0));   // the copy that last read this local surface
+        }
         if (b.color || b.depth) rc = crb_set_surfaces(c, b.color, b.depth, b.width, b.height, b.numSamples);
         if (rc == CRB_OK && b.vertices) rc = crb_set_vertex_buffer(c, b.vertices, b.vertexBytes);
         if (rc == CRB_OK && b.indices) rc = crb_set_index_buffer(c, b.indices, b.numTris);
         if (rc == CRB_OK && b.clear) rc = crb_deferred_clear(c, b.clearColor, b.clearDepth);
         if (rc == CRB_OK) rc = crb_draw_triangles_async(c, stream);
         if (rc != CRB_OK) return rc;
+        if (b.pushDst) {
+            CRB_CUDA(c, cudaEventRecord(cp.rendered[slot], s));
+            CRB_CUDA(c, cudaStreamWaitEvent(cp.side, cp.rendered[slot], 0));
+            CRB_CUDA(c, cudaMemcpyAsync(b.pushDst, c->color, b.pushBytes, cudaMemcpyDeviceToDevice, cp.side));
+            if (b.signalWord && crb_ipc_signal(b.signalWord, b.signalValue, cp.side) != CRB_OK) return setError(c, CRB_ERR_CUDA, "CudaRaster: frame mark failed");
+            CRB_CUDA(c, cudaEventRecord(cp.pushed[slot], cp.side));
+            cp.pushedValid[slot] = true;
+            cp.any = true;
+        } else if (b.signalWord) {
+            if (crb_ipc_signal(b.signalWord, b.signalValue, s) != CRB_OK) return setError(c, CRB_ERR_CUDA, "CudaRaster: frame mark failed");
+        }
     }
+    return CRB_OK;
+}
+
+int crb_batch_join(crb_ctx* c, void* stream) {
+    if (!c) return CRB_ERR_INVALID;
+    crb_ctx::Composite& cp = c->comp;
+    if (!cp.init || !cp.any) return CRB_OK;
+    CRB_CUDA(c, cudaSetDevice(c->device));
+    CRB_CUDA(c, cudaEventRecord(cp.last, cp.side));
+    CRB_CUDA(c, cudaStreamWaitEvent((cudaStream_t)stream, cp.last, 0));
     return CRB_OK;
 }
 

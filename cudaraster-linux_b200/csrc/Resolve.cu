@@ -88,6 +88,46 @@ __global__ void ipcSignalKernel(volatile uint32_t* word, uint32_t value) {
 }
 }  // namespace
 
+// ---- sort-first geometry cull: clip-space bounds per chunk of CRB_CHUNK_BOUNDS_TRIS consecutive triangles ------------------------
+// One CTA per chunk, one thread per triangle: min / max of x/w and y/w over the chunk's vertices (block reduction); a chunk with
+// a vertex at w <= 0 (its projection is unbounded) gets the whole plane.
+__global__ void __launch_bounds__(256) chunkBoundsKernel(const float4* __restrict__ verts, int stride4, const int32_t* __restrict__ idx, int numTris, float4* __restrict__ bounds) {
+    __shared__ float s_red[4][8];
+    const int tri = blockIdx.x * 256 + threadIdx.x;
+    const float inf = __int_as_float(0x7F800000);
+    float lox = inf, loy = inf, hix = -inf, hiy = -inf;
+    if (tri < numTris) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float4 v = __ldg(&verts[(size_t)__ldg(&idx[tri * 3 + k]) * stride4]);
+            if (v.w > 0.0f && v.x == v.x && v.y == v.y) {
+                const float x = v.x / v.w, y = v.y / v.w;
+                lox = fminf(lox, x); hix = fmaxf(hix, x); loy = fminf(loy, y); hiy = fmaxf(hiy, y);
+            } else {
+                lox = loy = -inf; hix = hiy = inf;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(0xFFFFFFFFu, lox, d)); loy = fminf(loy, __shfl_xor_sync(0xFFFFFFFFu, loy, d));
+        hix = fmaxf(hix, __shfl_xor_sync(0xFFFFFFFFu, hix, d)); hiy = fmaxf(hiy, __shfl_xor_sync(0xFFFFFFFFu, hiy, d));
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = lox; s_red[1][threadIdx.x >> 5] = loy; s_red[2][threadIdx.x >> 5] = hix; s_red[3][threadIdx.x >> 5] = hiy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { lox = fminf(lox, s_red[0][w]); loy = fminf(loy, s_red[1][w]); hix = fmaxf(hix, s_red[2][w]); hiy = fmaxf(hiy, s_red[3][w]); }
+        bounds[blockIdx.x] = make_float4(lox, loy, hix, hiy);
+    }
+}
+
+extern "C" int crb_compute_chunk_bounds(const void* d_vertices, int vertexStride, const int32_t* d_indices, int numTris, float* d_bounds, void* stream) {
+    if (numTris < 0 || vertexStride < 16 || (vertexStride & 15) || (numTris > 0 && (!d_vertices || !d_indices || !d_bounds))) return CRB_ERR_INVALID;
+    if (numTris == 0) return CRB_OK;
+    chunkBoundsKernel<<<(numTris + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)d_vertices, vertexStride / 16, d_indices, numTris, (float4*)d_bounds);
+    return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}
+
 extern "C" int crb_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[CRB_IPC_HANDLE_BYTES]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == CRB_IPC_HANDLE_BYTES, "handle size");
     if (!d_ptr || !handle || bytes == 0) return CRB_ERR_INVALID;

@@ -185,6 +185,11 @@ class PeerFrameSink:
         r = self.rank if rank is None else rank
         return self.base + ((k % self.depth) * self.world + r) * self.frame_bytes
 
+    def mark_pointer(self, k, rank=None):
+        """Device address of the 32-bit frame mark of (slot k % depth, rank)."""
+        r = self.rank if rank is None else rank
+        return self.base + self.flag_ofs + 4 * ((k % self.depth) * self.world + r)
+
     def surface(self, k, size, num_samples=1):
         """The colour surface rank `self.rank` renders frame k into (memory of rank `dst`)."""
         from .binding import CudaSurface

@@ -131,6 +131,18 @@ int crb_set_index_buffer(crb_ctx* ctx, const void* d_indices, int numTris);
  * Passing fullWidth = 0 restores the plain single viewport. */
 int crb_set_subviewport(crb_ctx* ctx, int fullWidth, int fullHeight, int x0, int y0);
 
+/* Sort-first geometry cull (new).  Every rank of a sort-first split sets up ALL triangles of the mesh and drops those outside
+ * its window one by one; with per-chunk bounds a rank skips whole chunks -- CRB_CHUNK_BOUNDS_TRIS consecutive input
+ * triangles -- whose clip-space bounding box lies outside the window, without touching their vertices.  The bounds depend
+ * on the mesh only (not on the window): crb_compute_chunk_bounds makes them once per mesh (device, stream ordered) --
+ * d_bounds[chunk] = {min x/w, min y/w, max x/w, max y/w}, the whole plane for a chunk with a vertex at w <= 0 --, and
+ * crb_set_chunk_bounds hands them to a context for the CURRENT vertex / index buffers (setting either buffer forgets them).
+ * A skipped chunk is exactly a chunk all of whose triangles the per-triangle window test would have culled: frames and
+ * setup records are unchanged. */
+#define CRB_CHUNK_BOUNDS_TRIS 256
+int crb_compute_chunk_bounds(const void* d_vertices, int vertexStride, const int32_t* d_indices, int numTris, float* d_bounds, void* stream);
+int crb_set_chunk_bounds(crb_ctx* ctx, const float* d_bounds);
+
 /* Binning strategy (new).  The general path is the stable two-level sort (bin raster + coarse raster) that keeps
  * every tile queue in submission order, like the reference.  The DIRECT path skips both levels: triangle setup counts
  * the tiles of every triangle, one kernel allocates the tile queues and one scatters the entries with atomics, in
@@ -211,8 +223,22 @@ typedef struct crb_batch_frame {
     int32_t numTris;
     int32_t clear;               /* != 0: crb_deferred_clear(clearColor, clearDepth) before the draw */
     uint32_t clearColor, clearDepth;
+    /* Composite step of a multi-GPU frame, enqueued with the frame so that a frame costs ONE host call:
+     *   pushDst != NULL   the finished colour surface (pushBytes bytes) is copied into pushDst -- a frame slot in the display
+     *                     GPU's memory (crb_ipc_open) -- by the DMA engines on an internal side stream, overlapped with the next
+     *                     frame; `surfaceSlot` (0..3) names the local colour surface the frame renders into: the render waits
+     *                     until the previous copy out of that surface has finished;
+     *   signalWord != NULL  signalValue is stored there after the frame (after its copy, if any): the consumer's frame mark. */
+    void* pushDst;
+    size_t pushBytes;
+    void* signalWord;
+    uint32_t signalValue;
+    int32_t surfaceSlot;
 } crb_batch_frame;
 int crb_draw_batch_async(crb_ctx* ctx, const crb_batch_frame* frames, int numFrames, void* stream);
+/* Makes `stream` wait for the copies crb_draw_batch_async put on the side stream (so that an event recorded on `stream`
+ * afterwards covers the composite); crb_finish waits for them as well. */
+int crb_batch_join(crb_ctx* ctx, void* stream);
 /* g_crAtomics read-back (CudaRaster.cpp:326). */
 int crb_get_counters(crb_ctx* ctx, crb_atomics* out);
 /* CudaRaster::getProfilingInfo (CudaRaster.cpp:367-497): the ProfilingMode_Default report, or -- for a pipe compiled with

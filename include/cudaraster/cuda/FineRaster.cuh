@@ -35,7 +35,10 @@ __device__ __forceinline__ void finishFrameState(const crb_frame& f) {
     // An overflowed frame leaves the self-cleaning scratch state dirty (its kernels return early), so the frames enqueued behind
     // it must not run on it: the flag is handed on (bit 4 = "an earlier frame of the batch overflowed") and every later frame
     // early-outs until the host has seen it (crb_finish) and reset the state.
+    // the frame's counters are final by now (every other kernel of the frame has ended): the host's copy is stored from here --
+    // a copy enqueued between two frames would hold the next frame's first kernel back by a copy-engine round trip
     if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(crb_atomics) / sizeof(int))) {
+        reinterpret_cast<volatile int*>(f.hostCounters)[threadIdx.x] = reinterpret_cast<const int*>(f.atomics)[threadIdx.x];
         const int sticky = (threadIdx.x == (int)(offsetof(crb_atomics, overflow) / sizeof(int)) && f.atomics->overflow != 0) ? 16 : 0;
         reinterpret_cast<int*>(f.nextAtomics)[threadIdx.x] = sticky;
     }

@@ -80,6 +80,7 @@ struct crb_frame {
     int32_t originX, originY;                // header subpixel coordinate + origin = subpixel position relative to the surface corner
     float clipLoX, clipHiX, clipLoY, clipHiY;   // parent viewport in full-frame NDC: the window triangles are clipped against
     float cullLoX, cullHiX, cullLoY, cullHiY;   // surface (scissor) in full-frame NDC: triangles wholly outside are culled early
+    const float4* chunkBounds;               // sort-first window: {min x/w, min y/w, max x/w, max y/w} per CRB_SETUP_THREADS input triangles, or nullptr
 
     int32_t deferredClear;
     uint32_t clearColor, clearDepth;
@@ -141,6 +142,7 @@ struct crb_frame {
 
     crb_atomics* atomics;         // counters of THIS frame (zero when the frame starts)
     crb_atomics* nextAtomics;     // counters of the next frame: zeroed by this frame's fine raster kernel
+    crb_atomics* hostCounters;    // mapped host memory: the fine raster kernel leaves a copy of this frame's counters there (no D2H copy on the stream)
     int32_t numSMs;
     int32_t debugFlags;           // CRB_DEBUG_FLAGS environment variable; bit 0: fine raster always takes the general coverage path
     int32_t chainLaunches;        // 1 = kernels are launched with programmatic stream serialization (see Util.cuh)

@@ -416,7 +416,20 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
     tmTotal.start();
     U32 tileCode = 0;
     U32 prof = 0;   // ProfilingMode_Counters: bit 0 triangle, 1 viewport cull, 2 backface cull, 3 between-pixels cull, 4 clipped, 5 survived
-    if (tri < f.numTris) {
+    // Sort-first window with per-chunk bounds (crb_set_chunk_bounds): a chunk whose clip-space box lies outside the window --
+    // by more than the rounding of the per-triangle test below, so that every one of its triangles WOULD be culled there --
+    // is dropped without reading a vertex.
+    bool chunkCulled = false;
+    if (f.windowed && f.chunkBounds != nullptr) {
+        const float4 b = __ldg(&f.chunkBounds[blockIdx.x]);
+        const F32 eps = 1.0e-5f;
+        chunkCulled = (b.x > f.cullHiX + eps * (1.0f + fabsf(f.cullHiX))) | (b.z < f.cullLoX - eps * (1.0f + fabsf(f.cullLoX))) |
+                      (b.y > f.cullHiY + eps * (1.0f + fabsf(f.cullHiY))) | (b.w < f.cullLoY - eps * (1.0f + fabsf(f.cullLoY)));
+    }
+    if (tri < f.numTris && chunkCulled) {
+        f.triSubtris[tri] = 0;
+        prof = 1 | 2;
+    } else if (tri < f.numTris) {
         prof = 1;
         tm.start();
         const int3 vidx = make_int3(__ldg(&f.indexBuffer[tri * 3 + 0]), __ldg(&f.indexBuffer[tri * 3 + 1]), __ldg(&f.indexBuffer[tri * 3 + 2]));

@@ -695,3 +695,45 @@ def test_profiling_mode_timers(raster, crb):
     vals = [float(x) for x in re.findall(r"([0-9.]+)%", info)]
     assert len(vals) == 10 and all(0.0 <= x <= 100.0 for x in vals)
     assert sum(vals[:5]) > 20.0 and sum(vals[5:]) > 20.0 and sum(vals[:5]) <= 100.5 and sum(vals[5:]) <= 100.5
+
+
+def test_sort_first_chunk_bounds_cull(raster, crb):
+    """crb_set_chunk_bounds: a sort-first window skips the chunks of 256 triangles whose clip-space box lies outside it.  Frames,
+    triSubtris and the surviving records must equal the render without bounds (and the oracle's), on the ordered and the direct
+    path; most chunks of a screen-ordered mesh are skipped, and a soup (every chunk spans the screen) loses none."""
+    import torch
+    fw, fh = 1024, 768
+    for name, (v, i) in (("grid", crb.scenes.grid_gouraud(300, 200)), ("soup", crb.scenes.random_soup(20000, seed=3, stride_floats=8, size=0.1))):
+        vb, ib = torch.from_numpy(v).cuda(), torch.from_numpy(i).cuda()
+        bounds = raster.computeChunkBounds(vb, ib, i.shape[0], 32)
+        b = bounds.cpu().numpy()
+        assert b.shape == ((i.shape[0] + 255) // 256, 4)
+        if name == "grid":
+            assert np.isfinite(b).all() and ((b[:, 3] - b[:, 1]) < 0.2).mean() > 0.9      # chunks are thin horizontal strips of the mesh
+        try:
+            for mode in (0, 3, 1):
+                raster.setBinningMode(mode)
+                for (x0, y0, w, h) in [(0, 0, 512, 384), (512, 384, 512, 384), (256, 192, 512, 384)]:
+                    out = {}
+                    for use in (False, True):
+                        color = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8)
+                        depth = crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_DEPTH32)
+                        raster.setSurfaces(color, depth)
+                        raster.setPixelPipe(None, crb.pipe_name("gouraud", 0, 3))
+                        raster.setVertexBuffer(vb, 0)
+                        raster.setIndexBuffer(ib, 0, i.shape[0])
+                        raster.setChunkBounds(bounds if use else None)
+                        raster.setSubViewport(fw, fh, x0, y0)
+                        raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
+                        raster.drawTriangles()
+                        out[use] = (color.numpy(), depth.numpy(), raster.getWorkBuffers(i.shape[0])["triSubtris"])
+                    assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
+                    assert np.array_equal(out[True][2], out[False][2])
+                    g = util.draw_gold(v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0))
+                    _check_surfaces(out[True][0], out[True][1], g, lsb=1)
+                    gs = util.gold_setup(v, i, w, h, "gouraud", 3, sub=(fw, fh, x0, y0))
+                    assert np.array_equal(out[True][2], gs["triSubtris"])
+        finally:
+            raster.setChunkBounds(None)
+            raster.setSubViewport(0, 0, 0, 0)
+            raster.setBinningMode(1)
