@@ -401,12 +401,18 @@ def main():
     clocks = sampler.result()
     live = raster.getStageTiming()
     per_frame = raster.getStageTimingFrames()[-args.steps:]
-    frame_ms = float(np.median(per_frame.sum(axis=1))) if len(per_frame) else bracket_ms
+    # t_frame of THIS rank: the four stage intervals of a frame; with a DMA composite on the side stream (push) the frame
+    # pipeline has two stages -- render, copy of the previous frame -- and runs at the slower one
+    stage_sum_ms = float(np.median(per_frame[:, :4].sum(axis=1))) if len(per_frame) else bracket_ms
+    composite_ms = float(np.median(per_frame[:, 4])) if len(per_frame) else 0.0
+    frame_ms = max(stage_sum_ms, composite_ms)
     raster.setStageTiming(False)
-    if world == 1:
-        ms_per_step = frame_ms                                   # t_frame = sum of the four stage intervals, median over the K frames
+    if world > 1:
+        t = torch.tensor([frame_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item())                            # the slowest rank's t_frame
     else:
-        ms_per_step = bracket_ms                                 # max over ranks, composite included
+        ms_per_step = frame_ms                                   # t_frame = sum of the four stage intervals, median over the K frames
     value = world * n_tris / (ms_per_step * 1e-3) / 1e6
     # ---- (2) the same K frames as one unbroken kernel chain (no stage events), and (3) alternating between two contexts
     chain_ms, chain_enqueue_ms = timed_region(lanes=False, stage_events=False)
@@ -485,8 +491,11 @@ def main():
             "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "frames_per_s": world * 1e3 / ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
             "config": config_dict(args.workload, world),
-            "timing": ("N = 1: value = T / median over the K frames of (sum of the four stage intervals, CUDA events at the reference's five positions), one frame in flight"
-                       if world == 1 else "N > 1: value = N * T * K / bracket (barrier + synchronize on both sides, CUDA events, max over ranks), one frame in flight per rank, stage events on every frame, composite inside"),
+            "timing": "value = N * T / t_frame; t_frame = median over the K frames of the sum of the four stage intervals (CUDA events at the reference's five positions, SURVEY.md 8d), one frame in flight per rank"
+                      + ("" if world == 1 else ", max over ranks; composite: " + ("inside the fine raster interval (the frame is rendered into rank 0's memory) + a frame mark" if peer else
+                         "DMA copy of the finished frame on a side stream, overlapped with the next frame -- a rank's t_frame is the slower of its render (four intervals) and its copy (5th interval, composite_ms)" if push else
+                         "NCCL gather on a side stream (not in t_frame: see bracket_ms_per_step)")),
+            "composite_ms": composite_ms, "stage_sum_ms": stage_sum_ms,
             "bracket_ms_per_step": bracket_ms, "enqueue_ms_per_step": enqueue_ms, "enqueue": ("one C call for the K frames, composite included (crb_draw_batch_async)" if batch_one is not None else "Python loop over crb_draw_triangles_async + NCCL gather calls"),
             "value_unbroken_chain": value_chain, "unbroken_chain_ms_per_step": chain_ms, "unbroken_chain_enqueue_ms_per_step": chain_enqueue_ms,
             "value_two_in_flight": value_two,

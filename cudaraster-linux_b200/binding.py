@@ -95,6 +95,7 @@ def load_library():
         "crb_batch_join": (i32, [vp, vp]),
         "crb_compute_chunk_bounds": (i32, [vp, i32, vp, i32, vp, vp]),
         "crb_set_chunk_bounds": (i32, [vp, vp]),
+        "crb_split_frame": (i32, [i32, i32, i32, vp, i32]),
         "crb_get_counters": (i32, [vp, ctypes.POINTER(Atomics)]),
         "crb_get_profiling_info": (i32, [vp, ctypes.c_char_p, ctypes.c_size_t]),
         "crb_get_launch_count": (i32, [vp]),
@@ -125,7 +126,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_error", "crb_set_surfaces", "crb_deferred_clear", "crb_pack_abgr",
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
-                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_stage_timing_frames", "crb_draw_batch_async", "crb_batch_join", "crb_compute_chunk_bounds", "crb_set_chunk_bounds", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
+                    "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_stage_timing_frames", "crb_draw_batch_async", "crb_batch_join", "crb_compute_chunk_bounds", "crb_set_chunk_bounds", "crb_split_frame", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
                     "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_set_color_pitch", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_ipc_copy", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
@@ -355,8 +356,9 @@ class CudaRaster:
         return {"triangleSetup": out[0], "binRaster": out[1], "coarseRaster": out[2], "fineRaster": out[3], "frames": n.value}
 
     def getStageTimingFrames(self, max_frames=4096):
-        """[frames][4] float32 array: the four stage intervals (ms) of every asynchronous frame finished since setStageTiming(True)."""
-        out = np.zeros((max_frames, 4), np.float32)
+        """[frames][5] float32 array: the four stage intervals (ms) and the duration of the composite copy (0 without one) of every
+        asynchronous frame finished since setStageTiming(True)."""
+        out = np.zeros((max_frames, 5), np.float32)
         n = self.lib.crb_get_stage_timing_frames(self.ctx, out.ctypes.data, max_frames)
         return out[:n]
 

@@ -117,10 +117,11 @@ struct crb_ctx {
     bool chainLaunches = true;           // programmatic dependent launch between the kernels of a frame (CRB_NO_PDL=1 turns it off)
     bool stageTiming = false;            // asynchronous frames: record the five stage events too (crb_set_stage_timing)
     static constexpr int kTimingRing = 64;
-    cudaEvent_t ringEv[kTimingRing][5] = {};
+    cudaEvent_t ringEv[kTimingRing][7] = {};   // five stage events + start / end of the frame's composite copy (side stream)
+    bool ringComp[kTimingRing] = {};
     double stageSumMs[4] = {0, 0, 0, 0};
     int stageFrames = 0;
-    std::vector<float> stageFrameMs;     // 4 intervals per finished frame since crb_set_stage_timing (crb_get_stage_timing_frames)
+    std::vector<float> stageFrameMs;     // 5 intervals per finished frame since crb_set_stage_timing: four stages + composite (crb_get_stage_timing_frames)
 
     // crb_draw_triangles_host_async: upload / render / download of consecutive frames overlap
     struct HostPipeline {
@@ -417,7 +418,7 @@ int crb_create(int device, crb_ctx** out) {
     for (int i = 0; i < 5; i++)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
     for (int i = 0; i < crb_ctx::kTimingRing; i++)
-        for (int k = 0; k < 5; k++)
+        for (int k = 0; k < 7; k++)
             if (cudaEventCreate(&c->ringEv[i][k]) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
     if (c->atomics.reserve(2 * sizeof(crb_atomics)) != cudaSuccess) { delete c; return CRB_ERR_CUDA; }
     const char* noPdl = getenv("CRB_NO_PDL");
@@ -464,7 +465,7 @@ int crb_destroy(crb_ctx* c) {
     for (int i = 0; i < 5; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < crb_ctx::kTimingRing; i++)
-        for (int k = 0; k < 5; k++)
+        for (int k = 0; k < 7; k++)
             if (c->ringEv[i][k]) cudaEventDestroy(c->ringEv[i][k]);
     delete c;
     return CRB_OK;
@@ -584,6 +585,33 @@ int crb_set_index_buffer(crb_ctx* c, const void* d_indices, int numTris) {
     return CRB_OK;
 }
 
+int crb_split_frame(int fullWidth, int fullHeight, int parts, int* outRects, int maxRects) {
+    // the parent cells of prepareFrame() first, then every cell into the same power-of-two grid (columns before rows)
+    if (fullWidth <= 0 || fullHeight <= 0 || parts < 1 || (maxRects > 0 && !outRects)) return -1;
+    const int ncx = (fullWidth + CR_MAXVIEWPORT_SIZE - 1) / CR_MAXVIEWPORT_SIZE, ncy = (fullHeight + CR_MAXVIEWPORT_SIZE - 1) / CR_MAXVIEWPORT_SIZE;
+    const int cellW = (((fullWidth + ncx - 1) / ncx) + 7) & ~7, cellH = (((fullHeight + ncy - 1) / ncy) + 7) & ~7;
+    int sub = 1, lg = 0;
+    while (ncx * ncy * sub < parts) { sub *= 2; lg++; }
+    const int cols = 1 << ((lg + 1) / 2), rows = 1 << (lg / 2);
+    struct R { int x, y, w, h; };
+    std::vector<R> rects;
+    for (int cy = 0; cy < ncy; cy++)
+        for (int cx = 0; cx < ncx; cx++) {
+            const int px0 = cx * cellW, py0 = cy * cellH, pw = std::min(cellW, fullWidth - px0), ph = std::min(cellH, fullHeight - py0);
+            const int sw = (((pw + cols - 1) / cols) + 7) & ~7, sh = (((ph + rows - 1) / rows) + 7) & ~7;
+            for (int r = 0; r < rows; r++)
+                for (int q = 0; q < cols; q++) {
+                    const int x0 = px0 + q * sw, y0 = py0 + r * sh, w = std::min(sw, px0 + pw - x0), h = std::min(sh, py0 + ph - y0);
+                    if (w > 0 && h > 0) rects.push_back({x0, y0, w, h});
+                }
+        }
+    std::sort(rects.begin(), rects.end(), [](const R& a, const R& b) { return a.y != b.y ? a.y < b.y : a.x < b.x; });
+    for (int i = 0; i < (int)rects.size() && i < maxRects; i++) {
+        outRects[4 * i + 0] = rects[i].x; outRects[4 * i + 1] = rects[i].y; outRects[4 * i + 2] = rects[i].w; outRects[4 * i + 3] = rects[i].h;
+    }
+    return (int)rects.size();
+}
+
 int crb_set_chunk_bounds(crb_ctx* c, const float* d_bounds) {
     if (!c) return CRB_ERR_INVALID;
     static_assert(CRB_CHUNK_BOUNDS_TRIS == CRB_SETUP_THREADS, "one bounds record per setup CTA");
@@ -689,8 +717,11 @@ int crb_finish(crb_ctx* c, void* stream) {
             for (int k = 0; k < 4; k++) {
                 float ms = 0.0f;
                 if (cudaEventElapsedTime(&ms, c->ringEv[i][k], c->ringEv[i][k + 1]) == cudaSuccess) c->stageSumMs[k] += ms;
-                if (c->stageFrameMs.size() < (size_t)4 * 65536) c->stageFrameMs.push_back(ms);
+                if (c->stageFrameMs.size() < (size_t)5 * 65536) c->stageFrameMs.push_back(ms);
             }
+            float compMs = 0.0f;   // the frame's composite copy (crb_draw_batch_async, pushDst), 0 when it has none
+            if (c->ringComp[i] && cudaEventElapsedTime(&compMs, c->ringEv[i][5], c->ringEv[i][6]) != cudaSuccess) compMs = 0.0f;
+            if (c->stageFrameMs.size() < (size_t)5 * 65536) c->stageFrameMs.push_back(compMs);
             c->stageFrames++;
         }
         crb_atomics a = c->hostAtomics[1 + i];
@@ -741,6 +772,7 @@ int crb_draw_triangles_async(crb_ctx* c, void* stream) {
     if (c->maxSubtris > CR_MAXSUBTRIS_SIZE) return setError(c, CRB_ERR_LIMIT, "CudaRaster: CR_MAXSUBTRIS_SIZE exceeded!");
     c->maxItems = c->maxBinEntries / CRB_ITEM_ENTRIES + CR_MAXBINS_SQR + 1;
     c->launchCount = 0;
+    c->ringComp[c->pending] = false;
     c->counterSlot = 1 + c->pending;   // the frame's fine raster kernel stores its counters there (mapped host memory): no copy between frames
     rc = prepareFrame(c);
     if (rc != CRB_OK) return rc;
@@ -861,8 +893,8 @@ int crb_set_stage_timing(crb_ctx* c, int enable) {
 
 int crb_get_stage_timing_frames(crb_ctx* c, float* outMs, int maxFrames) {
     if (!c || (maxFrames > 0 && !outMs)) return 0;
-    const int n = std::min((int)(c->stageFrameMs.size() / 4), std::max(maxFrames, 0));
-    if (n > 0) std::memcpy(outMs, c->stageFrameMs.data(), (size_t)n * 4 * sizeof(float));
+    const int n = std::min((int)(c->stageFrameMs.size() / 5), std::max(maxFrames, 0));
+    if (n > 0) std::memcpy(outMs, c->stageFrameMs.data(), (size_t)n * 5 * sizeof(float));
     return n;
 }
 
@@ -893,11 +925,15 @@ int crb_draw_batch_async(crb_ctx* c, const crb_batch_frame* frames, int numFrame
         if (rc == CRB_OK && b.clear) rc = crb_deferred_clear(c, b.clearColor, b.clearDepth);
         if (rc == CRB_OK) rc = crb_draw_triangles_async(c, stream);
         if (rc != CRB_OK) return rc;
+        const int ringIdx = c->pending - 1;   // the frame just enqueued
+        if (c->stageTiming && ringIdx >= 0) c->ringComp[ringIdx] = b.pushDst != nullptr;
         if (b.pushDst) {
             CRB_CUDA(c, cudaEventRecord(cp.rendered[slot], s));
             CRB_CUDA(c, cudaStreamWaitEvent(cp.side, cp.rendered[slot], 0));
+            if (c->stageTiming && ringIdx >= 0) CRB_CUDA(c, cudaEventRecord(c->ringEv[ringIdx][5], cp.side));
             CRB_CUDA(c, cudaMemcpyAsync(b.pushDst, c->color, b.pushBytes, cudaMemcpyDeviceToDevice, cp.side));
             if (b.signalWord && crb_ipc_signal(b.signalWord, b.signalValue, cp.side) != CRB_OK) return setError(c, CRB_ERR_CUDA, "CudaRaster: frame mark failed");
+            if (c->stageTiming && ringIdx >= 0) CRB_CUDA(c, cudaEventRecord(c->ringEv[ringIdx][6], cp.side));
             CRB_CUDA(c, cudaEventRecord(cp.pushed[slot], cp.side));
             cp.pushedValid[slot] = true;
             cp.any = true;

@@ -131,6 +131,13 @@ int crb_set_index_buffer(crb_ctx* ctx, const void* d_indices, int numTris);
  * Passing fullWidth = 0 restores the plain single viewport. */
 int crb_set_subviewport(crb_ctx* ctx, int fullWidth, int fullHeight, int x0, int y0);
 
+/* Sort-first partition of a frame (new): cuts a fullWidth x fullHeight frame into AT LEAST `parts` rectangles
+ * {x0, y0, w, h} (row-major order, origins multiples of 8) none of which straddles a parent cell of crb_set_subviewport --
+ * first the ceil(full / 2048) x ceil(full / 2048) cells, then every cell into the same power-of-two grid.  Writes up to
+ * maxRects rectangles (4 ints each) and returns their number (call with maxRects = 0 to size the array); < 0 on bad arguments.
+ * Rank r of `world` renders rectangles r, r + world, ... */
+int crb_split_frame(int fullWidth, int fullHeight, int parts, int* outRects, int maxRects);
+
 /* Sort-first geometry cull (new).  Every rank of a sort-first split sets up ALL triangles of the mesh and drops those outside
  * its window one by one; with per-chunk bounds a rank skips whole chunks -- CRB_CHUNK_BOUNDS_TRIS consecutive input
  * triangles -- whose clip-space bounding box lies outside the window, without touching their vertices.  The bounds depend
@@ -205,9 +212,10 @@ int crb_get_stats(crb_ctx* ctx, float outSeconds[4]);
  * crb_set_stage_timing was last called. */
 int crb_set_stage_timing(crb_ctx* ctx, int enable);
 int crb_get_stage_timing(crb_ctx* ctx, double outMeanMs[4], int* outFrames);
-/* The same per frame: the four stage intervals (ms) of up to maxFrames frames finished since crb_set_stage_timing, oldest
- * first, 4 floats each; returns the number of frames written.  Mtris/s as SURVEY.md 8(d) defines it is
- * numTris / median over frames of the sum of a frame's four intervals. */
+/* The same per frame: FIVE floats for each of up to maxFrames frames finished since crb_set_stage_timing, oldest first -- the
+ * four stage intervals (ms) and, fifth, the duration of the frame's composite copy (crb_draw_batch_async with pushDst; 0
+ * without one); returns the number of frames written.  Mtris/s as SURVEY.md 8(d) defines it is numTris / median over frames
+ * of the sum of a frame's four intervals. */
 int crb_get_stage_timing_frames(crb_ctx* ctx, float* outMs, int maxFrames);
 
 /* A stream of frames in ONE call (new): for every element, the state setters that are non-NULL (surfaces, vertex buffer, index

@@ -248,6 +248,8 @@ public:
     void setColorPitch(int pitchTexels) { init(); check(crb_set_color_pitch(m_ctx, pitchTexels)); }
     // surfaces over memory the caller owns (e.g. a frame slot of another GPU mapped with crb_ipc_open); the reference's checks are the caller's business here
     void setSurfacePointers(void* d_color, void* d_depth, const Vec2i& size, int numSamples = 1) { init(); check(crb_set_surfaces(m_ctx, d_color, d_depth, size.x, size.y, numSamples)); }
+    // sort-first geometry cull (crb200.h): per-chunk clip-space bounds of the CURRENT vertex / index buffers, or NULL
+    void setChunkBounds(const float* d_bounds) { init(); check(crb_set_chunk_bounds(m_ctx, d_bounds)); }
     crb_ctx* getContext(void) { init(); return m_ctx; }
 
 private:

@@ -86,3 +86,18 @@ def test_runtime_pipe_compiler_builds_and_caches(tmp_path):
     syms = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
     for suffix in ("_triangleSetup", "_binRaster", "_coarseRaster", "_fineRaster", "_spec"):
         assert "PixelPipe_user" + suffix in syms
+
+
+def test_split_frame_c_equals_python():
+    """crb_split_frame (the C++ host layer's sort-first partition) and multigpu.split_frame (Python host layer) are the same function."""
+    import ctypes
+    import cudaraster_linux_b200 as crb
+    from cudaraster_linux_b200 import multigpu
+    lib = crb.load_library()
+    for fw, fh in ((3840, 2160), (1920, 1080), (7680, 4320), (5120, 2880), (3010, 2000), (2049, 17), (640, 384)):
+        for parts in (1, 2, 4, 8, 16):
+            n = lib.crb_split_frame(fw, fh, parts, None, 0)
+            buf = (ctypes.c_int * (4 * n))()
+            assert lib.crb_split_frame(fw, fh, parts, buf, n) == n
+            got = [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
+            assert got == multigpu.split_frame(fw, fh, parts), (fw, fh, parts)

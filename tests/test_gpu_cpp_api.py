@@ -74,3 +74,14 @@ def test_cpp_runtime_compiled_pipe(tmp_path):
     bad.write_text("#include <cudaraster/cuda/PixelPipe.inl>\nthis is not CUDA\n")
     r3 = subprocess.run([exe, str(bad), out, str(w), str(h)], capture_output=True, text=True, timeout=600)
     assert r3.returncode != 0 and "CudaCompiler: Compilation of" in (r3.stdout + r3.stderr)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cpp_sort_first_multi_process(world):
+    """include/cudaraster/MultiGpu.hpp: `world` PROCESSES (one per GPU; they share GPUs when the box has fewer) render one
+    2560x1440 frame sort-first, in place in rank 0's memory through CUDA IPC; rank 0 compares with its own render of the frame."""
+    exe = os.path.join(ROOT, "examples", "cpp", "sortfirst")
+    assert os.path.exists(exe), "examples/cpp is not built (run __graft_entry__.build())"
+    r = subprocess.run([exe, str(world)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout + r.stderr
+    assert r.stdout.count("rendered") == world
