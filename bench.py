@@ -9,8 +9,10 @@ BASELINE.json configs[1] ("c2"): 1 M-triangle tessellated grid, Gouraud, depth t
 
 N = 1   the frame is rendered K times on cuda:0.
 N > 1   one process per GPU (torchrun); view-parallel sharding: every step each rank
-        renders ITS OWN view of the mesh and the colour frames are gathered to rank 0 with NCCL
-        (the composite is inside the timed region).  Weak scaling: per-GPU work is fixed.
+        renders one frame of the workload (the same frame on every rank, so that per-GPU work is exactly
+        the N = 1 workload) and the colour frames are composited on rank 0 (peer memory over NVLink, or
+        NCCL; the composite is inside the timed region).  Weak scaling.  The 48-view round-robin batch and
+        the 4K sort-first frame of BASELINE config 5 are tools/views_48.py and tools/sort_first_4k.py.
 
 Prints ONE JSON line (rank 0).  Keys: see the task contract; additionally
   value        N = 1: the metric SURVEY.md 8(d) defines -- T / t_frame, t_frame = the sum of the four stage intervals between CUDA
@@ -31,6 +33,7 @@ Prints ONE JSON line (rank 0).  Keys: see the task contract; additionally
 its own: its host emulators are broken in this port) with all host threads.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -94,7 +97,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.05)
 
     def result(self):
         self.stop_flag = True
@@ -118,7 +121,7 @@ def config_dict(workload, n_gpus):
     import cudaraster_linux_b200 as crb
     n_tris = {"c2": 1_000_000, "c3": 5_000_000, "c4": 10_000_000}[workload]
     return {"workload": desc, "triangles": n_tris, "resolution": [w, h], "samples": 1 << s_log2, "pipe": crb.pipe_name(shader, s_log2, flags, "BlendReplace"),
-            "sharding": "1 GPU" if n_gpus == 1 else "view-parallel: 1 view of the mesh per rank per step, colour frames composited on rank 0 inside the timed region",
+            "sharding": "1 GPU" if n_gpus == 1 else "view-parallel: 1 frame of the workload per rank per step (the same frame on every rank: per-GPU work = the N = 1 workload), colour frames composited on rank 0 inside the timed region",
             "l2": "GPU arm: inputs rotate over %d device copies and each frame rewrites its intermediates (setup records, queues, surfaces): working set > 126 MB L2; "
                   "CPU arm: one frame per step" % NUM_INPUT_COPIES}
 
@@ -202,6 +205,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true")
+    ap.add_argument("--no-stagger", action="store_true", help="N > 1, push composite: all ranks start their frame loops in phase")
     ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
                     help="2 = consecutive frames alternate between two contexts / streams / surface sets, so the (issue-bound) setup of one frame "
                          "overlaps the (latency-bound) fine raster of the other -- a double-buffered swap chain; 1 = one context, one stream")
@@ -245,13 +249,12 @@ def main():
     raster.setSurfaces(color, depth)
     raster.setPixelPipe(None, crb.pipe_name(shader, s_log2, flags, "BlendReplace"))
 
-    # view-parallel sharding: rank r renders view (step * world + r); N = 1 renders the identity view
-    views = crb.scenes.view_matrix_variants(48)
+    # view-parallel sharding: one frame per rank per step
     h_verts = torch.from_numpy(verts).pin_memory()
     h_idx = torch.from_numpy(idx).pin_memory()
     copies = []
     for k in range(NUM_INPUT_COPIES):
-        vv = verts if world == 1 else crb.scenes.apply_view(verts, views[(k * world + rank) % len(views)])
+        vv = verts   # every rank renders the C2 frame itself: per-GPU work is exactly the N = 1 workload (weak scaling); the 48-view batch of config 5(ii) is tools/views_48.py
         copies.append((torch.from_numpy(vv).to(dev), torch.from_numpy(idx).to(dev)))
     # N > 1, composite to rank 0.  Default: rank 0 owns two frame slots per rank, exported with CUDA IPC; every
     # rank renders STRAIGHT into its slot, so the fine raster's colour stores cross NVLink / NVSwitch while the frame is being
@@ -345,6 +348,7 @@ def main():
         stage_times[s] = stage_times[s][2:] or stage_times[s]
     join_lanes()
     sync_all()
+    frame_ns_estimate = 1e6 * sum(statistics.median(v) for v in stage_times.values())
     launches_per_frame = raster.getLaunchCount()
     direct = raster.lastFrameDirect()   # automatic binning mode: small-triangle frames of an order-independent pipe skip the bin / coarse sort
 
@@ -372,6 +376,9 @@ def main():
         raster.setStageTiming(stage_events)
         sync_all()
         e0.record(stream)
+        if push and not args.no_stagger:
+            # rank r starts r / N of a frame time late: the ranks' pushes then interleave at rank 0's NVLink ingress instead of arriving together
+            crb.load_library().crb_ipc_delay(ctypes.c_void_p(stream.cuda_stream), int(rank * frame_ns_estimate / world))
         if lanes:
             fork_lanes()
         t0 = time.perf_counter()
@@ -393,12 +400,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / args.steps, enqueue_ms
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    # clocks are sampled on rank 0 only: NVML queries from every process of the job measurably slow down the CUDA calls of
+    # all of them (enqueue_ms_per_step at N = 8: 0.14 ms with eight pollers, 0.03 ms without)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # ---- (1) THE METRIC: K frames, ONE frame in flight, the reference's five stage events on every frame
     bracket_ms, enqueue_ms = timed_region(lanes=False, stage_events=True)
-    clocks = sampler.result()
+    clocks = sampler.result() if sampler else None
     live = raster.getStageTiming()
     per_frame = raster.getStageTimingFrames()[-args.steps:]
     # t_frame of THIS rank: the four stage intervals of a frame; with a DMA composite on the side stream (push) the frame
@@ -407,10 +417,16 @@ def main():
     composite_ms = float(np.median(per_frame[:, 4])) if len(per_frame) else 0.0
     frame_ms = max(stage_sum_ms, composite_ms)
     raster.setStageTiming(False)
+    per_rank = None
     if world > 1:
         t = torch.tensor([frame_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step = float(t.item())                            # the slowest rank's t_frame
+        mine = torch.tensor([stage_sum_ms, composite_ms, enqueue_ms] + [float(np.median(per_frame[:, k])) for k in range(4)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"stage_sum_ms": [round(float(a[0]), 4) for a in allr], "composite_ms": [round(float(a[1]), 4) for a in allr], "enqueue_ms": [round(float(a[2]), 4) for a in allr],
+                    "setup_ms": [round(float(a[3]), 4) for a in allr], "fine_ms": [round(float(a[6]), 4) for a in allr]}
     else:
         ms_per_step = frame_ms                                   # t_frame = sum of the four stage intervals, median over the K frames
     value = world * n_tris / (ms_per_step * 1e-3) / 1e6
@@ -495,7 +511,7 @@ def main():
                       + ("" if world == 1 else ", max over ranks; composite: " + ("inside the fine raster interval (the frame is rendered into rank 0's memory) + a frame mark" if peer else
                          "DMA copy of the finished frame on a side stream, overlapped with the next frame -- a rank's t_frame is the slower of its render (four intervals) and its copy (5th interval, composite_ms)" if push else
                          "NCCL gather on a side stream (not in t_frame: see bracket_ms_per_step)")),
-            "composite_ms": composite_ms, "stage_sum_ms": stage_sum_ms,
+            "composite_ms": composite_ms, "stage_sum_ms": stage_sum_ms, "per_rank": per_rank,
             "bracket_ms_per_step": bracket_ms, "enqueue_ms_per_step": enqueue_ms, "enqueue": ("one C call for the K frames, composite included (crb_draw_batch_async)" if batch_one is not None else "Python loop over crb_draw_triangles_async + NCCL gather calls"),
             "value_unbroken_chain": value_chain, "unbroken_chain_ms_per_step": chain_ms, "unbroken_chain_enqueue_ms_per_step": chain_enqueue_ms,
             "value_two_in_flight": value_two,

@@ -156,6 +156,19 @@ extern "C" int crb_ipc_signal(void* d_word, uint32_t value, void* stream) {
     return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
 }
 
+// Stream-ordered pause (device spins on %globaltimer): ranks that composite into one display GPU start their frame loops out
+// of phase with it, so that their frame pushes interleave instead of meeting at the display GPU's NVLink ingress all at once.
+__global__ void ipcDelayKernel(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+extern "C" int crb_ipc_delay(void* stream, unsigned int nanoseconds) {
+    if (nanoseconds == 0) return CRB_OK;
+    ipcDelayKernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)(nanoseconds > 100000000u ? 100000000u : nanoseconds));
+    return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}
+
 extern "C" int crb_ipc_copy(void* d_dst, const void* d_src, size_t bytes, void* stream) {
     if (bytes && (!d_dst || !d_src)) return CRB_ERR_INVALID;
     return cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
