@@ -112,6 +112,7 @@ def load_library():
         "crb_ipc_signal": (i32, [vp, u32, vp]),
         "crb_ipc_copy": (i32, [vp, vp, ctypes.c_size_t, vp]),
         "crb_ipc_delay": (i32, [vp, u32]),
+        "crb_ipc_copy_2d": (i32, [vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp]),
         "crb_resolve_surface": (i32, [vp, i32, i32, i32, vp, i32, i32, vp]),
         "crb_write_ppm": (i32, [ctypes.c_char_p, vp, i32, i32, i32]),
         "crb_launch_vertex_shader": (i32, [vp, ctypes.c_char_p, vp, vp, i32, vp, ctypes.c_size_t, vp]),
@@ -128,7 +129,7 @@ EXPORTED_SYMBOLS = ["crb_abi_version", "crb_create", "crb_destroy", "crb_last_er
                     "crb_encode_clear_depth", "crb_set_pixel_pipe", "crb_set_pixel_pipe_by_name", "crb_set_vertex_buffer", "crb_set_index_buffer",
                     "crb_set_subviewport", "crb_draw_triangles", "crb_draw_triangles_async", "crb_finish", "crb_draw_triangles_host", "crb_draw_triangles_host_async", "crb_get_stats", "crb_get_counters",
                     "crb_set_stage_timing", "crb_get_stage_timing", "crb_get_stage_timing_frames", "crb_draw_batch_async", "crb_batch_join", "crb_compute_chunk_bounds", "crb_set_chunk_bounds", "crb_split_frame", "crb_get_profiling_info", "crb_get_launch_count", "crb_get_work_buffers", "crb_download",
-                    "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_set_color_pitch", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_ipc_copy", "crb_ipc_delay", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
+                    "crb_set_binning_mode", "crb_get_last_frame_direct", "crb_set_color_layout", "crb_set_color_pitch", "crb_ipc_alloc", "crb_ipc_free", "crb_ipc_open", "crb_ipc_close", "crb_ipc_signal", "crb_ipc_copy", "crb_ipc_delay", "crb_ipc_copy_2d", "crb_resolve_surface", "crb_write_ppm", "crb_launch_vertex_shader"]
 
 
 def pipe_name(base, samples_log2, flags, blend="BlendReplace"):

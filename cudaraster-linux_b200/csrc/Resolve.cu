@@ -156,6 +156,11 @@ extern "C" int crb_ipc_signal(void* d_word, uint32_t value, void* stream) {
     return cudaGetLastError() == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
 }
 
+extern "C" int crb_ipc_copy_2d(void* d_dst, size_t dstPitchBytes, const void* d_src, size_t srcPitchBytes, size_t widthBytes, size_t height, void* stream) {
+    if (widthBytes && height && (!d_dst || !d_src)) return CRB_ERR_INVALID;
+    return cudaMemcpy2DAsync(d_dst, dstPitchBytes, d_src, srcPitchBytes, widthBytes, height, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess ? CRB_OK : CRB_ERR_CUDA;
+}
+
 // Stream-ordered pause (device spins on %globaltimer): ranks that composite into one display GPU start their frame loops out
 // of phase with it, so that their frame pushes interleave instead of meeting at the display GPU's NVLink ingress all at once.
 __global__ void ipcDelayKernel(unsigned long long ns) {

@@ -321,6 +321,9 @@ int crb_ipc_signal(void* d_word, uint32_t value, void* stream);
 /* Stream-ordered device-to-device copy (either side may be mapped peer memory): the DMA engines move a finished frame
  * into its slot with full-size NVLink packets. */
 int crb_ipc_copy(void* d_dst, const void* d_src, size_t bytes, void* stream);
+/* The same for a rectangle (rows of widthBytes bytes): a sort-first window rendered locally, pasted into the full frame in the
+ * display GPU's memory by the DMA engines. */
+int crb_ipc_copy_2d(void* d_dst, size_t dstPitchBytes, const void* d_src, size_t srcPitchBytes, size_t widthBytes, size_t height, void* stream);
 /* Stream-ordered pause of `nanoseconds` (<= 0.1 s): rank r of a job that composites into one display GPU starts its frame loop
  * r / world of a frame time late, so that the ranks' frame pushes interleave at the display GPU's NVLink ingress. */
 int crb_ipc_delay(void* stream, unsigned int nanoseconds);

@@ -24,6 +24,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--composite", default="push", choices=["inplace", "push"],
+                    help="inplace: the fine raster stores straight into the full frame in rank 0's memory (32-byte rows over NVLink); push: rectangles are rendered into "
+                         "local surfaces and pasted into the full frame by the DMA engines on a side stream (2-D copy, overlapped with the next frame)")
     ap.add_argument("--no-bounds", action="store_true", help="without the per-chunk clip-space bounds (every rank then sets up every triangle)")
     args = ap.parse_args()
     import torch
@@ -57,10 +60,24 @@ def main():
     def frame_base(k):
         return sink.slot_pointer(k, rank=0) if sink else local_frames[k % 2].data_ptr()
 
+    push = args.composite == "push" and world > 1
+    lib = crb.load_library()
+    side = torch.cuda.Stream(device=dev) if push else None
+    local_colors = [[crb.CudaSurface((w, h), crb.CudaSurface.FORMAT_RGBA8, device=dev) for _, (x0, y0, w, h) in mine] for _ in range(2)] if push else None
+    pushed = [None, None]
+
     def render(k, base, my_rects, my_depths, asynchronous=True):
-        for (_, (x0, y0, w, h)), d in zip(my_rects, my_depths):
-            raster.setSurfaces(crb.CudaSurface.from_pointer(base + 4 * (y0 * fw + x0), (w, h), crb.CudaSurface.FORMAT_RGBA8), d)
-            raster.setColorPitch(fw)
+        import ctypes
+        stream = torch.cuda.current_stream(dev)
+        if push and pushed[k % 2] is not None:
+            stream.wait_event(pushed[k % 2])          # the paste that last read this set of local surfaces
+        for j, ((_, (x0, y0, w, h)), d) in enumerate(zip(my_rects, my_depths)):
+            if push:
+                raster.setSurfaces(local_colors[k % 2][j], d)
+                raster.setColorPitch(0)
+            else:
+                raster.setSurfaces(crb.CudaSurface.from_pointer(base + 4 * (y0 * fw + x0), (w, h), crb.CudaSurface.FORMAT_RGBA8), d)
+                raster.setColorPitch(fw)
             raster.setPixelPipe(None, pipe)
             raster.setVertexBuffer(vb, 0)
             raster.setIndexBuffer(ib, 0, n_tris)
@@ -68,7 +85,18 @@ def main():
             raster.setSubViewport(fw, fh, x0, y0)
             raster.deferredClear((0.2, 0.4, 0.8, 1.0), 1.0)
             raster.drawTriangles(asynchronous=asynchronous)
-        if sink:
+        if push:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            side.wait_event(ev)
+            for j, (_, (x0, y0, w, h)) in enumerate(my_rects):
+                c = local_colors[k % 2][j]
+                assert lib.crb_ipc_copy_2d(ctypes.c_void_p(base + 4 * (y0 * fw + x0)), fw * 4, ctypes.c_void_p(c.tensor.data_ptr()), c.rounded_size[0] * 4, w * 4, h,
+                                           ctypes.c_void_p(side.cuda_stream)) == 0
+            sink.publish(k, stream=side.cuda_stream)
+            pushed[k % 2] = torch.cuda.Event()
+            pushed[k % 2].record(side)
+        elif sink:
             sink.publish(k)
 
     def sync_all():
@@ -82,8 +110,12 @@ def main():
     stream = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    if push:
+        lib.crb_ipc_delay(__import__("ctypes").c_void_p(stream.cuda_stream), int(rank * 100000 / world))   # ranks out of phase: their pastes interleave at rank 0
     for k in range(args.frames):
         render(k, frame_base(k), mine, depths)
+    if push:
+        stream.wait_stream(side)
     e1.record(stream)
     raster.finish()
     sync_all()
@@ -111,7 +143,8 @@ def main():
         ok = bool(np.array_equal(got, want)) and bool((want != want[0]).any())
         line = {"metric": "Mtris/s", "value": n_tris / (ms * 1e-3) / 1e6, "unit": "Mtris/s", "frames_per_s": 1e3 / ms, "ms_per_frame": ms, "n_gpus": world,
                 "config": {"workload": "C5(i): 4M-triangle grid, Gouraud, depth test, 3840x2160, sort-first over %d rectangles" % len(rects),
-                           "composite": "rectangles rendered in place into rank 0's full frame (CUDA IPC peer memory, crb_set_color_pitch)" if world > 1 else "single GPU, rectangles rendered in place",
+                           "composite": ("rectangles rendered locally and pasted into rank 0's full frame by the DMA engines (2-D copy over NVLink on a side stream, overlapped with the next frame)" if push else
+                                         "rectangles rendered in place into rank 0's full frame (CUDA IPC peer memory, crb_set_color_pitch)") if world > 1 else "single GPU, rectangles rendered in place",
                            "geometry": "replicated; " + ("every rank sets up all triangles" if args.no_bounds else "per-chunk (256 triangles) clip-space bounds, computed once per mesh: a rank skips the chunks outside its rectangle"),
                            "frame_equals_single_gpu_render": ok}, "scaling": "strong", "frames": args.frames}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
