@@ -414,8 +414,8 @@ class CudaRaster:
         self._check(self.lib.crb_batch_join(self.ctx, ctypes.c_void_p(s)))
 
     def getProfilingInfo(self):
-        buf = ctypes.create_string_buffer(2048)
-        self._check(self.lib.crb_get_profiling_info(self.ctx, buf, 2048))
+        buf = ctypes.create_string_buffer(8192)
+        self._check(self.lib.crb_get_profiling_info(self.ctx, buf, 8192))
         return buf.value.decode()
 
     # -- extras ------------------------------------------------------------------------------

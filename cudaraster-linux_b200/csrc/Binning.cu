@@ -79,8 +79,10 @@ struct CellIndexer {
 //
 // Fast path (whole warp): every footprint is at most 2x2 cells -- four predicated slots, straight
 // line code.  Otherwise the generic three-pass enumeration with edge-refined cells.
+// Returns, in lane-local pieces that add up over the warp, the number of distinct cells the batch touched (every touched cell is
+// counted by its lowest lane) -- used by the profiling counters only.
 template <int SamplesLog2, int CellLog2, class OnPlaced>
-__device__ __forceinline__ void scatterBatch(WarpCells& wc, int32_t* __restrict__ queue, S32 entry, const TriFootprint& fp, int lane, unsigned ltMask, S32 winLoX, S32 winLoY,
+__device__ __forceinline__ int scatterBatch(WarpCells& wc, int32_t* __restrict__ queue, S32 entry, const TriFootprint& fp, int lane, unsigned ltMask, S32 winLoX, S32 winLoY,
                                              S32 winHiX, S32 winHiY, const CellIndexer cellOf, OnPlaced onPlaced) {
     const CellRange r = cellRange<CellLog2>(fp, winLoX, winLoY, winHiX, winHiY);
     if (!__any_sync(0xFFFFFFFFu, r.refine | (r.nx > 2) | (r.ny > 2))) {
@@ -99,13 +101,15 @@ __device__ __forceinline__ void scatterBatch(WarpCells& wc, int32_t* __restrict_
         if (v3) { m3 = wc.mask[c3]; const int pos = wc.cursor[c3] + __popc(m3 & ltMask); queue[pos] = entry; onPlaced(r.x0 + 1, r.y0 + 1, pos); }
         __syncwarp();
         // the lowest lane of every touched cell advances the cursor and clears the word
-        if (v0 && (m0 & ltMask) == 0) { wc.cursor[c0] += __popc(m0); wc.mask[c0] = 0; }
-        if (v1 && (m1 & ltMask) == 0) { wc.cursor[c1] += __popc(m1); wc.mask[c1] = 0; }
-        if (v2 && (m2 & ltMask) == 0) { wc.cursor[c2] += __popc(m2); wc.mask[c2] = 0; }
-        if (v3 && (m3 & ltMask) == 0) { wc.cursor[c3] += __popc(m3); wc.mask[c3] = 0; }
+        int touched = 0;
+        if (v0 && (m0 & ltMask) == 0) { wc.cursor[c0] += __popc(m0); wc.mask[c0] = 0; touched++; }
+        if (v1 && (m1 & ltMask) == 0) { wc.cursor[c1] += __popc(m1); wc.mask[c1] = 0; touched++; }
+        if (v2 && (m2 & ltMask) == 0) { wc.cursor[c2] += __popc(m2); wc.mask[c2] = 0; touched++; }
+        if (v3 && (m3 & ltMask) == 0) { wc.cursor[c3] += __popc(m3); wc.mask[c3] = 0; touched++; }
         __syncwarp();
-        return;
+        return touched;
     }
+    int touched = 0;
     forEachCell<SamplesLog2, CellLog2>(fp, winLoX, winLoY, winHiX, winHiY, [&](S32 cx, S32 cy) { atomicOr(&wc.mask[cellOf(cx, cy)], 1u << lane); });
     __syncwarp();
     forEachCell<SamplesLog2, CellLog2>(fp, winLoX, winLoY, winHiX, winHiY, [&](S32 cx, S32 cy) {
@@ -124,9 +128,42 @@ __device__ __forceinline__ void scatterBatch(WarpCells& wc, int32_t* __restrict_
         if (m != 0 && (m & ltMask) == 0) {
             wc.cursor[cell] += __popc(m);
             atomicExch(&wc.mask[cell], 0u);
+            touched++;
         }
     });
     __syncwarp();
+    return touched;
+}
+
+// ProfilingMode_Counters for one round (= one batch of 32 entries) of the bin (Bin = true) or coarse scatter; all 32 lanes call.
+// Reference counters: cuda/PrivateDefs.hpp:168-187, counted at BinRaster.inl:176, :222-264 and CoarseRaster.inl:291, :322-412, :463, :548-550.
+template <int ProfMode, int CellLog2, bool Bin>
+__device__ __forceinline__ void profScatterRound(const crb_frame& f, S32 entry, const TriFootprint& fp, S32 winLoX, S32 winLoY, S32 winHiX, S32 winHiY, int emits, int touched) {
+    if (ProfMode != ProfilingMode_Counters) return;
+    const CellRange r = cellRange<CellLog2>(fp, winLoX, winLoY, winHiX, winHiY);
+    const bool valid = entry >= 0;
+    const bool generic = __any_sync(0xFFFFFFFFu, r.refine | (r.nx > 2) | (r.ny > 2));   // the path scatterBatch took for this round
+    const U32 numValid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+    const U32 sumEmits = __reduce_add_sync(0xFFFFFFFFu, (U32)emits), sumTouched = __reduce_add_sync(0xFFFFFFFFu, (U32)touched);
+    if (Bin) {
+        const U32 area = __reduce_add_sync(0xFFFFFFFFu, valid ? (U32)(r.nx * r.ny) : 0u);
+        const U32 single = __popc(__ballot_sync(0xFFFFFFFFu, valid && r.nx * r.ny <= 1)), slow = __popc(__ballot_sync(0xFFFFFFFFu, valid && (r.refine || r.nx > 2 || r.ny > 2)));
+        if (laneId() == 0) {
+            profCount<ProfMode>(f, CRB_PROF_BinTrisPerRound, numValid, 1);
+            profCount<ProfMode>(f, CRB_PROF_BinTriBBArea, area, numValid);
+            profCount<ProfMode>(f, CRB_PROF_BinTriSinglePath, 100ull * single, numValid);
+            profCount<ProfMode>(f, CRB_PROF_BinTriFastPath, 100ull * (numValid - single - slow), numValid);
+            profCount<ProfMode>(f, CRB_PROF_BinTriSlowPath, 100ull * slow, numValid);
+        }
+    } else if (laneId() == 0) {
+        profCount<ProfMode>(f, CRB_PROF_CoarseRoundsPerBin, 1, 0);
+        profCount<ProfMode>(f, CRB_PROF_CoarseTrisPerRound, numValid, 1);
+        profCount<ProfMode>(f, CRB_PROF_CoarseTilesPerRound, sumTouched, 1);
+        profCount<ProfMode>(f, CRB_PROF_CoarseEmitsPerRound, sumEmits, 1);
+        profCount<ProfMode>(f, CRB_PROF_CoarseEmitsPerTri, sumEmits, numValid);
+        profCount<ProfMode>(f, CRB_PROF_CoarseCaseA, generic ? 0 : 100, 1);
+        profCount<ProfMode>(f, CRB_PROF_CoarseCaseC, generic ? 100 : 0, 1);
+    }
 }
 
 template <int SamplesLog2>
@@ -142,6 +179,7 @@ __device__ __forceinline__ TriFootprint footprintOf(const crb_frame& f, S32 entr
 //------------------------------------------------------------------------------------------------
 
 // One CTA per bin: exclusive scan of row `bin` of binCountMat[bin][chunk] over the chunks.
+template <int ProfMode>
 __global__ void __launch_bounds__(kScanThreads) binScanKernel(const __grid_constant__ crb_frame f) {
     __shared__ int s_warp[33];
     __shared__ int s_base[2];
@@ -149,6 +187,8 @@ __global__ void __launch_bounds__(kScanThreads) binScanKernel(const __grid_const
     if (threadIdx.x < 33) s_warp[threadIdx.x] = 0;
     __syncthreads();
     gridDepWait();
+    ProfTimer<ProfMode> tmScan;
+    tmScan.start();
     const int bin = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // thread t owns the 4-aligned run of chunks [first, first + perThread): 128-bit loads, coalesced
     const int perThread = (((f.numChunks + kScanThreads - 1) / kScanThreads) + 3) & ~3;
@@ -216,6 +256,8 @@ __global__ void __launch_bounds__(kScanThreads) binScanKernel(const __grid_const
             it.slot = k;
             f.items[itemBase + k] = it;
         }
+    tmScan.stop(f, CRB_TIMER_BinScan);
+    tmScan.stop(f, CRB_TIMER_BinTotal);
 }
 
 // Tile-level count of one placed bin-queue entry: the entry sits at slot `pos` of bin (bx, by), i.e.
@@ -235,7 +277,7 @@ __device__ __forceinline__ void countTilesOfPlacedEntry(const crb_frame& f, cons
 
 // One warp per chunk: expands the chunk's triangles into (triangle, sub-triangle) entries in
 // submission order and scatters them into the bin queue.  Loads run one batch ahead.
-template <int SamplesLog2>
+template <int SamplesLog2, int ProfMode>
 __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_constant__ crb_frame f) {
     __shared__ WarpCells s_cells[kWarps];
     __shared__ int s_list[kWarps][kMaxListEntries];
@@ -244,6 +286,9 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
     gridDepLaunchDependents();
     gridDepWait();
     if (chunk >= f.numChunks) return;
+    ProfTimer<ProfMode> tmTotal, tm;
+    tmTotal.start();
+    tm.start();
     const int triBegin = chunk * f.chunkTris, triEnd = min(triBegin + f.chunkTris, f.numTris);
     // triSubtris runs two batches ahead, headers one batch ahead and only for surviving triangles
     // (on a cull-heavy scene most header slots are never written and must not be fetched)
@@ -259,7 +304,16 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
         wc.mask[b] = 0;
     }
     __syncwarp();
+    tm.stop(f, CRB_TIMER_BinReadTriHeader);   // the chunk's cursors and the first triangle records
     const CellIndexer cellOf = {0, 0, -1, f.widthBins};
+    long long countClocks = 0;   // ProfilingMode_Timers: time inside the fused tile counting
+    auto countTimed = [&](const TriFootprint& fp, S32 bx, S32 by, int pos) {
+        if (ProfMode == ProfilingMode_Timers) {
+            const long long t0 = clock64();
+            countTilesOfPlacedEntry<SamplesLog2>(f, fp, bx, by, pos);
+            countClocks += clock64() - t0;
+        } else countTilesOfPlacedEntry<SamplesLog2>(f, fp, bx, by, pos);
+    };
 
 #pragma unroll 1
     for (int t0 = triBegin; t0 < triEnd; t0 += 32) {
@@ -273,8 +327,12 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
         if (__all_sync(0xFFFFFFFFu, n <= 1)) {
             const S32 entry = n == 1 ? tri * 8 + 7 : -1;
             const TriFootprint fp = footprintOf<SamplesLog2>(f, entry, h);
-            scatterBatch<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(wc, f.binQueue, entry, fp, lane, ltMask, 0, 0, f.widthBins - 1, f.heightBins - 1, cellOf,
-                                                                  [&](S32 bx, S32 by, int pos) { countTilesOfPlacedEntry<SamplesLog2>(f, fp, bx, by, pos); });
+            tm.start();
+            int emits = 0;
+            const int touched = scatterBatch<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(wc, f.binQueue, entry, fp, lane, ltMask, 0, 0, f.widthBins - 1, f.heightBins - 1, cellOf,
+                                                                                      [&](S32 bx, S32 by, int pos) { emits++; countTimed(fp, bx, by, pos); });
+            tm.stop(f, CRB_TIMER_BinRasterize);
+            profScatterRound<ProfMode, CR_BIN_LOG2 + CR_TILE_LOG2, true>(f, entry, fp, 0, 0, f.widthBins - 1, f.heightBins - 1, emits, touched);
         } else {
             // clipped triangles in the batch: lay the entries out in order first
             int numEntries;
@@ -288,12 +346,18 @@ __global__ void __launch_bounds__(kThreads, 4) binScatterKernel(const __grid_con
                 uint4 he = make_uint4(0, 0, 0, 0);
                 if (entry >= 0) he = __ldg(&f.triHeader[resolveDataIdx(entry, f.triHeader)]);
                 const TriFootprint fp = footprintOf<SamplesLog2>(f, entry, he);
-                scatterBatch<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(wc, f.binQueue, entry, fp, lane, ltMask, 0, 0, f.widthBins - 1, f.heightBins - 1, cellOf,
-                                                                      [&](S32 bx, S32 by, int pos) { countTilesOfPlacedEntry<SamplesLog2>(f, fp, bx, by, pos); });
+                tm.start();
+                int emits = 0;
+                const int touched = scatterBatch<SamplesLog2, CR_BIN_LOG2 + CR_TILE_LOG2>(wc, f.binQueue, entry, fp, lane, ltMask, 0, 0, f.widthBins - 1, f.heightBins - 1, cellOf,
+                                                                                          [&](S32 bx, S32 by, int pos) { emits++; countTimed(fp, bx, by, pos); });
+                tm.stop(f, CRB_TIMER_BinRasterize);
+                profScatterRound<ProfMode, CR_BIN_LOG2 + CR_TILE_LOG2, true>(f, entry, fp, 0, 0, f.widthBins - 1, f.heightBins - 1, emits, touched);
             }
             __syncwarp();
         }
     }
+    if (ProfMode == ProfilingMode_Timers && lane == 0 && countClocks > 0) atomicAdd(&f.profCounters[2 * CRB_PROF_NUM + CRB_TIMER_BinCountTiles], (unsigned long long)countClocks);
+    tmTotal.stop(f, CRB_TIMER_BinTotal);
 }
 
 //------------------------------------------------------------------------------------------------
@@ -336,6 +400,7 @@ __device__ __forceinline__ int blockExclusiveScan256g(int v, int group, int* s_w
 // items: the four quarters are prefix-summed concurrently and stitched through shared memory, so the
 // serial chain over the items of a crowded bin is four times shorter.
 constexpr int kScanGroups = 4;
+template <int ProfMode>
 __global__ void __launch_bounds__(kThreads * kScanGroups) coarseScanKernel(const __grid_constant__ crb_frame f) {
     __shared__ int s_warp[kWarps + 1];
     __shared__ int s_base[2];
@@ -348,8 +413,14 @@ __global__ void __launch_bounds__(kThreads * kScanGroups) coarseScanKernel(const
     if (threadIdx.x == 0) s_abort = f.atomics->overflow;
     __syncthreads();
     if (s_abort != 0) return;
+    ProfTimer<ProfMode> tmScan;
+    tmScan.start();
     const int bin = blockIdx.x, t = threadIdx.x & (kCells - 1), g = threadIdx.x >> 8;
     const int itemBase = f.binItemBase[bin], numItems = f.binItemCount[bin];
+    if (threadIdx.x == 0 && numItems > 0) {   // reference: CoarseRaster.inl:158-159 (bins a block picked; denominator of rounds per bin)
+        profCount<ProfMode>(f, CRB_PROF_CoarseBins, 1, 0);
+        profCount<ProfMode>(f, CRB_PROF_CoarseRoundsPerBin, 0, 1);
+    }
     const int perGroup = (numItems + kScanGroups - 1) / kScanGroups;
     const int k0 = min(g * perGroup, numItems), k1 = min(k0 + perGroup, numItems);
     int* const col = &f.tileCountMat[(size_t)itemBase * CR_BIN_SQR + t];
@@ -397,10 +468,12 @@ __global__ void __launch_bounds__(kThreads * kScanGroups) coarseScanKernel(const
             f.activeRecs[s_base[1] + activeOfs] = make_int4(gi, s_base[0] + ofs, tileTotal, 0);
         }
     }
+    tmScan.stop(f, CRB_TIMER_CoarseScan);
+    tmScan.stop(f, CRB_TIMER_CoarseTotal);
 }
 
 // One warp per work item.  Entries are loaded two batches ahead, headers one batch ahead.
-template <int SamplesLog2>
+template <int SamplesLog2, int ProfMode>
 __global__ void __launch_bounds__(kThreads, 4) coarseScatterKernel(const __grid_constant__ crb_frame f) {
     __shared__ WarpCells s_cells[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -408,6 +481,9 @@ __global__ void __launch_bounds__(kThreads, 4) coarseScatterKernel(const __grid_
     gridDepLaunchDependents();
     gridDepWait();
     if (f.atomics->overflow != 0 || item >= f.atomics->numCoarseItems) return;
+    ProfTimer<ProfMode> tmTotal, tm;
+    tmTotal.start();
+    tm.start();
     WarpCells& wc = s_cells[warp];
     const unsigned ltMask = laneMaskLt();
     const crb_item it = f.items[item];
@@ -428,16 +504,24 @@ __global__ void __launch_bounds__(kThreads, 4) coarseScatterKernel(const __grid_
         wc.mask[t] = 0;
     }
     __syncwarp();
+    tm.stop(f, CRB_TIMER_CoarseStreamRead);   // the item, its cursors, the first entries and headers
     const CellIndexer cellOf = {w.tx0, w.ty0, CR_BIN_LOG2, 0};
 #pragma unroll 1
     for (int b = 0; b < it.count; b += 32) {
+        tm.start();
         uint4 hNext = make_uint4(0, 0, 0, 0);
         if (entryNext >= 0) hNext = __ldg(&f.triHeader[resolveDataIdx(entryNext, f.triHeader)]);
         const S32 entryNext2 = b + 64 + lane < it.count ? __ldg(&src[b + 64 + lane]) : -1;
         const TriFootprint fp = footprintOf<SamplesLog2>(f, entryCur, hCur);
-        scatterBatch<SamplesLog2, CR_TILE_LOG2>(wc, f.tileQueue, entryCur, fp, lane, ltMask, w.tx0, w.ty0, w.tx1, w.ty1, cellOf, [](S32, S32, int) {});
+        tm.stop(f, CRB_TIMER_CoarseStreamRead);
+        tm.start();
+        int emits = 0;
+        const int touched = scatterBatch<SamplesLog2, CR_TILE_LOG2>(wc, f.tileQueue, entryCur, fp, lane, ltMask, w.tx0, w.ty0, w.tx1, w.ty1, cellOf, [&](S32, S32, int) { emits++; });
+        tm.stop(f, CRB_TIMER_CoarseRasterize);
+        profScatterRound<ProfMode, CR_TILE_LOG2, false>(f, entryCur, fp, w.tx0, w.ty0, w.tx1, w.ty1, emits, touched);
         entryCur = entryNext; hCur = hNext; entryNext = entryNext2;
     }
+    tmTotal.stop(f, CRB_TIMER_CoarseTotal);
 }
 
 //------------------------------------------------------------------------------------------------
@@ -619,22 +703,37 @@ inline int checkLaunch() { return cudaGetLastError() == cudaSuccess ? CRB_OK : C
 
 }  // namespace
 
-extern "C" int crb_launch_bin_raster(const crb_frame* f, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = launchChained(binScanKernel, f->numBins, kScanThreads, s, *f);
+namespace {
+template <int ProfMode>
+int launchBinRaster(const crb_frame* f, cudaStream_t s) {
+    cudaError_t e = launchChained(binScanKernel<ProfMode>, f->numBins, kScanThreads, s, *f);
     if (e == cudaSuccess && f->numTris > 0) {
         const int grid = (f->numChunks + kWarps - 1) / kWarps;
-        e = f->samplesLog2 == 0 ? launchChained(binScatterKernel<0>, grid, kThreads, s, *f) : launchChained(binScatterKernel<1>, grid, kThreads, s, *f);
+        e = f->samplesLog2 == 0 ? launchChained(binScatterKernel<0, ProfMode>, grid, kThreads, s, *f) : launchChained(binScatterKernel<1, ProfMode>, grid, kThreads, s, *f);
     }
     return e == cudaSuccess ? checkLaunch() : CRB_ERR_CUDA;
+}
+template <int ProfMode>
+int launchCoarseRaster(const crb_frame* f, cudaStream_t s) {
+    const int grid = max(1, (f->maxItems + kWarps - 1) / kWarps);
+    cudaError_t e = launchChained(coarseScanKernel<ProfMode>, f->numBins, kThreads * kScanGroups, s, *f);
+    if (e == cudaSuccess) e = f->samplesLog2 == 0 ? launchChained(coarseScatterKernel<0, ProfMode>, grid, kThreads, s, *f) : launchChained(coarseScatterKernel<1, ProfMode>, grid, kThreads, s, *f);
+    return e == cudaSuccess ? checkLaunch() : CRB_ERR_CUDA;
+}
+}  // namespace
+
+// The pipe's profiling mode (crb_frame::profilingMode, CR_PROFILING_MODE of the pipe's translation unit) picks the instrumented
+// instances: the default instances carry no profiling code.
+extern "C" int crb_launch_bin_raster(const crb_frame* f, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    return f->profilingMode == ProfilingMode_Counters ? launchBinRaster<ProfilingMode_Counters>(f, s)
+         : f->profilingMode == ProfilingMode_Timers ? launchBinRaster<ProfilingMode_Timers>(f, s) : launchBinRaster<ProfilingMode_Default>(f, s);
 }
 
 extern "C" int crb_launch_coarse_raster(const crb_frame* f, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    const int grid = max(1, (f->maxItems + kWarps - 1) / kWarps);
-    cudaError_t e = launchChained(coarseScanKernel, f->numBins, kThreads * kScanGroups, s, *f);
-    if (e == cudaSuccess) e = f->samplesLog2 == 0 ? launchChained(coarseScatterKernel<0>, grid, kThreads, s, *f) : launchChained(coarseScatterKernel<1>, grid, kThreads, s, *f);
-    return e == cudaSuccess ? checkLaunch() : CRB_ERR_CUDA;
+    return f->profilingMode == ProfilingMode_Counters ? launchCoarseRaster<ProfilingMode_Counters>(f, s)
+         : f->profilingMode == ProfilingMode_Timers ? launchCoarseRaster<ProfilingMode_Timers>(f, s) : launchCoarseRaster<ProfilingMode_Default>(f, s);
 }
 
 // Direct tile path: the two kernels that stand where the bin and coarse stages stand.

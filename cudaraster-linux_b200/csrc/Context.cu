@@ -297,6 +297,7 @@ int prepareFrame(crb_ctx* c) {
     CRB_CUDA(c, c->tileCursor.reserve(CR_MAXTILES_SQR * 4));
     CRB_CUDA(c, c->profCounters.reserve(CRB_PROF_WORDS * sizeof(unsigned long long)));
     f.profCounters = (unsigned long long*)c->profCounters.ptr;
+    f.profilingMode = c->spec.profilingMode;
     if (f.microMode) {
         const void* oldVis = c->visBuffer.ptr;
         const size_t need = (size_t)f.widthPixels * f.heightPixels * 8;
@@ -997,6 +998,20 @@ int crb_get_profiling_info(crb_ctx* c, char* buf, size_t bufSize) {
         snprintf(line, sizeof(line), "  - Vertex read      %4.1f%%\n", pct(CRB_TIMER_SetupVertexRead, CRB_TIMER_SetupTotal)); s += line;
         s += "- Marshal\n";
         snprintf(line, sizeof(line), "  - Bin histogram    %4.1f%%\n\n", pct(CRB_TIMER_SetupBinning, CRB_TIMER_SetupTotal)); s += line;
+        // bin / coarse stages (reference: cuda/PrivateDefs.hpp:221-248): the regions that exist in the count / scan / scatter kernels
+        s += "BinRaster:\n- Compute\n";
+        snprintf(line, sizeof(line), "  - Rasterize        %4.1f%%\n", pct(CRB_TIMER_BinRasterize, CRB_TIMER_BinTotal) - pct(CRB_TIMER_BinCountTiles, CRB_TIMER_BinTotal)); s += line;
+        s += "- Memory\n";
+        snprintf(line, sizeof(line), "  - Read tri header  %4.1f%%\n", pct(CRB_TIMER_BinReadTriHeader, CRB_TIMER_BinTotal)); s += line;
+        s += "- Marshal\n";
+        snprintf(line, sizeof(line), "  - Count emit       %4.1f%%\n", pct(CRB_TIMER_BinCountTiles, CRB_TIMER_BinTotal)); s += line;
+        snprintf(line, sizeof(line), "  - Allocate segs    %4.1f%%\n\n", pct(CRB_TIMER_BinScan, CRB_TIMER_BinTotal)); s += line;
+        s += "CoarseRaster:\n- Compute\n";
+        snprintf(line, sizeof(line), "  - Rasterize        %4.1f%%\n", pct(CRB_TIMER_CoarseRasterize, CRB_TIMER_CoarseTotal)); s += line;
+        s += "- Memory\n";
+        snprintf(line, sizeof(line), "  - Stream read      %4.1f%%\n", pct(CRB_TIMER_CoarseStreamRead, CRB_TIMER_CoarseTotal)); s += line;
+        s += "- Marshal\n";
+        snprintf(line, sizeof(line), "  - Count prefsum    %4.1f%%\n\n", pct(CRB_TIMER_CoarseScan, CRB_TIMER_CoarseTotal)); s += line;
         s += "FineRaster:\n";
         snprintf(line, sizeof(line), "- Shader             %4.1f%%\n", pct(CRB_TIMER_FineShade, CRB_TIMER_FineTotal)); s += line;
         s += "- Compute\n";
@@ -1023,12 +1038,30 @@ int crb_get_profiling_info(crb_ctx* c, char* buf, size_t bufSize) {
         snprintf(line, sizeof(line), "- Between pixels cull  %.1f%%\n", ratio(CRB_PROF_SetupBetweenPixelsCull)); s += line;
         snprintf(line, sizeof(line), "- Clipped              %.1f%%\n", ratio(CRB_PROF_SetupClipped)); s += line;
         snprintf(line, sizeof(line), "- Avg. samples / tri   %.2f\n\n", ratio(CRB_PROF_SetupSamplesPerTri)); s += line;
+        // bin / coarse stages: the reference's lines (cuda/PrivateDefs.hpp:168-187).  A "round" is one batch of 32 queue entries of a
+        // warp; the three coverage paths are the footprint classes of the scatter (one cell / at most 2x2 cells / edge-refined);
+        // there is no input ring buffer, no segment pool and no stream merge here, so those lines read 0.
         s += "BinRaster:\n";
-        snprintf(line, sizeof(line), "- Bin queue entries    %d\n", a.numBinEntries); s += line;
-        snprintf(line, sizeof(line), "- Entries / sub-tri    %.2f\n\n", (double)a.numBinEntries / std::max(a.numSubtris, 1)); s += line;
+        snprintf(line, sizeof(line), "- Input overflows      %.0f\n", 0.0); s += line;
+        snprintf(line, sizeof(line), "- Avg. triangles/round %.1f\n", ratio(CRB_PROF_BinTrisPerRound)); s += line;
+        snprintf(line, sizeof(line), "- Avg. tri bb size     %.1f\n", ratio(CRB_PROF_BinTriBBArea)); s += line;
+        snprintf(line, sizeof(line), "- Coverage single path %.1f%%\n", ratio(CRB_PROF_BinTriSinglePath)); s += line;
+        snprintf(line, sizeof(line), "- Coverage fast path   %.1f%%\n", ratio(CRB_PROF_BinTriFastPath)); s += line;
+        snprintf(line, sizeof(line), "- Coverage slow path   %.1f%%\n", ratio(CRB_PROF_BinTriSlowPath)); s += line;
+        snprintf(line, sizeof(line), "- Segment allocs/round %.1f\n", 0.0); s += line;
+        snprintf(line, sizeof(line), "- Bin queue entries    %d\n\n", a.numBinEntries); s += line;
         s += "CoarseRaster:\n";
-        snprintf(line, sizeof(line), "- Work items           %d\n", a.numCoarseItems); s += line;
-        snprintf(line, sizeof(line), "- Emits / Triangle     %.2f\n\n", (double)a.numTileEntries / std::max(a.numBinEntries, 1)); s += line;
+        snprintf(line, sizeof(line), "- Bins                 %.0f\n", (double)c->hostProf[2 * CRB_PROF_CoarseBins]); s += line;
+        snprintf(line, sizeof(line), "- Rounds / Bin         %.1f\n", ratio(CRB_PROF_CoarseRoundsPerBin)); s += line;
+        snprintf(line, sizeof(line), "- Merge / Round        %.1f\n", 0.0); s += line;
+        snprintf(line, sizeof(line), "- Triangles / Round    %.1f\n", ratio(CRB_PROF_CoarseTrisPerRound)); s += line;
+        snprintf(line, sizeof(line), "- Tiles / Round        %.1f\n", ratio(CRB_PROF_CoarseTilesPerRound)); s += line;
+        snprintf(line, sizeof(line), "- Emits / Round        %.1f\n", ratio(CRB_PROF_CoarseEmitsPerRound)); s += line;
+        snprintf(line, sizeof(line), "- Allocs / Round       %.1f\n", 0.0); s += line;
+        snprintf(line, sizeof(line), "- Emits / Triangle     %.2f\n", ratio(CRB_PROF_CoarseEmitsPerTri)); s += line;
+        snprintf(line, sizeof(line), "- Case A               %.0f%%\n", ratio(CRB_PROF_CoarseCaseA)); s += line;
+        snprintf(line, sizeof(line), "- Case B               %.0f%%\n", 0.0); s += line;
+        snprintf(line, sizeof(line), "- Case C               %.0f%%\n\n", ratio(CRB_PROF_CoarseCaseC)); s += line;
         s += "FineRaster:\n- Triangles culled\n";
         snprintf(line, sizeof(line), "  - Early Z kill       %.1f%%\n", ratio(CRB_PROF_FineEarlyZCull)); s += line;
         snprintf(line, sizeof(line), "  - Empty coverage     %.1f%%\n", ratio(CRB_PROF_FineEmptyCull)); s += line;

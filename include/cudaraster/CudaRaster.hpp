@@ -222,7 +222,7 @@ public:
     }
     std::string getProfilingInfo(void) {  // CudaRaster.cpp:367-497 (ProfilingMode_Default report)
         init();
-        char buf[2048];
+        char buf[8192];
         check(crb_get_profiling_info(m_ctx, buf, sizeof(buf)));
         return buf;
     }

@@ -41,12 +41,22 @@ typedef crb_atomics CRAtomics;
 enum {
     CRB_PROF_SetupViewportCull = 0, CRB_PROF_SetupBackfaceCull, CRB_PROF_SetupBetweenPixelsCull, CRB_PROF_SetupClipped, CRB_PROF_SetupSamplesPerTri,
     CRB_PROF_FineEarlyZCull, CRB_PROF_FineEmptyCull, CRB_PROF_FineZKill, CRB_PROF_FineMSAAKill, CRB_PROF_FineTriPerTile, CRB_PROF_FineFragPerTri,
-    CRB_PROF_FineFragPerTile, CRB_PROF_NUM
+    CRB_PROF_FineFragPerTile,
+    // bin / coarse stages (reference: cuda/PrivateDefs.hpp:168-187).  A "round" is one batch of 32 queue entries of a warp; the
+    // reference's three coverage paths map onto the footprint classes of scatterBatch: one cell / at most 2x2 cells / refined.
+    CRB_PROF_BinTrisPerRound, CRB_PROF_BinTriBBArea, CRB_PROF_BinTriSinglePath, CRB_PROF_BinTriFastPath, CRB_PROF_BinTriSlowPath,
+    CRB_PROF_CoarseBins, CRB_PROF_CoarseRoundsPerBin, CRB_PROF_CoarseTrisPerRound, CRB_PROF_CoarseTilesPerRound, CRB_PROF_CoarseEmitsPerRound, CRB_PROF_CoarseEmitsPerTri,
+    CRB_PROF_CoarseCaseA, CRB_PROF_CoarseCaseC,
+    CRB_PROF_NUM
 };
 // ProfilingMode_Timers (reference: CR_PROFILING_TIMERS, cuda/PrivateDefs.hpp:207-270): clock totals, stored behind the counters
 enum {
     CRB_TIMER_SetupTotal = 0, CRB_TIMER_SetupVertexRead, CRB_TIMER_SetupCullSnap, CRB_TIMER_SetupPleq, CRB_TIMER_SetupClip, CRB_TIMER_SetupBinning,
-    CRB_TIMER_FineTotal, CRB_TIMER_FineReadTile, CRB_TIMER_FinePixelCoverage, CRB_TIMER_FineZKill, CRB_TIMER_FineShade, CRB_TIMER_FineWriteTile, CRB_TIMER_NUM
+    CRB_TIMER_FineTotal, CRB_TIMER_FineReadTile, CRB_TIMER_FinePixelCoverage, CRB_TIMER_FineZKill, CRB_TIMER_FineShade, CRB_TIMER_FineWriteTile,
+    // bin stage: scan kernel (one CTA per bin) + scatter kernel (one warp per chunk); coarse stage likewise
+    CRB_TIMER_BinTotal, CRB_TIMER_BinScan, CRB_TIMER_BinReadTriHeader, CRB_TIMER_BinRasterize, CRB_TIMER_BinCountTiles,
+    CRB_TIMER_CoarseTotal, CRB_TIMER_CoarseScan, CRB_TIMER_CoarseStreamRead, CRB_TIMER_CoarseRasterize,
+    CRB_TIMER_NUM
 };
 #define CRB_PROF_WORDS (2 * CRB_PROF_NUM + CRB_TIMER_NUM)
 
@@ -139,6 +149,7 @@ struct crb_frame {
                                   // tile x0 | y0 << 8 | (nx-1) << 16 | (ny-1) << 17 | 1 << 31 of a footprint of at most 2x2 tiles
 
     unsigned long long* profCounters;   // [CRB_PROF_WORDS]: counter pairs, then timers; zeroed before every frame of a profiling pipe
+    int32_t profilingMode;              // the pipe's CR_PROFILING_MODE: picks the instrumented instances of the bin / coarse kernels (they live in the library)
 
     crb_atomics* atomics;         // counters of THIS frame (zero when the frame starts)
     crb_atomics* nextAtomics;     // counters of the next frame: zeroed by this frame's fine raster kernel

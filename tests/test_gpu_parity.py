@@ -528,6 +528,19 @@ def test_profiling_mode_counters(raster, crb, samples_log2):
     # culled = viewport + backface + between-pixels culls of unclipped triangles + clipped triangles that vanished
     assert abs((val["Viewport cull"] + val["Backface cull"] + val["Between pixels cull"]) - 100.0 * ((sub == 0).sum() - 0) / len(sub)) < val["Clipped"] + 0.1
     assert val["Clipped"] > 5.0 and val["Avg. tri/tile"] > 1 and val["Avg. frag/tri"] > 1
+    # bin / coarse stages (reference: cuda/PrivateDefs.hpp:168-187): every line of the reference's report, sane values
+    assert "BinRaster:" in info and "CoarseRaster:" in info
+    for k in ("Input overflows", "Avg. triangles/round", "Avg. tri bb size", "Coverage single path", "Coverage fast path", "Coverage slow path", "Segment allocs/round",
+              "Bins", "Rounds / Bin", "Merge / Round", "Triangles / Round", "Tiles / Round", "Emits / Round", "Allocs / Round", "Emits / Triangle", "Case A", "Case B", "Case C"):
+        assert k in val, k
+    assert 0 < val["Avg. triangles/round"] <= 32 and val["Avg. tri bb size"] >= 1.0
+    assert abs(val["Coverage single path"] + val["Coverage fast path"] + val["Coverage slow path"] - 100.0) < 0.5 and val["Coverage slow path"] > 0.0
+    nbins = ((w + 127) // 128) * ((h + 127) // 128)
+    assert 1 <= val["Bins"] <= nbins and val["Rounds / Bin"] >= 1 and 0 < val["Triangles / Round"] <= 32
+    assert val["Emits / Triangle"] >= 0.5 and val["Tiles / Round"] >= 1 and val["Emits / Round"] >= val["Tiles / Round"]
+    assert abs(val["Case A"] + val["Case C"] - 100.0) <= 1.0 and val["Case B"] == 0
+    c2 = raster.getCounters()
+    assert abs(val["Emits / Round"] * val["Rounds / Bin"] * val["Bins"] - c2["numTileEntries"]) <= 0.06 * c2["numTileEntries"] + 64      # the counters add up to the queue
     c = g["counts"]
     tiles = ((w + 7) // 8) * ((h + 7) // 8)
     if samples_log2 == 0:   # fragments the fine raster saw = all covered (triangle, pixel) pairs minus those of early-Z-culled triangles
@@ -692,9 +705,12 @@ def test_profiling_mode_timers(raster, crb):
     info = raster.getProfilingInfo()
     _check_surfaces(cc, cd, util.draw_gold(v, i, w, h, "gouraud", 3), lsb=1)
     assert "ProfilingMode_Timers" in info and "TriangleSetup:" in info and "FineRaster:" in info
-    vals = [float(x) for x in re.findall(r"([0-9.]+)%", info)]
-    assert len(vals) == 10 and all(0.0 <= x <= 100.0 for x in vals)
-    assert sum(vals[:5]) > 20.0 and sum(vals[5:]) > 20.0 and sum(vals[:5]) <= 100.5 and sum(vals[5:]) <= 100.5
+    assert "BinRaster:" in info and "CoarseRaster:" in info
+    vals = [float(x) for x in re.findall(r"(-?[0-9.]+)%", info)]
+    assert len(vals) == 17 and all(-0.5 <= x <= 100.5 for x in vals), vals
+    setup, binr, coarse, fine = vals[:5], vals[5:9], vals[9:12], vals[12:]
+    assert sum(setup) > 20.0 and sum(fine) > 20.0 and sum(setup) <= 100.5 and sum(fine) <= 100.5
+    assert 20.0 < sum(binr) <= 100.5 and 20.0 < sum(coarse) <= 100.5
 
 
 def test_sort_first_chunk_bounds_cull(raster, crb):
