@@ -333,6 +333,7 @@ struct FineBatch {
 template <class VertexClass, class FragmentShaderClass, class BlendShaderClass, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER_SM / CRB_FINE_WARPS) fineRasterSingleKernel(const __grid_constant__ crb_frame f) {
     __shared__ FineBatch s_batch[CRB_FINE_WARPS];
+    __shared__ __align__(128) U32 s_tileStage[CRB_FINE_WARPS][CR_TILE_SQR];   // tile-major colour surfaces: staging of the tile for the bulk store
 
     constexpr bool kDepth = (RenderModeFlags & RenderModeFlag_EnableDepth) != 0;
     constexpr bool kQuads = (RenderModeFlags & RenderModeFlag_EnableQuads) != 0;
@@ -588,8 +589,24 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         }
     }
 
-    colorPtr[0] = color[0];
-    colorPtr[colorStep] = color[1];
+    if (f.colorTiled) {
+        // Tile-major colour surface (a frame slot in a peer GPU's memory): the tile's 64 texels are contiguous, so the warp stages
+        // them in shared memory and ONE lane hands the 256 bytes to the bulk-copy engine (cp.async.bulk shared -> global, TMA):
+        // the tile crosses NVLink as one 256-byte write instead of 64 four-byte stores.
+        U32* const st = s_tileStage[warp];
+        st[lane] = color[0];
+        st[lane + 32] = color[1];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy stores above, before the async proxy reads them
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;" ::"l"(f.colorBuffer + (size_t)tileIdx * CR_TILE_SQR), "r"((U32)__cvta_generic_to_shared(st)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging buffer must outlive the read
+        }
+    } else {
+        colorPtr[0] = color[0];
+        colorPtr[colorStep] = color[1];
+    }
     if (kDepth || f.deferredClear) {
         depthPtr[0] = depth[0];
         depthPtr[rowStep] = depth[1];

@@ -201,18 +201,30 @@ __device__ __forceinline__ void gridDepWait() { asm volatile("griddepcontrol.wai
 
 // (static: every shared object must launch through ITS OWN copy -- nvcc links the CUDA runtime statically
 // into each of them, and a kernel can only be launched by the runtime instance it is registered with)
+// clusterSize > 1: the grid is launched as thread-block clusters of that many CTAs (distributed shared memory between them).
 template <class Kernel>
-static inline cudaError_t launchChained(Kernel kernel, int grid, int block, cudaStream_t stream, const crb_frame& f) {
+static inline cudaError_t launchChained(Kernel kernel, int grid, int block, cudaStream_t stream, const crb_frame& f, int clusterSize = 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (f.chainLaunches) {   // 0 = plain stream order (CRB_NO_PDL=1, a debugging aid)
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (clusterSize > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)clusterSize;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        n++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = f.chainLaunches ? 1 : 0;   // 0 = plain stream order (CRB_NO_PDL=1, a debugging aid)
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, f);
 }
 
