@@ -98,7 +98,12 @@ __device__ __forceinline__ void computeBarys(Vec3f& bary, Vec3f& baryDX, Vec3f& 
 // half-sample position of the shading point inside the pixel (low nibble x, high nibble y).
 template <class VertexClass, class FragmentShaderClass, int SamplesLog2, U32 RenderModeFlags>
 __device__ __forceinline__ void runFragmentShader(FragmentShaderClass& fs, const crb_frame& f, int triIdx, int dataIdx, int pixelX, int pixelY, U32 centroid) {
+#if CRB_WIDE_LD
+    uint4 t2, t3;   // rows 2 and 3 of the record in ONE 256-bit gather: uy, ub, vx, vy | vb, vi0, vi1, vi2
+    ldg256(&f.triData[(size_t)dataIdx * 4 + 2], t2, t3);
+#else
     const uint4 t3 = __ldg(&f.triData[(size_t)dataIdx * 4 + 3]);  // vb, vi0, vi1, vi2
+#endif
     // quads mode: the caller runs this converged on the four lanes of the pixel's 2x2 quad
     fs.m_quadMask = (RenderModeFlags & RenderModeFlag_EnableQuads) != 0 ? quadLaneMask() : (1u << laneId());
     fs.m_triIdx = triIdx;
@@ -116,7 +121,9 @@ __device__ __forceinline__ void runFragmentShader(FragmentShaderClass& fs, const
         fs.m_centroidDX = Vec3f(0.0f); fs.m_centroidDY = Vec3f(0.0f);
     } else {
         const uint4 t1 = __ldg(&f.triData[(size_t)dataIdx * 4 + 1]);  // wx, wy, wb, ux
+#if !CRB_WIDE_LD
         const uint4 t2 = __ldg(&f.triData[(size_t)dataIdx * 4 + 2]);  // uy, ub, vx, vy
+#endif
         const int3 wp = make_int3((S32)t1.x, (S32)t1.y, (S32)t1.z);
         const int3 up = make_int3((S32)t1.w, (S32)t2.x, (S32)t2.y);
         const int3 vp = make_int3((S32)t2.z, (S32)t2.w, (S32)t3.x);
@@ -358,12 +365,15 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         const int t = min(activeIdx, f.numTiles - 1);
 #endif
         rec = make_int4(t, __ldg(&f.tileStart[t]), __ldg(&f.tileCount[t]), 0);
-        const int ty = t / f.widthTiles, tx = t - ty * f.widthTiles;
-        vis = f.visBuffer + (size_t)((ty << CR_TILE_LOG2) + (lane >> 3)) * f.widthPixels + (tx << CR_TILE_LOG2) + (lane & 7);
-        v0 = vis[0];
-        v1 = vis[(size_t)4 * f.widthPixels];
     } else {
         rec = __ldg(&f.activeRecs[activeIdx]);
+    }
+    const int tileIdx = rec.x;
+    const int tileY = tileIdx / f.widthTiles, tileX = tileIdx - tileY * f.widthTiles;   // (the kernel's one integer division)
+    if (f.microMode != 0) {
+        vis = f.visBuffer + (size_t)((tileY << CR_TILE_LOG2) + (lane >> 3)) * f.widthPixels + (tileX << CR_TILE_LOG2) + (lane & 7);
+        v0 = vis[0];
+        v1 = vis[(size_t)4 * f.widthPixels];
     }
     if (f.atomics->overflow != 0) return;
     if (f.microMode != 0) {
@@ -378,8 +388,6 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     tm.start();
 
     FineBatch& sb = s_batch[warp];
-    const int tileIdx = rec.x;
-    const int tileY = tileIdx / f.widthTiles, tileX = tileIdx - tileY * f.widthTiles;
     const int queueStart = rec.y;
     const int queueCount = rec.z;
     const S32* __restrict__ queue = f.tileQueue + queueStart;

@@ -83,6 +83,7 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
     // or its depth-plane row: only the shading rows (w/u/v planes, vertex ids) are produced.
     F32 areaRcp = 0.0f;
     int2 wv0 = make_int2(0, 0);
+    uint4 row0 = make_uint4(0, 0, 0, 0), row1 = row0, row2 = row0, row3 = row0;   // the triData record
     if ((RenderModeFlags & (CRB_FLAG_DEPTH | CRB_FLAG_LERP)) != 0) {
         areaRcp = __frcp_rn((F32)area);
         // Plane equations are set up in viewport-corner coordinates (the reference's wv0) and, for
@@ -113,7 +114,7 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
             if ((zslope >> k) != tmp) zslope = FW_U32_MAX;
         }
         zp.z += zp.x * ((U32)f.subX0 << SamplesLog2) + zp.y * ((U32)f.subY0 << SamplesLog2);
-        if (!microOnly) td[0] = make_uint4(zp.x, zp.y, zp.z, zslope);
+        row0 = make_uint4(zp.x, zp.y, zp.z, zslope);
         if (zpOut) *zpOut = zp;
     }
 
@@ -135,11 +136,24 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
         wp.z += wp.x * ox2 + wp.y * oy2;
         up.z += up.x * ox2 + up.y * oy2;
         vp.z += vp.x * ox2 + vp.y * oy2;
-        td[1] = make_uint4(wp.x, wp.y, wp.z, up.x);
-        td[2] = make_uint4(up.y, up.z, vp.x, vp.y);
-        td[3] = make_uint4(vp.z, (U32)vidx.x, (U32)vidx.y, (U32)vidx.z);
+        row1 = make_uint4(wp.x, wp.y, wp.z, up.x);
+        row2 = make_uint4(up.y, up.z, vp.x, vp.y);
+        row3 = make_uint4(vp.z, (U32)vidx.x, (U32)vidx.y, (U32)vidx.z);
     } else {
-        td[3] = make_uint4(0u, (U32)vidx.x, (U32)vidx.y, (U32)vidx.z);
+        row3 = make_uint4(0u, (U32)vidx.x, (U32)vidx.y, (U32)vidx.z);
+    }
+    if (CRB_WIDE_ST && Unclipped && (CRB_WIDE_ST > 1 || microOnly)) {
+        // A micro triangle's record leaves as two whole 32-byte sectors, depth row included although nothing reads it: a
+        // half-written sector costs a DRAM fill when L2 evicts it (C2: fine raster 39.1 -> 37.4 us, setup unchanged).  Records
+        // that carry all four rows anyway stay on four 128-bit stores: as 256-bit stores C3's setup took 252 instead of 225 us.
+        // Fast path only: inside a non-inlined function (the clipper's cold path) ptxas 12.9 turns st.global.v8.b32 into a
+        // 32-bit store of the first element (found by the MSAA soup: words 1-7 of every clipped record came out zero).
+        stg256(td, row0, row1);
+        stg256(td + 2, row2, row3);
+    } else {
+        if ((RenderModeFlags & CRB_FLAG_DEPTH) != 0 && !microOnly) td[0] = row0;
+        if ((RenderModeFlags & CRB_FLAG_LERP) != 0) { td[1] = row1; td[2] = row2; }
+        td[3] = row3;
     }
 
     if (microOnly) return make_uint4(0, 0, 0, 0);
@@ -158,6 +172,14 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
 // (depth << 32 | entry + 1) into the visibility buffer -- and is never queued.  Kept out of line so that its
 // registers do not weigh on the setup kernel.  (x*, y*) = snapped vertices, viewport-centred subpixels (what the
 // header would hold); (pxLo*, n*) = its pixel rectangle in surface pixels.
+// Fire-and-forget 64-bit minimum on a GLOBAL address.  (atomicMin through a pointer read from the frame block inside a
+// non-inlined function is a GENERIC atomic: nvcc emits ATOM.E.MIN.64 with a predicate result, waits for it, and branches
+// into a shared-memory CAS fallback -- one L2 round trip per covered pixel on the thread's critical path.  red.global has
+// no result and no window check: REDG.E.MIN.64.)
+__device__ __forceinline__ void redMinGlobalU64(unsigned long long* gptr, unsigned long long v) {
+    asm volatile("red.global.min.u64 [%0], %1;" ::"l"(gptr), "l"(v));
+}
+
 static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 y0, S32 x1, S32 y1, S32 x2, S32 y2, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX,
                                                 S32 pxLoY, int nx, int ny) {
     // centre of pixel (pxLoX, pxLoY) in viewport-centred subpixels
@@ -169,7 +191,8 @@ static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 
     const S32 a0 = -(dy0 << CR_SUBPIXEL_LOG2), a1 = -(dy1 << CR_SUBPIXEL_LOG2), a2 = -(dy2 << CR_SUBPIXEL_LOG2);
     const S32 b0 = dx0 << CR_SUBPIXEL_LOG2, b1 = dx1 << CR_SUBPIXEL_LOG2, b2 = dx2 << CR_SUBPIXEL_LOG2;
     const unsigned long long id = (unsigned long long)(U32)(entry + 1);
-    unsigned long long* row = f.visBuffer + (size_t)pxLoY * f.widthPixels + pxLoX;
+    const size_t pitch = (size_t)f.widthPixels;
+    unsigned long long* row = reinterpret_cast<unsigned long long*>(__cvta_generic_to_global(f.visBuffer)) + (size_t)pxLoY * pitch + pxLoX;
     U32 zrow = zb + zx * (U32)pxLoX + zy * (U32)pxLoY;
 #pragma unroll 1
     for (int r = 0; r < ny; r++) {
@@ -177,13 +200,13 @@ static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 
         U32 z = zrow;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            if (c < nx && (t0 | t1 | t2) >= 0) atomicMin(row + c, ((unsigned long long)z << 32) | id);
+            if (c < nx && (t0 | t1 | t2) >= 0) redMinGlobalU64(row + c, ((unsigned long long)z << 32) | id);
             t0 += a0; t1 += a1; t2 += a2;
             z += zx;
         }
         e0 += b0; e1 += b1; e2 += b2;
         zrow += zy;
-        row += f.widthPixels;
+        row += pitch;
     }
 }
 
@@ -399,12 +422,14 @@ __device__ __forceinline__ U32 setupOneTriangle(const crb_frame& f, int tri, int
 template <class VertexClass, int SamplesLog2, U32 RenderModeFlags, int ProfMode = ProfilingMode_Default>
 static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS) triangleSetupKernel(const __grid_constant__ crb_frame f) {
     __shared__ SetupCtaShared scratch;
-    __shared__ int s_queuedAny;
+    __shared__ int s_queuedAny[CRB_SETUP_THREADS / 32];   // per WARP = per batch of 32 triangles (crb_frame::batchQueued)
+    __shared__ int s_ctaQueued;                            // the first warp of the CTA that queued something counts the CTA
     int* const s_binCount = scratch.binCount;
-    const SetupShared sh = {&s_queuedAny, &scratch};
+    const SetupShared sh = {&s_queuedAny[threadIdx.x >> 5], &scratch};
     gridDepLaunchDependents();
     for (int i = threadIdx.x; i < CR_MAXBINS_SQR; i += CRB_SETUP_THREADS) s_binCount[i] = 0;
-    if (threadIdx.x == 0) s_queuedAny = 0;
+    if ((threadIdx.x & 31) == 0) s_queuedAny[threadIdx.x >> 5] = 0;
+    if (threadIdx.x == 0) s_ctaQueued = 0;
     __syncthreads();
     gridDepWait();   // the previous frame's kernels still read the work buffers written below
 
@@ -448,16 +473,22 @@ static __global__ void __launch_bounds__(CRB_SETUP_THREADS, CRB_SETUP_MIN_BLOCKS
         profCountWarp<ProfMode>(f, CRB_PROF_SetupClipped, (prof & 16) != 0, (prof & 1) != 0);
         profCountWarp<ProfMode>(f, CRB_PROF_SetupSamplesPerTri, false, (prof & 32) != 0);   // denominator: triangles that survive setup (the fine raster adds the samples)
     }
-    // publish this CTA's bin histogram: one column of binCountMat[bin][chunk]
-    __syncthreads();
     if (f.directMode) {
-        // One word per triangle for the scatter pass -- but only where something was queued: a batch of 32 triangles that were all
-        // culled or rasterized right here (every batch of a micro-triangle frame) leaves ONE byte instead of 128 B of zeros.
-        if (s_queuedAny != 0 && tri < f.numTris) f.triTileCode[tri] = tileCode;
-        if ((threadIdx.x & 31) == 0 && tri < f.numTris) f.batchQueued[tri >> 5] = (uint8_t)(s_queuedAny != 0);
-        if (threadIdx.x == 0 && s_queuedAny != 0) atomicAdd(&f.atomics->numQueuedCtas, 1);
+        // One word per triangle for the scatter pass -- but only where something was queued: a batch of 32 triangles (= this warp)
+        // that were all culled or rasterized right here (every batch of a micro-triangle frame) leaves ONE byte instead of 128 B
+        // of zeros.  Everything here is warp-local: no CTA barrier at the end of the kernel on this path.
+        __syncwarp();
+        const int queued = *sh.queuedAny;
+        if (queued != 0 && tri < f.numTris) f.triTileCode[tri] = tileCode;
+        if ((threadIdx.x & 31) == 0 && tri < f.numTris) {
+            f.batchQueued[tri >> 5] = (uint8_t)(queued != 0);
+            // one global atomic per CTA, not per warp: 156 000 atomics on ONE address cost C3's setup 45 us
+            if (queued != 0 && atomicExch(&s_ctaQueued, 1) == 0) atomicAdd(&f.atomics->numQueuedCtas, 1);
+        }
         return;
     }
+    // publish this CTA's bin histogram: one column of binCountMat[bin][chunk]
+    __syncthreads();
     int* col = f.binCountMat + blockIdx.x / f.ctasPerChunk;
     if (f.ctasPerChunk == 1) {
         for (int b = threadIdx.x; b < f.numBins; b += CRB_SETUP_THREADS) col[(size_t)b * f.matPitch] = s_binCount[b];

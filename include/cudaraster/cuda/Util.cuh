@@ -24,6 +24,31 @@ __host__ __device__ __forceinline__ int msaaSampleX(int samplesLog2, int i) {
 
 #ifdef __CUDACC__
 
+// ---- 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256, PTX ISA 8.8 .v8.b32) ----------------------
+// A 64-byte triData record is two 32-byte halves {row 0, row 1} / {row 2, row 3}.  One 256-bit access per half instead of
+// one 128-bit access per row: half the L1 wavefronts of the record gathers (the fine raster is bound by them: ncu
+// l1tex__data_pipe_lsu_wavefronts) and whole 32-byte sectors on the way out (no partial-sector fills in L2).
+// The address must be 32-byte aligned and global.
+#ifndef CRB_WIDE_LDST
+#define CRB_WIDE_LDST 1
+#endif
+#ifndef CRB_WIDE_LD
+#define CRB_WIDE_LD CRB_WIDE_LDST
+#endif
+#ifndef CRB_WIDE_ST
+#define CRB_WIDE_ST CRB_WIDE_LDST
+#endif
+__device__ __forceinline__ void ldg256(const uint4* p, uint4& a, uint4& b) {
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+        : "l"(__cvta_generic_to_global(p)));
+}
+__device__ __forceinline__ void stg256(uint4* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(__cvta_generic_to_global(p)), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                 "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // ---- conversions with PTX semantics -----------------------------------------------------------
 __device__ __forceinline__ S32 f32ToS32SatRni(F32 a) { return __float2int_rn(a); }     // cvt.rni.sat.s32 (CUDA's float->int intrinsics saturate, NaN -> 0)
 __device__ __forceinline__ U32 f32ToU32SatRni(F32 a) { return __float2uint_rn(a); }    // cvt.rni.sat.u32
