@@ -179,8 +179,26 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
 __device__ __forceinline__ void redMinGlobalU64(unsigned long long* gptr, unsigned long long v) {
     asm volatile("red.global.min.u64 [%0], %1;" ::"l"(gptr), "l"(v));
 }
+// The same under a predicate (cond != 0), without a branch around it: @P REDG.E.MIN.64.
+__device__ __forceinline__ void redMinGlobalU64If(bool cond, unsigned long long* gptr, U32 hi, U32 lo) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 v;\n\tsetp.ne.b32 p, %0, 0;\n\tmov.b64 v, {%3, %2};\n\t@p red.global.min.u64 [%1], v;\n\t}" ::"r"((U32)cond), "l"(gptr),
+        "r"(hi), "r"(lo));
+}
 
-static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 y0, S32 x1, S32 y1, S32 x2, S32 y2, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX,
+#ifndef CRB_MICRO_PRED
+#define CRB_MICRO_PRED 1   // micro raster: predicated reductions in a straight-line row body (0: a branch around every reduction)
+#endif
+
+#ifndef CRB_MICRO_INLINE
+#define CRB_MICRO_INLINE 1   // inlined: no call, no R2UR descriptor shuffling, frame fields from the constant bank (0: the out-of-line version)
+#endif
+#if CRB_MICRO_INLINE
+#define CRB_MICRO_ATTR __forceinline__
+#else
+#define CRB_MICRO_ATTR __noinline__
+#endif
+static __device__ CRB_MICRO_ATTR void microRaster(const crb_frame& f, S32 x0, S32 y0, S32 x1, S32 y1, S32 x2, S32 y2, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX,
                                                 S32 pxLoY, int nx, int ny) {
     // centre of pixel (pxLoX, pxLoY) in viewport-centred subpixels
     const S32 px = (pxLoX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originX, py = (pxLoY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
@@ -190,10 +208,28 @@ static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 
     S32 e2 = (x0 - px) * dy2 - (y0 - py) * dx2 - ((dy2 > 0 || (dy2 == 0 && dx2 <= 0)) ? 1 : 0);
     const S32 a0 = -(dy0 << CR_SUBPIXEL_LOG2), a1 = -(dy1 << CR_SUBPIXEL_LOG2), a2 = -(dy2 << CR_SUBPIXEL_LOG2);
     const S32 b0 = dx0 << CR_SUBPIXEL_LOG2, b1 = dx1 << CR_SUBPIXEL_LOG2, b2 = dx2 << CR_SUBPIXEL_LOG2;
-    const unsigned long long id = (unsigned long long)(U32)(entry + 1);
     const size_t pitch = (size_t)f.widthPixels;
     unsigned long long* row = reinterpret_cast<unsigned long long*>(__cvta_generic_to_global(f.visBuffer)) + (size_t)pxLoY * pitch + pxLoX;
     U32 zrow = zb + zx * (U32)pxLoX + zy * (U32)pxLoY;
+#if CRB_MICRO_PRED
+    const U32 id = (U32)(entry + 1);
+#pragma unroll 1
+    for (int r = 0; r < ny; r++) {
+        // column c of the row: e_i + c * a_i; the sign of the OR of the three is the coverage test
+        const S32 m0 = e0 | e1 | e2;
+        const S32 m1 = (e0 + a0) | (e1 + a1) | (e2 + a2);
+        const S32 m2 = (e0 + 2 * a0) | (e1 + 2 * a1) | (e2 + 2 * a2);
+        const S32 m3 = (e0 + 3 * a0) | (e1 + 3 * a1) | (e2 + 3 * a2);
+        redMinGlobalU64If(m0 >= 0, row, zrow, id);
+        redMinGlobalU64If((m1 >= 0) & (nx > 1), row + 1, zrow + zx, id);
+        redMinGlobalU64If((m2 >= 0) & (nx > 2), row + 2, zrow + 2 * zx, id);
+        redMinGlobalU64If((m3 >= 0) & (nx > 3), row + 3, zrow + 3 * zx, id);
+        e0 += b0; e1 += b1; e2 += b2;
+        zrow += zy;
+        row += pitch;
+    }
+#else
+    const unsigned long long id = (unsigned long long)(U32)(entry + 1);
 #pragma unroll 1
     for (int r = 0; r < ny; r++) {
         S32 t0 = e0, t1 = e1, t2 = e2;
@@ -208,6 +244,7 @@ static __device__ __noinline__ void microRaster(const crb_frame& f, S32 x0, S32 
         zrow += zy;
         row += pitch;
     }
+#endif
 }
 
 // What binning needs from a finished sub-triangle (header h, queue entry `entry`, stored in record `slot`).  General path: the
