@@ -166,40 +166,25 @@ __device__ __forceinline__ uint4 setupTriangle(const crb_frame& f, uint4* th, ui
     return h;
 }
 
-// Micro-triangle path (crb_frame::microMode): a sub-triangle whose pixel-centre footprint is at most 4x4 pixels is
-// rasterized right here -- exact coverage of its <= 16 candidate pixels (the fine raster's own small-triangle
-// evaluation, FineRaster.cuh coverSmall4x4), plane depth per covered pixel, 64-bit atomicMin of
-// (depth << 32 | entry + 1) into the visibility buffer -- and is never queued.  Kept out of line so that its
-// registers do not weigh on the setup kernel.  (x*, y*) = snapped vertices, viewport-centred subpixels (what the
-// header would hold); (pxLo*, n*) = its pixel rectangle in surface pixels.
-// Fire-and-forget 64-bit minimum on a GLOBAL address.  (atomicMin through a pointer read from the frame block inside a
-// non-inlined function is a GENERIC atomic: nvcc emits ATOM.E.MIN.64 with a predicate result, waits for it, and branches
-// into a shared-memory CAS fallback -- one L2 round trip per covered pixel on the thread's critical path.  red.global has
-// no result and no window check: REDG.E.MIN.64.)
-__device__ __forceinline__ void redMinGlobalU64(unsigned long long* gptr, unsigned long long v) {
-    asm volatile("red.global.min.u64 [%0], %1;" ::"l"(gptr), "l"(v));
-}
-// The same under a predicate (cond != 0), without a branch around it: @P REDG.E.MIN.64.
+// Fire-and-forget 64-bit minimum on a GLOBAL address, under a predicate.  (atomicMin through a pointer read from the frame
+// block inside a non-inlined function is a GENERIC atomic: nvcc emits ATOM.E.MIN.64 with a predicate result, waits for it, and
+// branches into a shared-memory CAS fallback -- one L2 round trip per covered pixel on the thread's critical path.  red.global
+// has no result and no window check: REDG.E.MIN.64.)  v = hi << 32 | lo.
 __device__ __forceinline__ void redMinGlobalU64If(bool cond, unsigned long long* gptr, U32 hi, U32 lo) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 v;\n\tsetp.ne.b32 p, %0, 0;\n\tmov.b64 v, {%3, %2};\n\t@p red.global.min.u64 [%1], v;\n\t}" ::"r"((U32)cond), "l"(gptr),
         "r"(hi), "r"(lo));
 }
 
-#ifndef CRB_MICRO_PRED
-#define CRB_MICRO_PRED 1   // micro raster: predicated reductions in a straight-line row body (0: a branch around every reduction)
-#endif
-
-#ifndef CRB_MICRO_INLINE
-#define CRB_MICRO_INLINE 1   // inlined: no call, no R2UR descriptor shuffling, frame fields from the constant bank (0: the out-of-line version)
-#endif
-#if CRB_MICRO_INLINE
-#define CRB_MICRO_ATTR __forceinline__
-#else
-#define CRB_MICRO_ATTR __noinline__
-#endif
-static __device__ CRB_MICRO_ATTR void microRaster(const crb_frame& f, S32 x0, S32 y0, S32 x1, S32 y1, S32 x2, S32 y2, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX,
-                                                S32 pxLoY, int nx, int ny) {
+// Micro-triangle path (crb_frame::microMode): a sub-triangle whose pixel-centre footprint is at most 4x4 pixels is
+// rasterized right here -- exact coverage of its <= 16 candidate pixels (the fine raster's own small-triangle
+// evaluation, FineRaster.cuh coverSmall4x4), plane depth per covered pixel, 64-bit minimum of
+// (depth << 32 | entry + 1) into the visibility buffer -- and is never queued.  Inlined into the setup kernel: out of line it
+// re-read the frame fields through generic loads and moved the global-memory descriptor into uniform registers before every
+// reduction (C2 setup 39.8 -> 37.7 us inlined, at the same 48 registers).  (x*, y*) = snapped vertices, viewport-centred
+// subpixels (what the header would hold); (pxLo*, n*) = its pixel rectangle in surface pixels.
+static __device__ __forceinline__ void microRaster(const crb_frame& f, S32 x0, S32 y0, S32 x1, S32 y1, S32 x2, S32 y2, U32 zx, U32 zy, U32 zb, S32 entry, S32 pxLoX,
+                                                   S32 pxLoY, int nx, int ny) {
     // centre of pixel (pxLoX, pxLoY) in viewport-centred subpixels
     const S32 px = (pxLoX << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originX, py = (pxLoY << CR_SUBPIXEL_LOG2) + (CR_SUBPIXEL_SIZE >> 1) - f.originY;
     const S32 dx0 = x1 - x0, dy0 = y1 - y0, dx1 = x2 - x1, dy1 = y2 - y1, dx2 = x0 - x2, dy2 = y0 - y2;
@@ -211,7 +196,6 @@ static __device__ CRB_MICRO_ATTR void microRaster(const crb_frame& f, S32 x0, S3
     const size_t pitch = (size_t)f.widthPixels;
     unsigned long long* row = reinterpret_cast<unsigned long long*>(__cvta_generic_to_global(f.visBuffer)) + (size_t)pxLoY * pitch + pxLoX;
     U32 zrow = zb + zx * (U32)pxLoX + zy * (U32)pxLoY;
-#if CRB_MICRO_PRED
     const U32 id = (U32)(entry + 1);
 #pragma unroll 1
     for (int r = 0; r < ny; r++) {
@@ -228,23 +212,6 @@ static __device__ CRB_MICRO_ATTR void microRaster(const crb_frame& f, S32 x0, S3
         zrow += zy;
         row += pitch;
     }
-#else
-    const unsigned long long id = (unsigned long long)(U32)(entry + 1);
-#pragma unroll 1
-    for (int r = 0; r < ny; r++) {
-        S32 t0 = e0, t1 = e1, t2 = e2;
-        U32 z = zrow;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            if (c < nx && (t0 | t1 | t2) >= 0) redMinGlobalU64(row + c, ((unsigned long long)z << 32) | id);
-            t0 += a0; t1 += a1; t2 += a2;
-            z += zx;
-        }
-        e0 += b0; e1 += b1; e2 += b2;
-        zrow += zy;
-        row += pitch;
-    }
-#endif
 }
 
 // What binning needs from a finished sub-triangle (header h, queue entry `entry`, stored in record `slot`).  General path: the
