@@ -120,7 +120,7 @@ __device__ __forceinline__ void runFragmentShader(FragmentShaderClass& fs, const
         fs.m_centroid = Vec3f(0.0f, 0.0f, 1.0f);
         fs.m_centroidDX = Vec3f(0.0f); fs.m_centroidDY = Vec3f(0.0f);
     } else {
-        const uint4 t1 = __ldg(&f.triData[(size_t)dataIdx * 4 + 1]);  // wx, wy, wb, ux
+        const uint4 t1 = ldg128Record(&f.triData[(size_t)dataIdx * 4 + 1]);  // wx, wy, wb, ux
 #if !CRB_WIDE_LD
         const uint4 t2 = __ldg(&f.triData[(size_t)dataIdx * 4 + 2]);  // uy, ub, vx, vy
 #endif
@@ -372,8 +372,13 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
     const int tileY = tileIdx / f.widthTiles, tileX = tileIdx - tileY * f.widthTiles;   // (the kernel's one integer division)
     if (f.microMode != 0) {
         vis = f.visBuffer + (size_t)((tileY << CR_TILE_LOG2) + (lane >> 3)) * f.widthPixels + (tileX << CR_TILE_LOG2) + (lane & 7);
+#if CRB_FINE_STREAM & 1
+        v0 = __ldcs(vis);
+        v1 = __ldcs(vis + (size_t)4 * f.widthPixels);
+#else
         v0 = vis[0];
         v1 = vis[(size_t)4 * f.widthPixels];
+#endif
     }
     if (f.atomics->overflow != 0) return;
     if (f.microMode != 0) {
@@ -423,8 +428,13 @@ static __global__ void __launch_bounds__(CRB_FINE_WARPS * 32, CRB_FINE_WARPS_PER
         // Micro-triangle visibility (TriangleSetup.cuh microRaster): the (depth, entry + 1) minimum over the triangles that
         // setup rasterized itself (loaded at the top of the kernel).  It joins the tile state under the same rule as a
         // queued fragment, and the buffer gets its neutral value back for the next frame.
+#if CRB_FINE_STREAM & 1
+        if (v0 != ~0ull) __stcs(vis, ~0ull);
+        if (v1 != ~0ull) __stcs(vis + (size_t)4 * f.widthPixels, ~0ull);
+#else
         if (v0 != ~0ull) vis[0] = ~0ull;
         if (v1 != ~0ull) vis[(size_t)4 * f.widthPixels] = ~0ull;
+#endif
         if (v0 != ~0ull && (U32)(v0 >> 32) < depth[0]) { depth[0] = (U32)(v0 >> 32); winner[0] = (S32)(U32)v0 - 1; }
         if (v1 != ~0ull && (U32)(v1 >> 32) < depth[1]) { depth[1] = (U32)(v1 >> 32); winner[1] = (S32)(U32)v1 - 1; }
     }

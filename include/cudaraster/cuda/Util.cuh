@@ -38,10 +38,26 @@ __host__ __device__ __forceinline__ int msaaSampleX(int samplesLog2, int i) {
 #ifndef CRB_WIDE_ST
 #define CRB_WIDE_ST CRB_WIDE_LDST
 #endif
+#ifndef CRB_FINE_STREAM
+#define CRB_FINE_STREAM 3   // bit 0 = visibility buffer with streaming (evict-first) accesses, bit 1 = record gathers without L1 allocation: both are read once, the vertices they would displace from L1 are reused (C2 fine raster 34.9 -> 34.1 us)
+#endif
 __device__ __forceinline__ void ldg256(const uint4* p, uint4& a, uint4& b) {
+#if CRB_FINE_STREAM & 2
+    asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
         : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
         : "l"(__cvta_generic_to_global(p)));
+}
+__device__ __forceinline__ uint4 ldg128Record(const uint4* p) {
+#if CRB_FINE_STREAM & 2
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(__cvta_generic_to_global(p)));
+    return r;
+#else
+    return __ldg(p);
+#endif
 }
 __device__ __forceinline__ void stg256(uint4* p, const uint4& a, const uint4& b) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(__cvta_generic_to_global(p)), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
