@@ -51,7 +51,7 @@ def test_micro_raster_uses_fire_and_forget_reductions(sass):
 
 
 def test_wide_record_accesses(sass):
-    assert sum(_count(sass, "fineRaster", "LDG.E.ENL2.256").values()) > 0
+    assert sum(_count(sass, "fineRaster", "ENL2.256.CONSTANT").values()) > 0   # LDG.E[.NA].ENL2.256.CONSTANT (NA = no L1 allocation)
     st = _count(sass, "triangleSetupKernel", "STG.E.ENL2.256")
     assert sum(st.values()) > 0
     # ptxas 12.9 miscompiles st.global.v8.b32 inside non-inlined functions: the wide store must only exist on the inlined fast

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 lib = os.path.join(ROOT, "cudaraster-linux_b200", "libcrb200.so")
 WHAT = [("UBLKCP", "cp.async.bulk shared -> global (bulk-copy engine, TMA path)"),
-        ("LDG.E.ENL2.256", "256-bit global load (ld.global.nc.v8.b32)"),
+        ("ENL2.256.CONSTANT", "256-bit global load (ld.global.nc[.L1::no_allocate].v8.b32 -> LDG.E[.NA].ENL2.256.CONSTANT)"),
         ("STG.E.ENL2.256", "256-bit global store (st.global.v8.b32)"),
         ("REDG.E.MIN.64", "red.global.min.u64 (visibility-buffer write of the micro raster)"),
         ("UCGABAR_ARV", "cluster barrier arrive (cluster.sync of the DSMEM bin scan)"),
